@@ -1,0 +1,143 @@
+// ec.cuh — BN254 G1 / G2 group law for sm_100a in extended Jacobian ("XYZZ") coordinates.
+//
+// Replaces ark-ec's short_weierstrass::Projective arithmetic used inside the five
+// MSMs and the proof assembly of ark-groth16's create_proof_with_assignment
+// (reached from the reference at src/backend/snark.rs:364 and :442).  Group
+// elements are unique, so any correct law yields the same affine results; XYZZ is
+// chosen because the mixed addition that dominates bucket / table accumulation costs
+// 8M + 2S with no inversion.
+//
+// Affine points use (0, 0) for the point at infinity ((0,0) is on neither curve);
+// XYZZ points use zz == 0.  All special cases (infinity, P + P, P + (-P)) are
+// handled, because proving-key queries legitimately contain identity points and
+// repeated points (SURVEY.md §7 hard part 5).
+#pragma once
+#include "field.cuh"
+
+namespace lzkp {
+
+template <class F>
+struct Affine {
+    F x, y;
+    LZ_HD bool is_inf() const { return x.is_zero() && y.is_zero(); }
+    LZ_HD static Affine inf() { return Affine{F::zero(), F::zero()}; }
+    LZ_HD Affine neg() const { return Affine{x, y.neg()}; }
+};
+
+template <class F>
+struct XYZZ {
+    F x, y, zz, zzz;
+    LZ_HD bool is_inf() const { return zz.is_zero(); }
+    LZ_HD static XYZZ inf() { return XYZZ{F::one(), F::one(), F::zero(), F::zero()}; }
+    LZ_HD static XYZZ from_affine(const Affine<F> &p) {
+        if (p.is_inf()) return inf();
+        return XYZZ{p.x, p.y, F::one(), F::one()};
+    }
+    LZ_HD XYZZ neg() const { return XYZZ{x, y.neg(), zz, zzz}; }
+
+    // 2 * (affine p), p != inf   (mdbl-2008-s-1, a = 0)
+    LZ_HD static XYZZ dbl_affine(const Affine<F> &p) {
+        if (p.y.is_zero()) return inf();
+        F U = p.y.dbl(), V = U.sqr(), W = U * V, S = p.x * V;
+        F xx = p.x.sqr(), M = xx.dbl() + xx;
+        XYZZ r;
+        r.x = M.sqr() - S.dbl();
+        r.y = M * (S - r.x) - W * p.y;
+        r.zz = V;
+        r.zzz = W;
+        return r;
+    }
+    // *this = 2 * *this   (dbl-2008-s-1, a = 0): 6M + 3S
+    LZ_HD void dbl() {
+        if (is_inf()) return;
+        if (y.is_zero()) { *this = inf(); return; }
+        F U = y.dbl(), V = U.sqr(), W = U * V, S = x * V;
+        F xx = x.sqr(), M = xx.dbl() + xx;
+        F X3 = M.sqr() - S.dbl();
+        F Y3 = M * (S - X3) - W * y;
+        x = X3; y = Y3;
+        zz = V * zz;
+        zzz = W * zzz;
+    }
+    // *this += affine p   (madd-2008-s): 8M + 2S
+    LZ_HD void madd(const Affine<F> &p) {
+        if (p.is_inf()) return;
+        if (is_inf()) { *this = from_affine(p); return; }
+        F U2 = p.x * zz, S2 = p.y * zzz;
+        F Pp = U2 - x, R = S2 - y;
+        if (Pp.is_zero()) {
+            if (R.is_zero()) *this = dbl_affine(p);
+            else *this = inf();
+            return;
+        }
+        F PP = Pp.sqr(), PPP = Pp * PP, Q = x * PP;
+        F X3 = R.sqr() - PPP - Q.dbl();
+        F Y3 = R * (Q - X3) - y * PPP;
+        x = X3; y = Y3;
+        zz = zz * PP;
+        zzz = zzz * PPP;
+    }
+    // *this += q   (add-2008-s): 12M + 2S
+    LZ_HD void add(const XYZZ &q) {
+        if (q.is_inf()) return;
+        if (is_inf()) { *this = q; return; }
+        F U1 = x * q.zz, U2 = q.x * zz, S1 = y * q.zzz, S2 = q.y * zzz;
+        F Pp = U2 - U1, R = S2 - S1;
+        if (Pp.is_zero()) {
+            if (R.is_zero()) dbl();
+            else *this = inf();
+            return;
+        }
+        F PP = Pp.sqr(), PPP = Pp * PP, Q = U1 * PP;
+        F X3 = R.sqr() - PPP - Q.dbl();
+        F Y3 = R * (Q - X3) - S1 * PPP;
+        x = X3; y = Y3;
+        zz = zz * q.zz * PP;
+        zzz = zzz * q.zzz * PPP;
+    }
+    // x/zz, y/zzz with one inversion:  t = 1/(zz*zzz); 1/zz = t*zzz; 1/zzz = t*zz
+    LZ_HD Affine<F> to_affine() const {
+        if (is_inf()) return Affine<F>::inf();
+        F t = (zz * zzz).inverse();
+        return Affine<F>{x * (t * zzz), y * (t * zz)};
+    }
+};
+
+// k * p for a canonical 254-bit scalar (limbs little-endian), MSB-first double-and-add.
+template <class F>
+LZ_HD XYZZ<F> scalar_mul(const XYZZ<F> &p, const Fr &k_canonical) {
+    XYZZ<F> acc = XYZZ<F>::inf();
+    bool started = false;
+#pragma unroll 1
+    for (int i = 253; i >= 0; i--) {
+        if (started) acc.dbl();
+        if ((k_canonical.l[i >> 5] >> (i & 31)) & 1u) {
+            acc.add(p);
+            started = true;
+        }
+    }
+    return acc;
+}
+
+using G1Affine = Affine<Fq>;
+using G2Affine = Affine<Fq2>;
+using G1XYZZ = XYZZ<Fq>;
+using G2XYZZ = XYZZ<Fq2>;
+
+// y^2 == x^3 + b ?
+LZ_HD bool g1_on_curve(const G1Affine &p) {
+    if (p.is_inf()) return true;
+    Fq b3;
+#pragma unroll
+    for (int i = 0; i < 8; i++) b3.l[i] = FqParams::B3(i);
+    return p.y.sqr() == p.x.sqr() * p.x + b3;
+}
+LZ_HD bool g2_on_curve(const G2Affine &p) {
+    if (p.is_inf()) return true;
+    Fq2 b;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { b.c0.l[i] = FqParams::G2B_C0(i); b.c1.l[i] = FqParams::G2B_C1(i); }
+    return p.y.sqr() == p.x.sqr() * p.x + b;
+}
+
+}  // namespace lzkp

@@ -1,0 +1,23 @@
+// Host build of libzkp_b200/csrc/field.cuh (row primitives take their portable C++
+// bodies) so the Montgomery composition logic can be checked without a GPU.
+#include "../../libzkp_b200/csrc/field.cuh"
+#include <cstring>
+using namespace lzkp;
+template <class F> static void ld(F &f, const uint8_t *p) { std::memcpy(f.l, p, 32); }
+template <class F> static void st(uint8_t *p, const F &f) { std::memcpy(p, f.l, 32); }
+extern "C" {
+// op: 0 mul(raw Montgomery product), 1 add, 2 sub, 3 neg, 4 from_canonical, 5 to_canonical, 6 inverse, 7 sqr
+void fr_op(int op, const uint8_t *a, const uint8_t *b, uint8_t *o) {
+    Fr x, y, r; ld(x, a); ld(y, b);
+    switch (op) { case 0: r = x * y; break; case 1: r = x + y; break; case 2: r = x - y; break; case 3: r = x.neg(); break;
+        case 4: r = Fr::from_canonical(x); break; case 5: r = x.to_canonical(); break; case 6: r = x.inverse(); break; default: r = x.sqr(); }
+    st(o, r);
+}
+void fq_op(int op, const uint8_t *a, const uint8_t *b, uint8_t *o) {
+    Fq x, y, r; ld(x, a); ld(y, b);
+    switch (op) { case 0: r = x * y; break; case 1: r = x + y; break; case 2: r = x - y; break; case 3: r = x.neg(); break;
+        case 4: r = Fq::from_canonical(x); break; case 5: r = x.to_canonical(); break; case 6: r = x.inverse(); break; default: r = x.sqr(); }
+    st(o, r);
+}
+int fq_gt(const uint8_t *a, const uint8_t *b) { Fq x, y; ld(x, a); ld(y, b); return Fq::gt_canonical(x, y); }
+}
