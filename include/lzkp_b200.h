@@ -1,0 +1,127 @@
+/* lzkp_b200.h — C ABI of the B200-native Groth16/BN254 proving engine for libzkp.
+ *
+ * Drop-in boundary: these entry points are what a Rust `extern "C"`
+ * FFI crate inside libzkp binds in place of the calls it makes today into
+ * ark-groth16 / ark-serialize:
+ *
+ *   lzkp_pk_load            <- ProvingKey::<Bn254>::deserialize_uncompressed, src/backend/snark.rs:64
+ *                              (and the OnceLock fill at snark.rs:295-339: upload once, keep resident)
+ *   lzkp_circuit_load /     <- ConstraintSynthesizer::generate_constraints + cs.to_matrices(), done once per
+ *   lzkp_circuit_builtin       circuit instead of on every prove (snark.rs:263-290, 515-584)
+ *   lzkp_prove_batch        <- Groth16::<Bn254>::prove(&pk, circuit, rng) + proof.serialize_uncompressed,
+ *                              snark.rs:364,369-373 and :442,447-451; n_proofs = 1 is the single-proof drop-in
+ *   lzkp_prove_equality_batch / lzkp_prove_membership_batch
+ *                           <- the par_iter().map(process_batch_operation) of src/advanced/batch.rs:123-131,
+ *                              grouped per circuit, with the witness generated on the device
+ *   lzkp_witness_map        <- LibsnarkReduction::witness_map (inside prove)        [ark-groth16, un-vendored]
+ *   lzkp_msm_g1 / _g2       <- VariableBaseMSM::msm_bigint                         [ark-ec, un-vendored]
+ *   lzkp_ntt                <- Radix2EvaluationDomain::{fft,ifft}_in_place, coset  [ark-poly, un-vendored]
+ *   lzkp_commit_value_snark <- commit_value_snark, src/utils/commitment.rs:14-16
+ *
+ * Conventions
+ *   - Return 0 on success, a negative LZKP_E_* code on failure.  Nothing throws or aborts across
+ *     the ABI; lzkp_last_error() gives a thread-local message.  The Rust shim maps non-zero (or a
+ *     non-zero per-proof status) to `vec![]`, the reference's failure convention (snark.rs:345-371).
+ *   - All byte formats are ark-serialize's: field elements 32 B canonical little-endian;
+ *     G1 affine uncompressed 64 B, G2 128 B, flags in the top two bits of the last byte;
+ *     Proof<Bn254> = A(G1) || B(G2) || C(G1) = 256 B; Vec<T> = u64 LE length || items.
+ *   - The prover randomness r, s is an INPUT (the reference draws it from OsRng, snark.rs:363,441);
+ *     the caller supplies canonical scalars.
+ *   - The caller owns every buffer; the engine never frees caller memory.  Calls block until done.
+ *   - There is no CPU fallback: every entry point that computes fails with LZKP_E_NO_DEVICE when
+ *     no CUDA device is usable.
+ */
+#ifndef LZKP_B200_H
+#define LZKP_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LZKP_OK 0
+#define LZKP_E_INVALID (-1)    /* bad argument / malformed bytes */
+#define LZKP_E_NO_DEVICE (-2)  /* CUDA device missing or unusable */
+#define LZKP_E_CUDA (-3)       /* CUDA runtime error (see lzkp_last_error) */
+#define LZKP_E_STATE (-4)      /* call order (e.g. prove before circuit_load) */
+#define LZKP_E_NOMEM (-5)      /* device memory budget exceeded */
+#define LZKP_E_UNSUPPORTED (-6)
+
+#define LZKP_CIRCUIT_EQUALITY 0   /* param = MiMC rounds (110 = the reference's EqualityCircuit) */
+#define LZKP_CIRCUIT_MEMBERSHIP 1 /* param = set slots (64 = the reference's MAX_SET_SIZE)     */
+
+typedef struct lzkp_pk lzkp_pk;
+
+typedef struct lzkp_pk_options {
+    int window_bits;          /* fixed-base table window c in [8,16]; 0 = choose from the memory budget */
+    uint64_t table_budget_bytes; /* cap for the resident window tables; 0 = 60% of free device memory */
+    uint32_t max_chunk;       /* proofs per device pass; 0 = default (8192) */
+} lzkp_pk_options;
+
+/* Select the CUDA device(s) this process drives (one process per GPU: n_devices == 1). Idempotent. */
+int lzkp_init(const int *devices, int n_devices);
+int lzkp_shutdown(void);
+const char *lzkp_last_error(void);
+/* Number of engine kernels launched by this process so far (bench.py's gpu_launches). */
+uint64_t lzkp_kernel_launches(void);
+
+/* Parse an ark-serialize uncompressed ProvingKey<Bn254> (exactly the bytes snark.rs:97-101 writes),
+ * upload it, and build the resident fixed-base window tables.  validate != 0 adds the on-curve and
+ * subgroup checks deserialize_uncompressed performs. */
+int lzkp_pk_load(const uint8_t *pk_bytes, size_t len, int validate, lzkp_pk **out);
+int lzkp_pk_load_ex(const uint8_t *pk_bytes, size_t len, int validate, const lzkp_pk_options *opt, lzkp_pk **out);
+void lzkp_pk_free(lzkp_pk *pk);
+/* info[0..8) = n_vars, n_inst, n_wit, domain n, window bits c, windows W, table bytes, max_chunk */
+int lzkp_pk_info(const lzkp_pk *pk, uint64_t info[8]);
+
+/* R1CS matrices, once per circuit: CSR with m rows over z = instance || witness (column 0 = One);
+ * coefficients 32 B canonical LE. */
+int lzkp_circuit_load(lzkp_pk *pk, uint32_t m, uint32_t n_inst, uint32_t n_wit,
+                      const uint32_t *a_rowptr, const uint32_t *a_col, const uint8_t *a_val,
+                      const uint32_t *b_rowptr, const uint32_t *b_col, const uint8_t *b_val,
+                      const uint32_t *c_rowptr, const uint32_t *c_col, const uint8_t *c_val);
+/* The two libzkp circuits, synthesised natively (same rows/columns as generate_constraints). */
+int lzkp_circuit_builtin(lzkp_pk *pk, int kind, uint32_t param);
+/* Shape and CSR export of a builtin circuit without a pk (parity tests): shape = m, n_inst, n_wit,
+ * nnzA, nnzB, nnzC.  Pass NULL arrays to query the shape only. */
+int lzkp_builtin_circuit_csr(int kind, uint32_t param, uint64_t shape[6], uint32_t *rowptr[3], uint32_t *col[3],
+                             uint8_t *val[3]);
+
+/* n_proofs proofs from full assignments: z is n_proofs x n_vars x 32 B (z[0] = 1), r and s are
+ * n_proofs x 32 B, proofs_out n_proofs x 256 B, status n_proofs ints (0 = ok). */
+int lzkp_prove_batch(lzkp_pk *pk, size_t n_proofs, const uint8_t *z, const uint8_t *r, const uint8_t *s,
+                     uint8_t *proofs_out, int32_t *status);
+/* Equality batch (prove_equality_zk x n): a, b u64; commitments n x 32 B or NULL (then MiMC5(a) is
+ * computed on the device and, if commitments_out != NULL, returned).  status 1 = a != b (snark.rs:344). */
+int lzkp_prove_equality_batch(lzkp_pk *pk, size_t n_proofs, const uint64_t *a, const uint64_t *b,
+                              const uint8_t *commitments, const uint8_t *r, const uint8_t *s, uint8_t *proofs_out,
+                              uint8_t *commitments_out, int32_t *status);
+/* Membership batch (prove_membership_zk x n): sets is n x set_stride u64, set_len[i] entries used.
+ * status 2 = empty / oversized set or value not in set (snark.rs:406,415-418). */
+int lzkp_prove_membership_batch(lzkp_pk *pk, size_t n_proofs, const uint64_t *value, const uint64_t *sets,
+                                const uint32_t *set_len, uint32_t set_stride, const uint8_t *commitments,
+                                const uint8_t *r, const uint8_t *s, uint8_t *proofs_out, uint8_t *commitments_out,
+                                int32_t *status);
+/* Same as lzkp_prove_equality_batch with every buffer already in device memory (a, b: u64[n];
+ * r, s: n x 32 B; proofs: n x 256 B; status: int32[n]) on CUDA stream `stream` (cudaStream_t or NULL).
+ * Asynchronous: returns after enqueueing. */
+int lzkp_prove_equality_batch_device(lzkp_pk *pk, size_t n_proofs, const void *d_a, const void *d_b, const void *d_r,
+                                     const void *d_s, void *d_proofs, void *d_status, void *stream);
+
+/* a3-a7 only: h_out is n_proofs x n x 32 B canonical. */
+int lzkp_witness_map(lzkp_pk *pk, size_t n_proofs, const uint8_t *z, uint8_t *h_out);
+
+/* Variable-base MSM over arbitrary bases (ark affine uncompressed) and canonical scalars. */
+int lzkp_msm_g1(const uint8_t *bases_affine, const uint8_t *scalars, size_t n, uint8_t *out_affine);
+int lzkp_msm_g2(const uint8_t *bases_affine, const uint8_t *scalars, size_t n, uint8_t *out_affine);
+/* In-place radix-2 (i)NTT over Fr on 2^log_n canonical elements, optionally on the coset 5*H. */
+int lzkp_ntt(uint8_t *data, uint32_t log_n, int inverse, int coset);
+
+/* MiMC-5 commitment of a u64 (commit_value_snark), 32 B canonical LE.  Host arithmetic, no device. */
+int lzkp_commit_value_snark(uint64_t value, uint8_t out[32]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -35,8 +35,8 @@ struct XYZZ {
     }
     LZ_HD XYZZ neg() const { return XYZZ{x, y.neg(), zz, zzz}; }
 
-    // 2 * (affine p), p != inf   (mdbl-2008-s-1, a = 0)
-    LZ_HD static XYZZ dbl_affine(const Affine<F> &p) {
+    // 2 * (affine p), p != inf   (mdbl-2008-s-1, a = 0).  Rare branch of madd: not inlined.
+    LZ_COLD static XYZZ dbl_affine(const Affine<F> &p) {
         if (p.y.is_zero()) return inf();
         F U = p.y.dbl(), V = U.sqr(), W = U * V, S = p.x * V;
         F xx = p.x.sqr(), M = xx.dbl() + xx;
@@ -59,6 +59,9 @@ struct XYZZ {
         zz = V * zz;
         zzz = W * zzz;
     }
+    LZ_COLD void dbl_cold() { dbl(); }
+    LZ_COLD void add_cold(const XYZZ &q) { add(q); }
+    LZ_COLD void madd_cold(const Affine<F> &p) { madd(p); }
     // *this += affine p   (madd-2008-s): 8M + 2S
     LZ_HD void madd(const Affine<F> &p) {
         if (p.is_inf()) return;
@@ -84,7 +87,7 @@ struct XYZZ {
         F U1 = x * q.zz, U2 = q.x * zz, S1 = y * q.zzz, S2 = q.y * zzz;
         F Pp = U2 - U1, R = S2 - S1;
         if (Pp.is_zero()) {
-            if (R.is_zero()) dbl();
+            if (R.is_zero()) dbl_cold();
             else *this = inf();
             return;
         }
@@ -96,7 +99,7 @@ struct XYZZ {
         zzz = zzz * q.zzz * PPP;
     }
     // x/zz, y/zzz with one inversion:  t = 1/(zz*zzz); 1/zz = t*zzz; 1/zzz = t*zz
-    LZ_HD Affine<F> to_affine() const {
+    LZ_COLD Affine<F> to_affine() const {
         if (is_inf()) return Affine<F>::inf();
         F t = (zz * zzz).inverse();
         return Affine<F>{x * (t * zzz), y * (t * zz)};
@@ -105,14 +108,14 @@ struct XYZZ {
 
 // k * p for a canonical 254-bit scalar (limbs little-endian), MSB-first double-and-add.
 template <class F>
-LZ_HD XYZZ<F> scalar_mul(const XYZZ<F> &p, const Fr &k_canonical) {
+LZ_COLD XYZZ<F> scalar_mul(const XYZZ<F> &p, const Fr &k_canonical) {
     XYZZ<F> acc = XYZZ<F>::inf();
     bool started = false;
 #pragma unroll 1
     for (int i = 253; i >= 0; i--) {
-        if (started) acc.dbl();
+        if (started) acc.dbl_cold();
         if ((k_canonical.l[i >> 5] >> (i & 31)) & 1u) {
-            acc.add(p);
+            acc.add_cold(p);
             started = true;
         }
     }
@@ -125,14 +128,14 @@ using G1XYZZ = XYZZ<Fq>;
 using G2XYZZ = XYZZ<Fq2>;
 
 // y^2 == x^3 + b ?
-LZ_HD bool g1_on_curve(const G1Affine &p) {
+static LZ_COLD bool g1_on_curve(const G1Affine &p) {
     if (p.is_inf()) return true;
     Fq b3;
 #pragma unroll
     for (int i = 0; i < 8; i++) b3.l[i] = FqParams::B3(i);
     return p.y.sqr() == p.x.sqr() * p.x + b3;
 }
-LZ_HD bool g2_on_curve(const G2Affine &p) {
+static LZ_COLD bool g2_on_curve(const G2Affine &p) {
     if (p.is_inf()) return true;
     Fq2 b;
 #pragma unroll

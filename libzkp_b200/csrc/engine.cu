@@ -1,0 +1,726 @@
+// engine.cu — host side of the engine and the C ABI of include/lzkp_b200.h.
+//
+// One process drives one GPU (torchrun launches one rank per device); the proving key,
+// its fixed-base window tables, the R1CS matrices and the NTT tables stay resident in
+// HBM from lzkp_pk_load / lzkp_circuit_load until lzkp_pk_free (the reference keeps the
+// same objects in process-wide OnceLocks, src/backend/snark.rs:295-339).
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.h"
+#include "host_util.h"
+#include "kernels_prove.cuh"
+#include "tables.h"
+#include "large.h"
+
+using namespace lzkp;
+using namespace lzkp::eng;
+
+// ------------------------------------------------------------------------ plumbing
+static thread_local std::string g_err;
+static std::mutex g_mu;
+static int g_device = -1;
+static bool g_mimc_uploaded = false;
+
+namespace lzkp {
+namespace eng {
+std::atomic<uint64_t> g_launches{0};
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+int DBuf::alloc(size_t n) {
+    release();
+    if (n == 0) n = 16;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e != cudaSuccess) {
+        p = nullptr;
+        cudaGetLastError();
+        return fail(LZKP_E_NOMEM, "cudaMalloc(" + std::to_string(n) + "): " + cudaGetErrorString(e));
+    }
+    bytes = n;
+    return LZKP_OK;
+}
+void DBuf::release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+}
+int ensure_device() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_device < 0) {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n == 0) {
+            cudaGetLastError();
+            return fail(LZKP_E_NO_DEVICE, "no CUDA device: this engine has no CPU fallback");
+        }
+        int dev = 0;
+        if (const char *lr = getenv("LOCAL_RANK")) dev = atoi(lr) % n;
+        g_device = dev;
+    }
+    CUDA_TRY(cudaSetDevice(g_device));
+    if (!g_mimc_uploaded) {
+        std::vector<Fr> c(110);
+        for (uint32_t i = 0; i < 110; i++) c[i] = host::mimc_constant(i);
+        CUDA_TRY(cudaMemcpyToSymbol(c_mimc, c.data(), sizeof(Fr) * 110));
+        g_mimc_uploaded = true;
+    }
+    return LZKP_OK;
+}
+}  // namespace eng
+}  // namespace lzkp
+
+
+// ------------------------------------------------------------------------ pk object
+struct MsmPlan {                 // one curve
+    DBuf table;                  // Affine<F>[rows * W * N]
+    DBuf unit_dig, unit_tbl;     // uint32[n_units]
+    DBuf items[3];               // uint2[n_items[v]] for the three granularities
+    DBuf msm_items[3];           // uint2[n_msm]: item range of each MSM
+    uint32_t n_items[3] = {0, 0, 0};
+    uint32_t n_units = 0, n_rows = 0, n_msm = 0;
+    std::vector<uint32_t> msm_unit_begin;   // host: first unit of each MSM (+ end)
+};
+static const uint32_t kUnitsPerItem[3] = {32, 128, 512};
+
+struct lzkp_pk {
+    std::mutex mu;
+    uint32_t n_vars = 0, n_inst = 0, n_wit = 0, n = 0, log_n = 0, m = 0;
+    bool has_circuit = false;
+    int kind = -1;
+    uint32_t kind_param = 0;
+    int c = 16;
+    uint32_t W = 16, N = 32768;
+    uint64_t table_bytes = 0;
+    uint32_t max_chunk = 8192;
+    uint32_t n_dig_rows = 0, nz = 0;
+    MsmPlan g1, g2;
+    ProofConsts consts;
+    // circuit
+    DBuf csr_rowptr[3], csr_col[3], csr_val[3];
+    CsrDev csr[3];
+    DBuf tw_fwd, tw_inv, coset_br, uncoset_br;
+    NttTables ntt;
+    // workspace (sized for ws_chunk proofs)
+    uint32_t ws_chunk = 0;
+    DBuf ws_z, ws_abc, ws_h, ws_dig, ws_r, ws_s, ws_rs, ws_part1, ws_part2, ws_res1, ws_res2, ws_proofs, ws_status,
+        ws_a, ws_b, ws_commit, ws_sets, ws_setlen;
+    cudaStream_t stream = nullptr;
+    ~lzkp_pk() {
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+// ------------------------------------------------------------------------ lookup plans
+struct BaseRef { uint32_t dig_row, tbl_row; };
+static int finish_plan(MsmPlan &pl, const std::vector<std::vector<BaseRef>> &msms, uint32_t W) {
+    std::vector<uint32_t> ud, ut;
+    pl.msm_unit_begin.clear();
+    for (auto &ms : msms) {
+        pl.msm_unit_begin.push_back((uint32_t)ud.size());
+        for (auto &b : ms)
+            for (uint32_t w = 0; w < W; w++) {
+                ud.push_back(b.dig_row * W + w);
+                ut.push_back(b.tbl_row * W + w);
+            }
+    }
+    pl.msm_unit_begin.push_back((uint32_t)ud.size());
+    pl.n_units = (uint32_t)ud.size();
+    pl.n_msm = (uint32_t)msms.size();
+    TRY(upload(pl.unit_dig, ud));
+    TRY(upload(pl.unit_tbl, ut));
+    for (int v = 0; v < 3; v++) {
+        std::vector<uint2> items, mi;
+        for (uint32_t q = 0; q < pl.n_msm; q++) {
+            uint32_t first = (uint32_t)items.size();
+            for (uint32_t u = pl.msm_unit_begin[q]; u < pl.msm_unit_begin[q + 1]; u += kUnitsPerItem[v])
+                items.push_back(make_uint2(u, std::min(u + kUnitsPerItem[v], pl.msm_unit_begin[q + 1])));
+            mi.push_back(make_uint2(first, (uint32_t)items.size()));
+        }
+        pl.n_items[v] = (uint32_t)items.size();
+        TRY(upload(pl.items[v], items));
+        TRY(upload(pl.msm_items[v], mi));
+    }
+    return LZKP_OK;
+}
+
+// ------------------------------------------------------------------------ pk load
+namespace {
+struct Reader {
+    const uint8_t *p, *end;
+    bool take(size_t n, const uint8_t **out) {
+        if ((size_t)(end - p) < n) return false;
+        *out = p;
+        p += n;
+        return true;
+    }
+    bool g1(host::G1Canon &o) { const uint8_t *b; return take(64, &b) && host::read_g1(b, o); }
+    bool g2(host::G2Canon &o) { const uint8_t *b; return take(128, &b) && host::read_g2(b, o); }
+    bool vec_g1(std::vector<host::G1Canon> &v) {
+        const uint8_t *b;
+        if (!take(8, &b)) return false;
+        uint64_t len;
+        memcpy(&len, b, 8);
+        if (len > (uint64_t)(end - p) / 64) return false;
+        v.resize(len);
+        for (auto &x : v) if (!g1(x)) return false;
+        return true;
+    }
+    bool vec_g2(std::vector<host::G2Canon> &v) {
+        const uint8_t *b;
+        if (!take(8, &b)) return false;
+        uint64_t len;
+        memcpy(&len, b, 8);
+        if (len > (uint64_t)(end - p) / 128) return false;
+        v.resize(len);
+        for (auto &x : v) if (!g2(x)) return false;
+        return true;
+    }
+};
+host::G1Canon neg_canon(const host::G1Canon &p) {
+    host::G1Canon r = p;
+    if (!host::is_inf(p)) {
+        Fq m = Fq::modulus();
+        sub8(r.y.l, m.l, p.y.l);
+    }
+    return r;
+}
+}  // namespace
+
+static int pk_load_impl(const uint8_t *bytes, size_t len, int validate, const lzkp_pk_options *opt, lzkp_pk *pk) {
+    static_assert(sizeof(host::G1Canon) == sizeof(G1Affine) && sizeof(host::G2Canon) == sizeof(G2Affine), "layout");
+    Reader rd{bytes, bytes + len};
+    host::G1Canon alpha_g1, beta_g1, delta_g1;
+    host::G2Canon beta_g2, gamma_g2, delta_g2;
+    std::vector<host::G1Canon> gamma_abc, a_q, b1_q, h_q, l_q;
+    std::vector<host::G2Canon> b2_q;
+    bool ok = rd.g1(alpha_g1) && rd.g2(beta_g2) && rd.g2(gamma_g2) && rd.g2(delta_g2) && rd.vec_g1(gamma_abc) &&
+              rd.g1(beta_g1) && rd.g1(delta_g1) && rd.vec_g1(a_q) && rd.vec_g1(b1_q) && rd.vec_g2(b2_q) &&
+              rd.vec_g1(h_q) && rd.vec_g1(l_q);
+    if (!ok || rd.p != rd.end) return fail(LZKP_E_INVALID, "proving key: malformed ark-serialize bytes");
+    const uint32_t nv = (uint32_t)a_q.size();
+    if (nv < 2 || b1_q.size() != nv || b2_q.size() != nv || l_q.size() >= nv || gamma_abc.size() + l_q.size() != nv)
+        return fail(LZKP_E_INVALID, "proving key: inconsistent query lengths");
+    const uint32_t n = (uint32_t)h_q.size() + 1;
+    if (n < 2 || (n & (n - 1))) return fail(LZKP_E_INVALID, "proving key: h_query length + 1 is not a power of two");
+    pk->n_vars = nv;
+    pk->n_wit = (uint32_t)l_q.size();
+    pk->n_inst = nv - pk->n_wit;
+    pk->n = n;
+    pk->log_n = 0;
+    while ((1u << pk->log_n) < n) pk->log_n++;
+    pk->nz = nv - 1;
+    pk->n_dig_rows = pk->nz + 3 + (n - 1);
+    const uint32_t ROW_R = pk->nz, ROW_S = pk->nz + 1, ROW_RS = pk->nz + 2, ROW_H = pk->nz + 3;
+
+    // --- base lists (identity points are dropped: they contribute nothing to any MSM) ---
+    std::vector<host::G1Canon> rows1;
+    std::vector<host::G2Canon> rows2;
+    std::vector<std::vector<BaseRef>> msm1(4), msm2(1);
+    auto add1 = [&](const host::G1Canon &p) { rows1.push_back(p); return (uint32_t)rows1.size() - 1; };
+    for (uint32_t j = 1; j < nv; j++) if (!host::is_inf(a_q[j])) msm1[0].push_back({j - 1, add1(a_q[j])});
+    for (uint32_t j = 1; j < nv; j++) if (!host::is_inf(b1_q[j])) msm1[1].push_back({j - 1, add1(b1_q[j])});
+    for (uint32_t j = 0; j < pk->n_wit; j++) if (!host::is_inf(l_q[j])) msm1[2].push_back({pk->n_inst + j - 1, add1(l_q[j])});
+    for (uint32_t i = 0; i + 1 < n; i++) if (!host::is_inf(h_q[i])) msm1[3].push_back({ROW_H + i, add1(h_q[i])});
+    if (!host::is_inf(delta_g1)) {
+        uint32_t rd1 = add1(delta_g1), rnd1 = add1(neg_canon(delta_g1));
+        msm1[0].push_back({ROW_R, rd1});      // A  += r * delta_g1
+        msm1[1].push_back({ROW_S, rd1});      // B1 += s * delta_g1
+        msm1[2].push_back({ROW_RS, rnd1});    // C  -= rs * delta_g1 (folded into the L sum)
+    }
+    for (uint32_t j = 1; j < nv; j++)
+        if (!host::is_inf(b2_q[j])) { rows2.push_back(b2_q[j]); msm2[0].push_back({j - 1, (uint32_t)rows2.size() - 1}); }
+    if (!host::is_inf(delta_g2)) { rows2.push_back(delta_g2); msm2[0].push_back({ROW_S, (uint32_t)rows2.size() - 1}); }
+    pk->g1.n_rows = (uint32_t)rows1.size();
+    pk->g2.n_rows = (uint32_t)rows2.size();
+
+    // --- window size from the memory budget ---
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    uint64_t budget = opt && opt->table_budget_bytes ? opt->table_budget_bytes : (uint64_t)(free_b * 0.6);
+    int c = opt && opt->window_bits ? opt->window_bits : 0;
+    if (const char *e = getenv("LZKP_WINDOW_BITS")) if (!c) c = atoi(e);
+    auto bytes_for = [&](int cc) {
+        uint64_t W = (256 + cc - 1) / cc, N = 1ull << (cc - 1);
+        return (rows1.size() * 64ull + rows2.size() * 128ull) * W * N;
+    };
+    if (c == 0) {
+        c = 16;
+        while (c > 8 && bytes_for(c) > budget) c--;
+    }
+    if (c < 8 || c > 16) return fail(LZKP_E_INVALID, "window_bits must be in [8,16]");
+    if (bytes_for(c) > free_b) return fail(LZKP_E_NOMEM, "window tables do not fit in device memory");
+    pk->c = c;
+    pk->W = (256 + c - 1) / c;
+    pk->N = 1u << (c - 1);
+    pk->table_bytes = bytes_for(c);
+    pk->max_chunk = opt && opt->max_chunk ? opt->max_chunk : 8192;
+    if (pk->max_chunk > 32768) pk->max_chunk = 32768;
+
+    CUDA_TRY(cudaStreamCreateWithFlags(&pk->stream, cudaStreamNonBlocking));
+    cudaStream_t st = pk->stream;
+
+    // --- upload points, to Montgomery, optional validation ---
+    std::vector<host::G1Canon> misc1 = {alpha_g1, beta_g1, delta_g1, a_q[0], b1_q[0]};
+    std::vector<host::G2Canon> misc2 = {beta_g2, gamma_g2, delta_g2, b2_q[0]};
+    DBuf d_rows1, d_rows2, d_misc1, d_misc2, d_out1, d_out2;
+    TRY(upload(d_rows1, rows1)); TRY(upload(d_rows2, rows2)); TRY(upload(d_misc1, misc1)); TRY(upload(d_misc2, misc2));
+    auto to_mont = [&](DBuf &b, size_t n_fq) {
+        if (n_fq) LAUNCH(k_fq_to_mont, (unsigned)((n_fq + 127) / 128), 128, 0, st, b.as<Fq>(), n_fq);
+    };
+    to_mont(d_rows1, rows1.size() * 2); to_mont(d_rows2, rows2.size() * 4);
+    to_mont(d_misc1, misc1.size() * 2); to_mont(d_misc2, misc2.size() * 4);
+    if (validate) {
+        // everything deserialize_uncompressed would check: all vk and query points
+        std::vector<host::G1Canon> all1 = gamma_abc;
+        std::vector<host::G2Canon> all2;
+        DBuf d_all1, d_bad;
+        TRY(upload(d_all1, all1));
+        to_mont(d_all1, all1.size() * 2);
+        TRY(d_bad.alloc(sizeof(int)));
+        CUDA_TRY(cudaMemsetAsync(d_bad.p, 0, sizeof(int), st));
+        auto chk1 = [&](DBuf &b, size_t cnt) {
+            if (cnt) LAUNCH(k_check_g1, (unsigned)((cnt + 63) / 64), 64, 0, st, b.as<G1Affine>(), (uint32_t)cnt, d_bad.as<int>());
+        };
+        auto chk2 = [&](DBuf &b, size_t cnt) {
+            if (cnt) LAUNCH(k_check_g2, (unsigned)((cnt + 63) / 64), 64, 0, st, b.as<G2Affine>(), (uint32_t)cnt, d_bad.as<int>());
+        };
+        chk1(d_rows1, rows1.size()); chk1(d_misc1, misc1.size()); chk1(d_all1, all1.size());
+        chk2(d_rows2, rows2.size()); chk2(d_misc2, misc2.size());
+        int bad = 0;
+        CUDA_TRY(cudaMemcpyAsync(&bad, d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (bad) return fail(LZKP_E_INVALID, "proving key: " + std::to_string(bad) + " point(s) off-curve or outside the subgroup");
+    }
+    // --- constant terms of calculate_coeff: vk_param + query[0] ---
+    TRY(d_out1.alloc(2 * sizeof(G1Affine))); TRY(d_out2.alloc(sizeof(G2Affine)));
+    LAUNCH((k_affine_add<Fq>), 1, 1, 0, st, d_misc1.as<G1Affine>() + 0, d_misc1.as<G1Affine>() + 3, d_out1.as<G1Affine>() + 0, 0);
+    LAUNCH((k_affine_add<Fq>), 1, 1, 0, st, d_misc1.as<G1Affine>() + 1, d_misc1.as<G1Affine>() + 4, d_out1.as<G1Affine>() + 1, 0);
+    LAUNCH((k_affine_add<Fq2>), 1, 1, 0, st, d_misc2.as<G2Affine>() + 0, d_misc2.as<G2Affine>() + 3, d_out2.as<G2Affine>(), 0);
+    G1Affine c1[2];
+    G2Affine c2;
+    CUDA_TRY(cudaMemcpyAsync(c1, d_out1.p, sizeof(c1), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(&c2, d_out2.p, sizeof(c2), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    pk->consts.a0 = c1[0]; pk->consts.b0 = c1[1]; pk->consts.b2 = c2;
+
+    // --- resident window tables + lookup plans ---
+    TRY(pk->g1.table.alloc((size_t)rows1.size() * pk->W * pk->N * sizeof(G1Affine)));
+    TRY(pk->g2.table.alloc((size_t)rows2.size() * pk->W * pk->N * sizeof(G2Affine)));
+    if (!rows1.empty())
+        TRY(build_table_g1(d_rows1.p, (uint32_t)rows1.size(), c, pk->W, pk->N, pk->g1.table.p, st));
+    if (!rows2.empty())
+        TRY(build_table_g2(d_rows2.p, (uint32_t)rows2.size(), c, pk->W, pk->N, pk->g2.table.p, st));
+    TRY(finish_plan(pk->g1, msm1, pk->W));
+    TRY(finish_plan(pk->g2, msm2, pk->W));
+    CUDA_TRY(cudaGetLastError());
+    return LZKP_OK;
+}
+
+// ------------------------------------------------------------------------ circuit load
+static int circuit_install(lzkp_pk *pk, uint32_t m, uint32_t n_inst, uint32_t n_wit, const uint32_t *const rowptr[3],
+                           const uint32_t *const col[3], const uint8_t *const val[3]) {
+    if (n_inst != pk->n_inst || n_wit != pk->n_wit) return fail(LZKP_E_INVALID, "circuit shape does not match the proving key");
+    uint64_t need = (uint64_t)m + n_inst;
+    uint32_t n = 1;
+    while (n < need) n <<= 1;
+    if (n != pk->n) return fail(LZKP_E_INVALID, "circuit domain size does not match the proving key's h_query");
+    if (pk->log_n > 12) return fail(LZKP_E_UNSUPPORTED, "batched witness map supports domains up to 2^12");
+    cudaStream_t st = pk->stream;
+    for (int k = 0; k < 3; k++) {
+        uint32_t nnz = rowptr[k][m];
+        for (uint32_t i = 0; i < nnz; i++) if (col[k][i] >= pk->n_vars) return fail(LZKP_E_INVALID, "matrix column out of range");
+        TRY(pk->csr_rowptr[k].alloc(sizeof(uint32_t) * (m + 1)));
+        TRY(pk->csr_col[k].alloc(sizeof(uint32_t) * nnz));
+        TRY(pk->csr_val[k].alloc(sizeof(Fr) * (size_t)nnz));
+        CUDA_TRY(cudaMemcpy(pk->csr_rowptr[k].p, rowptr[k], sizeof(uint32_t) * (m + 1), cudaMemcpyHostToDevice));
+        if (nnz) {
+            CUDA_TRY(cudaMemcpy(pk->csr_col[k].p, col[k], sizeof(uint32_t) * nnz, cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMemcpy(pk->csr_val[k].p, val[k], 32 * (size_t)nnz, cudaMemcpyHostToDevice));
+            LAUNCH(k_to_r2_form, (nnz + 127) / 128, 128, 0, st, pk->csr_val[k].as<Fr>(), nnz);
+        }
+        pk->csr[k] = CsrDev{pk->csr_rowptr[k].as<uint32_t>(), pk->csr_col[k].as<uint32_t>(), pk->csr_val[k].as<Fr>()};
+    }
+    pk->m = m;
+    // NTT tables: w = ROOT28^(2^(28-log n)); host arithmetic for the handful of scalars
+    Fr w, wi, g, gi;
+    for (int i = 0; i < 8; i++) { w.l[i] = FrParams::ROOT28(i); wi.l[i] = FrParams::ROOT28_INV(i); g.l[i] = FrParams::GEN(i); gi.l[i] = FrParams::GEN_INV(i); }
+    for (uint32_t i = pk->log_n; i < 28; i++) { w = w.sqr(); wi = wi.sqr(); }
+    Fr ninv = host::fr_from_u64(n).inverse();
+    Fr gn = g;
+    for (uint32_t i = 0; i < pk->log_n; i++) gn = gn.sqr();
+    Fr zinv = (gn - Fr::one()).inverse();
+    TRY(pk->tw_fwd.alloc(sizeof(Fr) * (n / 2))); TRY(pk->tw_inv.alloc(sizeof(Fr) * (n / 2)));
+    TRY(pk->coset_br.alloc(sizeof(Fr) * n)); TRY(pk->uncoset_br.alloc(sizeof(Fr) * n));
+    LAUNCH(k_pow_table, (n / 2 + 127) / 128, 128, 0, st, pk->tw_fwd.as<Fr>(), w, Fr::one(), n / 2, 0u);
+    LAUNCH(k_pow_table, (n / 2 + 127) / 128, 128, 0, st, pk->tw_inv.as<Fr>(), wi, Fr::one(), n / 2, 0u);
+    LAUNCH(k_pow_table, (n + 127) / 128, 128, 0, st, pk->coset_br.as<Fr>(), g, ninv, n, pk->log_n);
+    LAUNCH(k_pow_table, (n + 127) / 128, 128, 0, st, pk->uncoset_br.as<Fr>(), gi, ninv.to_canonical(), n, pk->log_n);
+    pk->ntt = NttTables{pk->tw_fwd.as<Fr>(), pk->tw_inv.as<Fr>(), pk->coset_br.as<Fr>(), pk->uncoset_br.as<Fr>(), nullptr, ninv, zinv};
+    size_t smem = (size_t)32 * n;
+    if (smem > 48 * 1024) {
+        CUDA_TRY(cudaFuncSetAttribute(k_ntt_icoset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_ntt_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
+    pk->has_circuit = true;
+    return LZKP_OK;
+}
+
+// ------------------------------------------------------------------------ proving pipeline
+static inline int item_variant(uint32_t P) { return P >= 2048 ? 2 : (P >= 256 ? 1 : 0); }
+static int ensure_workspace(lzkp_pk *pk, uint32_t P) {
+    if (P <= pk->ws_chunk) return LZKP_OK;
+    size_t part1 = 0, part2 = 0;       // worst case over the batch sizes <= P
+    for (uint32_t q : {1u, 256u, 2048u}) {
+        if (q > P) break;
+        uint32_t pp = q == 1u ? std::min(P, 255u) : (q == 256u ? std::min(P, 2047u) : P);
+        part1 = std::max(part1, (size_t)pk->g1.n_items[item_variant(pp)] * pp);
+        part2 = std::max(part2, (size_t)pk->g2.n_items[item_variant(pp)] * pp);
+    }
+    const size_t nv = pk->n_vars, n = pk->n;
+    TRY(pk->ws_z.ensure(P * nv * 32));
+    TRY(pk->ws_abc.ensure(3 * P * n * 32));
+    TRY(pk->ws_h.ensure(P * n * 32));
+    TRY(pk->ws_dig.ensure((size_t)pk->n_dig_rows * pk->W * P * sizeof(int16_t)));
+    TRY(pk->ws_r.ensure(P * 32)); TRY(pk->ws_s.ensure(P * 32)); TRY(pk->ws_rs.ensure(P * 32));
+    TRY(pk->ws_part1.ensure(part1 * sizeof(G1XYZZ)));
+    TRY(pk->ws_part2.ensure(part2 * sizeof(G2XYZZ)));
+    TRY(pk->ws_res1.ensure((size_t)4 * P * sizeof(G1XYZZ)));
+    TRY(pk->ws_res2.ensure((size_t)P * sizeof(G2XYZZ)));
+    TRY(pk->ws_proofs.ensure((size_t)P * 256));
+    TRY(pk->ws_status.ensure((size_t)P * sizeof(int32_t)));
+    TRY(pk->ws_a.ensure(P * 8)); TRY(pk->ws_b.ensure(P * 8)); TRY(pk->ws_commit.ensure(P * 32));
+    pk->ws_chunk = P;
+    return LZKP_OK;
+}
+
+// Witness map on P assignments already in ws_z (canonical): fills ws_h (canonical).
+static int run_witness_map(lzkp_pk *pk, uint32_t P, cudaStream_t st) {
+    const uint32_t n = pk->n, threads = std::max(32u, std::min(n / 2, 512u));
+    const size_t smem = (size_t)32 * n;
+    LAUNCH(k_spmv_abc, dim3((n + 127) / 128, P), 128, 0, st, pk->csr[0], pk->csr[1], pk->csr[2], pk->ws_z.as<Fr>(),
+           pk->ws_abc.as<Fr>(), P, pk->n_vars, pk->m, pk->n_inst, n);
+    LAUNCH(k_ntt_icoset, dim3(P, 3), threads, smem, st, pk->ws_abc.as<Fr>(), pk->ntt, P, pk->log_n);
+    LAUNCH(k_ntt_final, P, threads, smem, st, pk->ws_abc.as<Fr>(), pk->ws_h.as<Fr>(), pk->ntt, P, pk->log_n);
+    return LZKP_OK;
+}
+
+// From ws_z, r, s (device, canonical) to proofs (device).  status must be initialised by the caller.
+static int run_prove(lzkp_pk *pk, uint32_t P, const Fr *d_r, const Fr *d_s, uint8_t *d_proofs, int32_t *d_status,
+                     cudaStream_t st) {
+    TRY(run_witness_map(pk, P, st));
+    const uint32_t c = pk->c, W = pk->W, gx = (P + 127) / 128;
+    int16_t *dig = pk->ws_dig.as<int16_t>();
+    LAUNCH(k_fr_mul_canonical, gx, 128, 0, st, d_r, d_s, pk->ws_rs.as<Fr>(), P);
+    LAUNCH(k_digits, dim3(gx, pk->nz), 128, 0, st, pk->ws_z.as<Fr>(), pk->n_vars, 1u, dig, 0u, P, c, W, d_status);
+    LAUNCH(k_digits, dim3(gx, 1), 128, 0, st, d_r, 1u, 0u, dig, pk->nz, P, c, W, d_status);
+    LAUNCH(k_digits, dim3(gx, 1), 128, 0, st, d_s, 1u, 0u, dig, pk->nz + 1, P, c, W, d_status);
+    LAUNCH(k_digits, dim3(gx, 1), 128, 0, st, pk->ws_rs.as<Fr>(), 1u, 0u, dig, pk->nz + 2, P, c, W, d_status);
+    LAUNCH(k_digits, dim3(gx, pk->n - 1), 128, 0, st, pk->ws_h.as<Fr>(), pk->n, 0u, dig, pk->nz + 3, P, c, W, d_status);
+    // item granularity: enough blocks to fill 148 SMs even for small batches
+    int v = item_variant(P);
+    auto args = [&](MsmPlan &pl, void *partial, void *out) {
+        return BatchMsmArgs{pl.table.p, pk->N, pl.unit_dig.as<uint32_t>(), pl.unit_tbl.as<uint32_t>(), pl.items[v].p,
+                            pl.n_items[v], pl.msm_items[v].p, pl.n_msm, dig, P, partial, out};
+    };
+    batch_msm_g1(args(pk->g1, pk->ws_part1.p, pk->ws_res1.p), st);
+    batch_msm_g2(args(pk->g2, pk->ws_part2.p, pk->ws_res2.p), st);
+    LAUNCH(k_assemble, (P + 63) / 64, 64, 0, st, pk->ws_res1.as<G1XYZZ>(), pk->ws_res2.as<G2XYZZ>(), pk->consts, d_r, d_s,
+           P, d_proofs);
+    return LZKP_OK;
+}
+
+static void blank_failed(size_t n, const int32_t *status, uint8_t *proofs) {
+    for (size_t i = 0; i < n; i++)
+        if (status[i]) memset(proofs + 256 * i, 0, 256);
+}
+
+// ------------------------------------------------------------------------ stand-alone small NTT
+// n <= 4096: one CTA, whole vector in shared memory (k_ntt_small).  Larger sizes: ntt_large.cu.
+static int small_ntt_host(uint8_t *data, uint32_t log_n, int inverse, int coset) {
+    const uint32_t n = 1u << log_n;
+    DBuf d, tw_f, tw_i, cbr, ubr;
+    TRY(d.alloc((size_t)n * 32));
+    TRY(tw_f.alloc(sizeof(Fr) * std::max(1u, n / 2))); TRY(tw_i.alloc(sizeof(Fr) * std::max(1u, n / 2)));
+    TRY(cbr.alloc(sizeof(Fr) * n)); TRY(ubr.alloc(sizeof(Fr) * n));
+    Fr w, wi, g, gi;
+    for (int i = 0; i < 8; i++) { w.l[i] = FrParams::ROOT28(i); wi.l[i] = FrParams::ROOT28_INV(i); g.l[i] = FrParams::GEN(i); gi.l[i] = FrParams::GEN_INV(i); }
+    for (uint32_t i = log_n; i < 28; i++) { w = w.sqr(); wi = wi.sqr(); }
+    Fr ninv = host::fr_from_u64(n).inverse();
+    cudaStream_t st = nullptr;
+    if (n >= 2) {
+        LAUNCH(k_pow_table, (n / 2 + 127) / 128, 128, 0, st, tw_f.as<Fr>(), w, Fr::one(), n / 2, 0u);
+        LAUNCH(k_pow_table, (n / 2 + 127) / 128, 128, 0, st, tw_i.as<Fr>(), wi, Fr::one(), n / 2, 0u);
+    }
+    LAUNCH(k_pow_table, (n + 127) / 128, 128, 0, st, cbr.as<Fr>(), g, ninv, n, log_n);
+    LAUNCH(k_pow_table, (n + 127) / 128, 128, 0, st, ubr.as<Fr>(), gi, ninv.to_canonical(), n, log_n);
+    NttTables T{tw_f.as<Fr>(), tw_i.as<Fr>(), cbr.as<Fr>(), ubr.as<Fr>(), nullptr, ninv, Fr::zero()};
+    CUDA_TRY(cudaMemcpy(d.p, data, (size_t)n * 32, cudaMemcpyHostToDevice));
+    size_t smem = (size_t)32 * n;
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_ntt_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LAUNCH(k_ntt_small, 1, std::max(32u, std::min(n / 2, 512u)), smem, st, d.as<Fr>(), T, log_n, inverse, coset);
+    CUDA_TRY(cudaMemcpy(data, d.p, (size_t)n * 32, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaGetLastError());
+    return LZKP_OK;
+}
+
+// ------------------------------------------------------------------------ C ABI
+#pragma GCC visibility push(default)
+extern "C" {
+
+int lzkp_init(const int *devices, int n_devices) {
+    if (devices && n_devices > 0) {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (g_device >= 0 && g_device != devices[0]) return fail(LZKP_E_STATE, "device already selected");
+        g_device = devices[0];
+    }
+    return ensure_device();
+}
+int lzkp_shutdown(void) { return LZKP_OK; }
+const char *lzkp_last_error(void) { return g_err.c_str(); }
+uint64_t lzkp_kernel_launches(void) { return g_launches.load(); }
+
+int lzkp_pk_load_ex(const uint8_t *pk_bytes, size_t len, int validate, const lzkp_pk_options *opt, lzkp_pk **out) {
+    if (!pk_bytes || !out) return fail(LZKP_E_INVALID, "null argument");
+    *out = nullptr;
+    TRY(ensure_device());
+    lzkp_pk *pk = new (std::nothrow) lzkp_pk();
+    if (!pk) return fail(LZKP_E_NOMEM, "host allocation failed");
+    int rc = pk_load_impl(pk_bytes, len, validate, opt, pk);
+    if (rc != LZKP_OK) {
+        delete pk;
+        return rc;
+    }
+    *out = pk;
+    return LZKP_OK;
+}
+int lzkp_pk_load(const uint8_t *pk_bytes, size_t len, int validate, lzkp_pk **out) {
+    return lzkp_pk_load_ex(pk_bytes, len, validate, nullptr, out);
+}
+void lzkp_pk_free(lzkp_pk *pk) {
+    if (!pk) return;
+    if (g_device >= 0) cudaSetDevice(g_device);
+    delete pk;
+}
+int lzkp_pk_info(const lzkp_pk *pk, uint64_t info[8]) {
+    if (!pk || !info) return fail(LZKP_E_INVALID, "null argument");
+    info[0] = pk->n_vars; info[1] = pk->n_inst; info[2] = pk->n_wit; info[3] = pk->n;
+    info[4] = (uint64_t)pk->c; info[5] = pk->W; info[6] = pk->table_bytes; info[7] = pk->max_chunk;
+    return LZKP_OK;
+}
+
+int lzkp_circuit_load(lzkp_pk *pk, uint32_t m, uint32_t n_inst, uint32_t n_wit, const uint32_t *a_rowptr,
+                      const uint32_t *a_col, const uint8_t *a_val, const uint32_t *b_rowptr, const uint32_t *b_col,
+                      const uint8_t *b_val, const uint32_t *c_rowptr, const uint32_t *c_col, const uint8_t *c_val) {
+    if (!pk || !a_rowptr || !b_rowptr || !c_rowptr) return fail(LZKP_E_INVALID, "null argument");
+    TRY(ensure_device());
+    std::lock_guard<std::mutex> lk(pk->mu);
+    const uint32_t *rp[3] = {a_rowptr, b_rowptr, c_rowptr}, *cl[3] = {a_col, b_col, c_col};
+    const uint8_t *vl[3] = {a_val, b_val, c_val};
+    pk->kind = -1;
+    return circuit_install(pk, m, n_inst, n_wit, rp, cl, vl);
+}
+static host::R1cs synth(int kind, uint32_t param) {
+    return kind == LZKP_CIRCUIT_EQUALITY ? host::synth_equality(param) : host::synth_membership(param);
+}
+int lzkp_circuit_builtin(lzkp_pk *pk, int kind, uint32_t param) {
+    if (!pk || (kind != LZKP_CIRCUIT_EQUALITY && kind != LZKP_CIRCUIT_MEMBERSHIP) || param == 0)
+        return fail(LZKP_E_INVALID, "bad circuit kind / parameter");
+    TRY(ensure_device());
+    std::lock_guard<std::mutex> lk(pk->mu);
+    host::R1cs cs = synth(kind, param);
+    const host::Csr *M[3] = {&cs.A, &cs.B, &cs.C};
+    const uint32_t *rp[3], *cl[3];
+    const uint8_t *vl[3];
+    for (int k = 0; k < 3; k++) {
+        rp[k] = M[k]->rowptr.data(); cl[k] = M[k]->col.data();
+        vl[k] = reinterpret_cast<const uint8_t *>(M[k]->val.data());
+    }
+    TRY(circuit_install(pk, cs.m, cs.n_inst, cs.n_wit, rp, cl, vl));
+    pk->kind = kind;
+    pk->kind_param = param;
+    return LZKP_OK;
+}
+int lzkp_builtin_circuit_csr(int kind, uint32_t param, uint64_t shape[6], uint32_t *rowptr[3], uint32_t *col[3],
+                             uint8_t *val[3]) {
+    if ((kind != LZKP_CIRCUIT_EQUALITY && kind != LZKP_CIRCUIT_MEMBERSHIP) || param == 0 || !shape)
+        return fail(LZKP_E_INVALID, "bad circuit kind / parameter");
+    host::R1cs cs = synth(kind, param);
+    const host::Csr *M[3] = {&cs.A, &cs.B, &cs.C};
+    shape[0] = cs.m; shape[1] = cs.n_inst; shape[2] = cs.n_wit;
+    for (int k = 0; k < 3; k++) shape[3 + k] = M[k]->col.size();
+    if (rowptr && col && val)
+        for (int k = 0; k < 3; k++) {
+            memcpy(rowptr[k], M[k]->rowptr.data(), sizeof(uint32_t) * (cs.m + 1));
+            memcpy(col[k], M[k]->col.data(), sizeof(uint32_t) * M[k]->col.size());
+            memcpy(val[k], M[k]->val.data(), 32 * M[k]->col.size());
+        }
+    return LZKP_OK;
+}
+
+int lzkp_prove_batch(lzkp_pk *pk, size_t n_proofs, const uint8_t *z, const uint8_t *r, const uint8_t *s,
+                     uint8_t *proofs_out, int32_t *status) {
+    if (!pk || (n_proofs && (!z || !r || !s || !proofs_out || !status))) return fail(LZKP_E_INVALID, "null argument");
+    TRY(ensure_device());
+    std::lock_guard<std::mutex> lk(pk->mu);
+    if (!pk->has_circuit) return fail(LZKP_E_STATE, "lzkp_circuit_load has not been called");
+    cudaStream_t st = pk->stream;
+    const size_t nv = pk->n_vars;
+    for (size_t off = 0; off < n_proofs; off += pk->max_chunk) {
+        uint32_t P = (uint32_t)std::min<size_t>(pk->max_chunk, n_proofs - off);
+        TRY(ensure_workspace(pk, P));
+        CUDA_TRY(cudaMemcpyAsync(pk->ws_z.p, z + off * nv * 32, (size_t)P * nv * 32, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(pk->ws_r.p, r + off * 32, (size_t)P * 32, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(pk->ws_s.p, s + off * 32, (size_t)P * 32, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemsetAsync(pk->ws_status.p, 0, (size_t)P * 4, st));
+        TRY(run_prove(pk, P, pk->ws_r.as<Fr>(), pk->ws_s.as<Fr>(), pk->ws_proofs.as<uint8_t>(), pk->ws_status.as<int32_t>(), st));
+        CUDA_TRY(cudaMemcpyAsync(proofs_out + off * 256, pk->ws_proofs.p, (size_t)P * 256, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(status + off, pk->ws_status.p, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaGetLastError());
+    }
+    blank_failed(n_proofs, status, proofs_out);
+    return LZKP_OK;
+}
+
+int lzkp_prove_equality_batch(lzkp_pk *pk, size_t n_proofs, const uint64_t *a, const uint64_t *b,
+                              const uint8_t *commitments, const uint8_t *r, const uint8_t *s, uint8_t *proofs_out,
+                              uint8_t *commitments_out, int32_t *status) {
+    if (!pk || (n_proofs && (!a || !b || !r || !s || !proofs_out || !status))) return fail(LZKP_E_INVALID, "null argument");
+    TRY(ensure_device());
+    std::lock_guard<std::mutex> lk(pk->mu);
+    if (!pk->has_circuit || pk->kind != LZKP_CIRCUIT_EQUALITY) return fail(LZKP_E_STATE, "pk is not bound to the builtin equality circuit");
+    cudaStream_t st = pk->stream;
+    for (size_t off = 0; off < n_proofs; off += pk->max_chunk) {
+        uint32_t P = (uint32_t)std::min<size_t>(pk->max_chunk, n_proofs - off);
+        TRY(ensure_workspace(pk, P));
+        CUDA_TRY(cudaMemcpyAsync(pk->ws_a.p, a + off, (size_t)P * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(pk->ws_b.p, b + off, (size_t)P * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(pk->ws_r.p, r + off * 32, (size_t)P * 32, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(pk->ws_s.p, s + off * 32, (size_t)P * 32, cudaMemcpyHostToDevice, st));
+        if (commitments) CUDA_TRY(cudaMemcpyAsync(pk->ws_commit.p, commitments + off * 32, (size_t)P * 32, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemsetAsync(pk->ws_status.p, 0, (size_t)P * 4, st));
+        LAUNCH(k_witgen_equality, (P + 127) / 128, 128, 0, st, pk->ws_a.as<uint64_t>(), pk->ws_b.as<uint64_t>(),
+               commitments ? pk->ws_commit.as<Fr>() : nullptr, pk->ws_z.as<Fr>(), pk->ws_commit.as<Fr>(),
+               pk->ws_status.as<int32_t>(), P, pk->kind_param, pk->n_vars);
+        TRY(run_prove(pk, P, pk->ws_r.as<Fr>(), pk->ws_s.as<Fr>(), pk->ws_proofs.as<uint8_t>(), pk->ws_status.as<int32_t>(), st));
+        CUDA_TRY(cudaMemcpyAsync(proofs_out + off * 256, pk->ws_proofs.p, (size_t)P * 256, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(status + off, pk->ws_status.p, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
+        if (commitments_out) CUDA_TRY(cudaMemcpyAsync(commitments_out + off * 32, pk->ws_commit.p, (size_t)P * 32, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaGetLastError());
+    }
+    blank_failed(n_proofs, status, proofs_out);
+    return LZKP_OK;
+}
+
+int lzkp_prove_membership_batch(lzkp_pk *pk, size_t n_proofs, const uint64_t *value, const uint64_t *sets,
+                                const uint32_t *set_len, uint32_t set_stride, const uint8_t *commitments,
+                                const uint8_t *r, const uint8_t *s, uint8_t *proofs_out, uint8_t *commitments_out,
+                                int32_t *status) {
+    if (!pk || (n_proofs && (!value || !sets || !set_len || !r || !s || !proofs_out || !status)))
+        return fail(LZKP_E_INVALID, "null argument");
+    TRY(ensure_device());
+    std::lock_guard<std::mutex> lk(pk->mu);
+    if (!pk->has_circuit || pk->kind != LZKP_CIRCUIT_MEMBERSHIP) return fail(LZKP_E_STATE, "pk is not bound to the builtin membership circuit");
+    cudaStream_t st = pk->stream;
+    for (size_t off = 0; off < n_proofs; off += pk->max_chunk) {
+        uint32_t P = (uint32_t)std::min<size_t>(pk->max_chunk, n_proofs - off);
+        TRY(ensure_workspace(pk, P));
+        TRY(pk->ws_sets.ensure((size_t)P * set_stride * 8));
+        TRY(pk->ws_setlen.ensure((size_t)P * 4));
+        CUDA_TRY(cudaMemcpyAsync(pk->ws_a.p, value + off, (size_t)P * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(pk->ws_sets.p, sets + off * set_stride, (size_t)P * set_stride * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(pk->ws_setlen.p, set_len + off, (size_t)P * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(pk->ws_r.p, r + off * 32, (size_t)P * 32, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(pk->ws_s.p, s + off * 32, (size_t)P * 32, cudaMemcpyHostToDevice, st));
+        if (commitments) CUDA_TRY(cudaMemcpyAsync(pk->ws_commit.p, commitments + off * 32, (size_t)P * 32, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemsetAsync(pk->ws_status.p, 0, (size_t)P * 4, st));
+        LAUNCH(k_witgen_membership, (P + 127) / 128, 128, 0, st, pk->ws_a.as<uint64_t>(), pk->ws_sets.as<uint64_t>(),
+               pk->ws_setlen.as<uint32_t>(), set_stride, commitments ? pk->ws_commit.as<Fr>() : nullptr, pk->ws_z.as<Fr>(),
+               pk->ws_commit.as<Fr>(), pk->ws_status.as<int32_t>(), P, pk->kind_param, pk->n_vars);
+        TRY(run_prove(pk, P, pk->ws_r.as<Fr>(), pk->ws_s.as<Fr>(), pk->ws_proofs.as<uint8_t>(), pk->ws_status.as<int32_t>(), st));
+        CUDA_TRY(cudaMemcpyAsync(proofs_out + off * 256, pk->ws_proofs.p, (size_t)P * 256, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(status + off, pk->ws_status.p, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
+        if (commitments_out) CUDA_TRY(cudaMemcpyAsync(commitments_out + off * 32, pk->ws_commit.p, (size_t)P * 32, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaGetLastError());
+    }
+    blank_failed(n_proofs, status, proofs_out);
+    return LZKP_OK;
+}
+
+int lzkp_prove_equality_batch_device(lzkp_pk *pk, size_t n_proofs, const void *d_a, const void *d_b, const void *d_r,
+                                     const void *d_s, void *d_proofs, void *d_status, void *stream) {
+    if (!pk || !d_a || !d_b || !d_r || !d_s || !d_proofs || !d_status) return fail(LZKP_E_INVALID, "null argument");
+    TRY(ensure_device());
+    std::lock_guard<std::mutex> lk(pk->mu);
+    if (!pk->has_circuit || pk->kind != LZKP_CIRCUIT_EQUALITY) return fail(LZKP_E_STATE, "pk is not bound to the builtin equality circuit");
+    cudaStream_t st = (cudaStream_t)stream;
+    for (size_t off = 0; off < n_proofs; off += pk->max_chunk) {
+        uint32_t P = (uint32_t)std::min<size_t>(pk->max_chunk, n_proofs - off);
+        TRY(ensure_workspace(pk, P));
+        int32_t *stat = (int32_t *)d_status + off;
+        CUDA_TRY(cudaMemsetAsync(stat, 0, (size_t)P * 4, st));
+        LAUNCH(k_witgen_equality, (P + 127) / 128, 128, 0, st, (const uint64_t *)d_a + off, (const uint64_t *)d_b + off,
+               (const Fr *)nullptr, pk->ws_z.as<Fr>(), pk->ws_commit.as<Fr>(), stat, P, pk->kind_param, pk->n_vars);
+        TRY(run_prove(pk, P, (const Fr *)d_r + off, (const Fr *)d_s + off, (uint8_t *)d_proofs + off * 256, stat, st));
+    }
+    CUDA_TRY(cudaGetLastError());
+    return LZKP_OK;
+}
+
+int lzkp_witness_map(lzkp_pk *pk, size_t n_proofs, const uint8_t *z, uint8_t *h_out) {
+    if (!pk || (n_proofs && (!z || !h_out))) return fail(LZKP_E_INVALID, "null argument");
+    TRY(ensure_device());
+    std::lock_guard<std::mutex> lk(pk->mu);
+    if (!pk->has_circuit) return fail(LZKP_E_STATE, "lzkp_circuit_load has not been called");
+    cudaStream_t st = pk->stream;
+    const size_t nv = pk->n_vars, n = pk->n;
+    for (size_t off = 0; off < n_proofs; off += pk->max_chunk) {
+        uint32_t P = (uint32_t)std::min<size_t>(pk->max_chunk, n_proofs - off);
+        TRY(ensure_workspace(pk, P));
+        CUDA_TRY(cudaMemcpyAsync(pk->ws_z.p, z + off * nv * 32, (size_t)P * nv * 32, cudaMemcpyHostToDevice, st));
+        TRY(run_witness_map(pk, P, st));
+        CUDA_TRY(cudaMemcpyAsync(h_out + off * n * 32, pk->ws_h.p, (size_t)P * n * 32, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaGetLastError());
+    }
+    return LZKP_OK;
+}
+
+int lzkp_msm_g1(const uint8_t *bases_affine, const uint8_t *scalars, size_t n, uint8_t *out_affine) {
+    if (!out_affine || (n && (!bases_affine || !scalars))) return fail(LZKP_E_INVALID, "null argument");
+    TRY(ensure_device());
+    return large_msm_g1_host(bases_affine, scalars, n, out_affine);
+}
+int lzkp_msm_g2(const uint8_t *bases_affine, const uint8_t *scalars, size_t n, uint8_t *out_affine) {
+    if (!out_affine || (n && (!bases_affine || !scalars))) return fail(LZKP_E_INVALID, "null argument");
+    TRY(ensure_device());
+    return large_msm_g2_host(bases_affine, scalars, n, out_affine);
+}
+int lzkp_ntt(uint8_t *data, uint32_t log_n, int inverse, int coset) {
+    if (!data || log_n > 28) return fail(LZKP_E_INVALID, "bad argument");
+    TRY(ensure_device());
+    if (log_n <= 12) return small_ntt_host(data, log_n, inverse, coset);
+    return large_ntt_host(data, log_n, inverse, coset);
+}
+
+int lzkp_commit_value_snark(uint64_t value, uint8_t out[32]) {
+    if (!out) return fail(LZKP_E_INVALID, "null argument");
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    host::commit_value_snark(value, out);
+    return LZKP_OK;
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

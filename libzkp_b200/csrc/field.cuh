@@ -20,8 +20,10 @@
 
 #if defined(__CUDACC__)
 #define LZ_HD __host__ __device__ __forceinline__
+#define LZ_COLD __host__ __device__ __noinline__
 #else
 #define LZ_HD inline
+#define LZ_COLD inline
 #endif
 #define LZ_CONST_ARRAY(NAME, ...)                                   \
     LZ_HD static constexpr uint32_t NAME(int i) {                   \
@@ -187,7 +189,7 @@ LZ_HD uint32_t sub8(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b
 // Field element.  P supplies INV, MOD(i), ONE(i), R2(i), ...
 // --------------------------------------------------------------------------
 template <class P>
-struct Fp {
+struct alignas(16) Fp {
     uint32_t l[8];
 
     LZ_HD static Fp zero() {
@@ -308,8 +310,8 @@ struct Fp {
         o.l[0] = 1;
         return *this * o;
     }
-    // Fermat inverse x^(p-2); 0 -> 0.  Rare (3 per proof), so kept compact: runtime loop.
-    LZ_HD Fp inverse() const {
+    // Fermat inverse x^(p-2); 0 -> 0.  Rare (3 per proof), so kept compact: runtime loop, not inlined.
+    LZ_COLD Fp inverse() const {
         uint32_t e[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) e[i] = P::PM2(i);

@@ -1,0 +1,77 @@
+// msm_batch.cu — the five MSMs of a batch of proofs as fixed-base table gathers + XYZZ mixed adds
+// (replaces VariableBaseMSM::msm_bigint inside ark-groth16's prover,
+// reached from src/backend/snark.rs:364 and :442).
+#include "tables.h"
+#include "dev_util.cuh"
+
+namespace lzkp {
+
+// ---------------------------------------------------------------- batched table MSM
+// A "unit" is one (base, window) pair: it names a digit row and a table row.  An "item" is a
+// contiguous run of units of one MSM.  Thread (p, item) gathers table[unit][|d|-1] for its proof's
+// digit d of every unit in the item and accumulates in XYZZ.  Lanes of a warp are 32 different proofs
+// walking the same units, so a warp-step touches one N*sizeof(point) slab (2 MiB for G1 at c=16).
+template <class F>
+__device__ __forceinline__ Affine<F> gather_point(const Affine<F> *table, uint32_t N, uint32_t tbl_unit, int d) {
+    int mag = d < 0 ? -d : d;
+    Affine<F> pt = ldg_vec(table + (size_t)tbl_unit * N + (uint32_t)(mag - 1));
+    if (d < 0) pt.y = pt.y.neg();
+    return pt;
+}
+template <class F, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_msm_batch(const Affine<F> *__restrict__ table, uint32_t N,
+                                                     const uint32_t *__restrict__ unit_dig,
+                                                     const uint32_t *__restrict__ unit_tbl,
+                                                     const uint2 *__restrict__ items, const int16_t *__restrict__ dig,
+                                                     uint32_t P, XYZZ<F> *__restrict__ partial) {
+    const uint32_t p = blockIdx.x * BLOCK + threadIdx.x, item = blockIdx.y;
+    if (p >= P) return;
+    const uint2 range = items[item];
+    XYZZ<F> acc = XYZZ<F>::inf();
+    int d = dig[(size_t)__ldg(unit_dig + range.x) * P + p];
+    Affine<F> pt = Affine<F>::inf();
+    if (d) pt = gather_point(table, N, __ldg(unit_tbl + range.x), d);
+    for (uint32_t u = range.x; u < range.y; u++) {
+        int dn = 0;
+        Affine<F> ptn = Affine<F>::inf();
+        if (u + 1 < range.y) {
+            dn = dig[(size_t)__ldg(unit_dig + u + 1) * P + p];
+            if (dn) ptn = gather_point(table, N, __ldg(unit_tbl + u + 1), dn);
+        }
+        if (d) acc.madd(pt);
+        d = dn;
+        pt = ptn;
+    }
+    st_vec(partial + (size_t)item * P + p, acc);
+}
+// out[q * P + p] = sum of partial[item][p] over the items of MSM q.  grid (ceil(P/128), n_msm)
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_reduce(const XYZZ<F> *partial, const uint2 *msm_items, uint32_t P,
+                                                    XYZZ<F> *out) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x, q = blockIdx.y;
+    if (p >= P) return;
+    uint2 r = msm_items[q];
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t it = r.x; it < r.y; it++) acc.add_cold(ld_vec(partial + (size_t)it * P + p));
+    st_vec(out + (size_t)q * P + p, acc);
+}
+
+
+namespace eng {
+
+void batch_msm_g1(const BatchMsmArgs &a, cudaStream_t st) {
+    const uint32_t gx = (a.P + 127) / 128;
+    LAUNCH((k_msm_batch<Fq, 128>), dim3(gx, a.n_items), 128, 0, st, (const G1Affine *)a.table, a.N, a.unit_dig,
+           a.unit_tbl, (const uint2 *)a.items, a.dig, a.P, (G1XYZZ *)a.partial);
+    LAUNCH((k_msm_reduce<Fq>), dim3(gx, a.n_msm), 128, 0, st, (const G1XYZZ *)a.partial, (const uint2 *)a.msm_items,
+           a.P, (G1XYZZ *)a.out);
+}
+void batch_msm_g2(const BatchMsmArgs &a, cudaStream_t st) {
+    LAUNCH((k_msm_batch<Fq2, 64>), dim3((a.P + 63) / 64, a.n_items), 64, 0, st, (const G2Affine *)a.table, a.N,
+           a.unit_dig, a.unit_tbl, (const uint2 *)a.items, a.dig, a.P, (G2XYZZ *)a.partial);
+    LAUNCH((k_msm_reduce<Fq2>), dim3((a.P + 127) / 128, a.n_msm), 128, 0, st, (const G2XYZZ *)a.partial,
+           (const uint2 *)a.msm_items, a.P, (G2XYZZ *)a.out);
+}
+
+}  // namespace eng
+}  // namespace lzkp

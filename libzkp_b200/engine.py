@@ -1,0 +1,184 @@
+"""Thin numpy-level wrappers over the C ABI (include/lzkp_b200.h).
+
+Byte formats are ark-serialize's: field elements 32 B canonical little-endian,
+G1 affine 64 B, G2 affine 128 B, proofs 256 B.  Arrays are ``uint8`` with a trailing byte axis.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import check, lib
+
+EQUALITY = _ffi.LZKP_CIRCUIT_EQUALITY
+MEMBERSHIP = _ffi.LZKP_CIRCUIT_MEMBERSHIP
+
+
+def _p(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _u8(a, shape_tail: int) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    if a.size % shape_tail:
+        raise ValueError(f"byte array size {a.size} is not a multiple of {shape_tail}")
+    return a.reshape(-1, shape_tail)
+
+
+def init(device: Optional[int] = None) -> None:
+    """lzkp_init: bind this process to one CUDA device (one process per GPU)."""
+    if device is None:
+        check(lib().lzkp_init(None, 0))
+    else:
+        arr = (C.c_int * 1)(int(device))
+        check(lib().lzkp_init(arr, 1))
+
+
+def kernel_launches() -> int:
+    return int(lib().lzkp_kernel_launches())
+
+
+def commit_value_snark(value: int) -> bytes:
+    """commit_value_snark (src/utils/commitment.rs:14-16): 32 B LE MiMC-5 commitment of a u64."""
+    out = (C.c_uint8 * 32)()
+    check(lib().lzkp_commit_value_snark(C.c_uint64(int(value) & (2**64 - 1)), out))
+    return bytes(out)
+
+
+def builtin_circuit_csr(kind: int, param: int):
+    """Shape and CSR matrices of a builtin circuit: (m, n_inst, n_wit), [(rowptr, col, val)] * 3."""
+    shape = (C.c_uint64 * 6)()
+    check(lib().lzkp_builtin_circuit_csr(kind, param, shape, None, None, None))
+    m, n_inst, n_wit = int(shape[0]), int(shape[1]), int(shape[2])
+    mats = [(np.zeros(m + 1, np.uint32), np.zeros(int(shape[3 + k]), np.uint32),
+             np.zeros((int(shape[3 + k]), 32), np.uint8)) for k in range(3)]
+    rp = (C.c_void_p * 3)(*[m_[0].ctypes.data for m_ in mats])
+    cl = (C.c_void_p * 3)(*[m_[1].ctypes.data for m_ in mats])
+    vl = (C.c_void_p * 3)(*[m_[2].ctypes.data for m_ in mats])
+    check(lib().lzkp_builtin_circuit_csr(kind, param, shape, rp, cl, vl))
+    return (m, n_inst, n_wit), mats
+
+
+class ProvingKey:
+    """A proving key resident in HBM (lzkp_pk): the object the reference keeps in its OnceLock
+    (src/backend/snark.rs:295-339), plus the circuit's R1CS matrices and NTT tables."""
+
+    def __init__(self, pk_bytes: bytes, validate: bool = False, window_bits: int = 0,
+                 table_budget_bytes: int = 0, max_chunk: int = 0):
+        self._h = C.c_void_p()
+        buf = np.frombuffer(pk_bytes, dtype=np.uint8)
+        opt = _ffi.PkOptions(window_bits, table_budget_bytes, max_chunk)
+        check(lib().lzkp_pk_load_ex(_p(buf), len(pk_bytes), int(validate), C.byref(opt), C.byref(self._h)))
+        info = (C.c_uint64 * 8)()
+        check(lib().lzkp_pk_info(self._h, info))
+        (self.n_vars, self.n_inst, self.n_wit, self.n, self.window_bits, self.windows, self.table_bytes,
+         self.max_chunk) = [int(x) for x in info]
+
+    def close(self):
+        if self._h:
+            lib().lzkp_pk_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- circuit binding
+    def circuit_builtin(self, kind: int, param: int) -> "ProvingKey":
+        check(lib().lzkp_circuit_builtin(self._h, kind, param))
+        return self
+
+    def circuit_load(self, m: int, n_inst: int, n_wit: int, mats) -> "ProvingKey":
+        flat = []
+        keep = []
+        for rowptr, col, val in mats:
+            rowptr = np.ascontiguousarray(rowptr, np.uint32)
+            col = np.ascontiguousarray(col, np.uint32)
+            val = np.ascontiguousarray(val, np.uint8)
+            keep += [rowptr, col, val]
+            flat += [_p(rowptr), _p(col), _p(val)]
+        check(lib().lzkp_circuit_load(self._h, m, n_inst, n_wit, *flat))
+        return self
+
+    # ---- proving
+    def prove_batch(self, z, r, s) -> Tuple[np.ndarray, np.ndarray]:
+        z = _u8(z, 32 * self.n_vars)
+        n = z.shape[0]
+        r, s = _u8(r, 32), _u8(s, 32)
+        if r.shape[0] != n or s.shape[0] != n:
+            raise ValueError("r, s must hold one scalar per proof")
+        proofs = np.zeros((n, 256), np.uint8)
+        status = np.zeros(n, np.int32)
+        check(lib().lzkp_prove_batch(self._h, n, _p(z), _p(r), _p(s), _p(proofs), _p(status)))
+        return proofs, status
+
+    def prove_equality_batch(self, a, b, r, s, commitments=None):
+        a = np.ascontiguousarray(a, np.uint64)
+        b = np.ascontiguousarray(b, np.uint64)
+        n = a.shape[0]
+        r, s = _u8(r, 32), _u8(s, 32)
+        cm = None if commitments is None else _u8(commitments, 32)
+        proofs = np.zeros((n, 256), np.uint8)
+        cm_out = np.zeros((n, 32), np.uint8)
+        status = np.zeros(n, np.int32)
+        check(lib().lzkp_prove_equality_batch(self._h, n, _p(a), _p(b), _p(cm), _p(r), _p(s), _p(proofs), _p(cm_out),
+                                              _p(status)))
+        return proofs, cm_out, status
+
+    def prove_membership_batch(self, value, sets, set_len, r, s, commitments=None):
+        value = np.ascontiguousarray(value, np.uint64)
+        sets = np.ascontiguousarray(sets, np.uint64)
+        set_len = np.ascontiguousarray(set_len, np.uint32)
+        n = value.shape[0]
+        stride = sets.shape[1] if sets.ndim == 2 else 0
+        r, s = _u8(r, 32), _u8(s, 32)
+        cm = None if commitments is None else _u8(commitments, 32)
+        proofs = np.zeros((n, 256), np.uint8)
+        cm_out = np.zeros((n, 32), np.uint8)
+        status = np.zeros(n, np.int32)
+        check(lib().lzkp_prove_membership_batch(self._h, n, _p(value), _p(sets), _p(set_len), stride, _p(cm), _p(r),
+                                                _p(s), _p(proofs), _p(cm_out), _p(status)))
+        return proofs, cm_out, status
+
+    def prove_equality_batch_device(self, n: int, d_a: int, d_b: int, d_r: int, d_s: int, d_proofs: int,
+                                    d_status: int, stream: int = 0) -> None:
+        """All arguments are device pointers (ints); asynchronous on `stream`."""
+        check(lib().lzkp_prove_equality_batch_device(self._h, n, d_a, d_b, d_r, d_s, d_proofs, d_status, stream))
+
+    def witness_map(self, z) -> np.ndarray:
+        z = _u8(z, 32 * self.n_vars)
+        n = z.shape[0]
+        h = np.zeros((n, self.n, 32), np.uint8)
+        check(lib().lzkp_witness_map(self._h, n, _p(z), _p(h)))
+        return h
+
+
+def msm_g1(bases, scalars) -> bytes:
+    bases, scalars = _u8(bases, 64), _u8(scalars, 32)
+    n = min(bases.shape[0], scalars.shape[0])       # msm_bigint truncates to the shorter input
+    out = np.zeros(64, np.uint8)
+    check(lib().lzkp_msm_g1(_p(bases), _p(scalars), n, _p(out)))
+    return out.tobytes()
+
+
+def msm_g2(bases, scalars) -> bytes:
+    bases, scalars = _u8(bases, 128), _u8(scalars, 32)
+    n = min(bases.shape[0], scalars.shape[0])
+    out = np.zeros(128, np.uint8)
+    check(lib().lzkp_msm_g2(_p(bases), _p(scalars), n, _p(out)))
+    return out.tobytes()
+
+
+def ntt(data, inverse: bool = False, coset: bool = False) -> np.ndarray:
+    a = _u8(data, 32).copy()
+    n = a.shape[0]
+    log_n = n.bit_length() - 1
+    if n == 0 or (1 << log_n) != n:
+        raise ValueError("NTT size must be a power of two")
+    check(lib().lzkp_ntt(_p(a), log_n, int(inverse), int(coset)))
+    return a

@@ -1,0 +1,257 @@
+"""Host-side mirror of the reference's SNARK backend (src/backend/snark.rs) over the C ABI.
+
+Same names, argument meaning and failure convention as ``SnarkBackend`` (snark.rs:293-495) and the
+``ZkpBackend`` trait (src/backend/mod.rs:5-8): proving returns ``b""`` on any failure
+(snark.rs:345,350,361,366,371).  What differs is where the work happens: the calls the reference
+makes into ark-groth16 (``Groth16::<Bn254>::prove``, snark.rs:364 and :442) are replaced by
+``lzkp_prove_equality_batch`` / ``lzkp_prove_membership_batch`` on a proving key that was uploaded
+once (the reference's OnceLock fill, snark.rs:295-339) and stays resident in HBM.
+
+In production this layer is Rust (INTEGRATION.md shows the ``extern "C"`` shim); no Rust toolchain
+exists in this image, so the mirror is Python.  It never touches ``oracle/``.
+"""
+from __future__ import annotations
+
+import os
+import secrets
+import threading
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import engine
+from .errors import ConfigError
+
+R_MOD = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+MIMC_ROUNDS = 110          # snark.rs:182
+MAX_SET_SIZE = 64          # snark.rs:503
+
+_lock = threading.RLock()
+_key_dir_override: Optional[str] = None
+_setups: Dict[str, object] = {}      # prefix -> Setup | Exception text (OnceLock<Result<..>>)
+# Test / deployment hook: a callable(prefix) -> (pk_bytes, vk_bytes) used when no key files exist.
+_generator: Optional[Callable[[str], Tuple[bytes, bytes]]] = None
+_pk_options = {"window_bits": 0, "table_budget_bytes": 0, "max_chunk": 0, "validate": False}
+
+
+class OsRng:
+    """Prover randomness r, s: the reference draws Fr::rand from OsRng (snark.rs:363,441)."""
+
+    def next_fr(self) -> int:
+        return secrets.randbelow(R_MOD)
+
+
+class Setup:
+    def __init__(self, pk: engine.ProvingKey, vk_bytes: bytes):
+        self.pk = pk
+        self.vk_bytes = vk_bytes
+
+
+def configure(window_bits: int = 0, table_budget_bytes: int = 0, max_chunk: int = 0, validate: bool = False,
+              generator: Optional[Callable[[str], Tuple[bytes, bytes]]] = None) -> None:
+    """Engine options used when a setup is first loaded (window size of the resident tables, ...)."""
+    global _generator
+    with _lock:
+        _pk_options.update(window_bits=window_bits, table_budget_bytes=table_budget_bytes, max_chunk=max_chunk,
+                           validate=validate)
+        _generator = generator
+
+
+def reset() -> None:
+    """Drop loaded setups and the key-dir override (tests only; the reference has no equivalent)."""
+    global _key_dir_override
+    with _lock:
+        for v in _setups.values():
+            if isinstance(v, Setup):
+                v.pk.close()
+        _setups.clear()
+        _key_dir_override = None
+
+
+def _get_key_dir() -> Optional[str]:               # snark.rs:23-30
+    with _lock:
+        if _key_dir_override is not None:
+            return _key_dir_override
+    return os.environ.get("LIBZKP_SNARK_KEY_DIR")
+
+
+def _key_paths(prefix: str) -> Optional[Tuple[str, str]]:   # snark.rs:32-38
+    d = _get_key_dir()
+    if d is None:
+        return None
+    return os.path.join(d, f"{prefix}_pk.bin"), os.path.join(d, f"{prefix}_vk.bin")
+
+
+def set_snark_key_dir(path: str) -> bool:          # snark.rs:141-171 (advanced::set_snark_key_dir returns true)
+    global _key_dir_override
+    if path == "":
+        raise ConfigError("SNARK key directory cannot be empty")
+    with _lock:
+        if _setups:
+            raise ConfigError("SNARK setup is already initialized; set LIBZKP_SNARK_KEY_DIR before first proof")
+        if _key_dir_override is not None and _key_dir_override != path:
+            raise ConfigError(f"SNARK key directory already set to {_key_dir_override}; new value {path} rejected")
+        _key_dir_override = path
+    return True
+
+
+def is_snark_initialized() -> bool:                # snark.rs:173-175
+    with _lock:
+        return bool(_setups)
+
+
+def _generate(prefix: str) -> Tuple[bytes, bytes]:
+    if _generator is not None:
+        return _generator(prefix)
+    from . import setup as _setup               # device-side circuit_specific_setup
+    return _setup.generate(prefix)
+
+
+def _load_or_generate(prefix: str) -> Tuple[bytes, bytes]:   # snark.rs:122-139
+    paths = _key_paths(prefix)
+    if paths is not None:
+        pk_path, vk_path = paths
+        if os.path.exists(pk_path) and os.path.exists(vk_path):
+            with open(pk_path, "rb") as f:
+                pk = f.read()
+            with open(vk_path, "rb") as f:
+                vk = f.read()
+            return pk, vk
+        pk, vk = _generate(prefix)
+        try:                                       # best effort, errors ignored (snark.rs:130-132)
+            os.makedirs(os.path.dirname(pk_path) or ".", exist_ok=True)
+            with open(pk_path, "wb") as f:
+                f.write(pk)
+            with open(vk_path, "wb") as f:
+                f.write(vk)
+        except OSError:
+            pass
+        return pk, vk
+    return _generate(prefix)
+
+
+_CIRCUITS = {"equality_mimc": (engine.EQUALITY, MIMC_ROUNDS), "membership_mimc": (engine.MEMBERSHIP, MAX_SET_SIZE)}
+
+
+def _get_setup(prefix: str):
+    """OnceLock<Result<SnarkKeyPair, String>> (snark.rs:295-327): the outcome, good or bad, is kept."""
+    with _lock:
+        got = _setups.get(prefix)
+        if got is None:
+            try:
+                pk_bytes, vk_bytes = _load_or_generate(prefix)
+                o = _pk_options
+                pk = engine.ProvingKey(pk_bytes, validate=o["validate"], window_bits=o["window_bits"],
+                                       table_budget_bytes=o["table_budget_bytes"], max_chunk=o["max_chunk"])
+                kind, param = _CIRCUITS[prefix]
+                pk.circuit_builtin(kind, param)
+                got = Setup(pk, vk_bytes)
+            except Exception as e:                 # noqa: BLE001 - mirrors Result<_, String>
+                got = f"setup failed: {e!r}"
+            _setups[prefix] = got
+        return got
+
+
+def mimc_commitment(value: int) -> bytes:
+    """fr_to_commitment(mimc_hash_native(value)) (snark.rs:201-221)."""
+    return engine.commit_value_snark(value)
+
+
+def _fr_from_commitment(b: bytes) -> Optional[int]:   # snark.rs:224-229: canonical only
+    if len(b) != 32:
+        return None
+    v = int.from_bytes(b, "little")
+    return v if v < R_MOD else None
+
+
+def _scalars(rng, n: int) -> np.ndarray:
+    return np.frombuffer(b"".join(rng.next_fr().to_bytes(32, "little") for _ in range(n)), np.uint8).reshape(n, 32)
+
+
+class SnarkBackend:
+    """Static-method mirror of ``SnarkBackend`` (snark.rs:293) + the batched entry points."""
+
+    @staticmethod
+    def get_universal_setup():
+        return _get_setup("equality_mimc")
+
+    @staticmethod
+    def get_membership_setup():
+        return _get_setup("membership_mimc")
+
+    # ---- single proofs (the reference's signatures; rng is the OsRng seam, SURVEY.md headline fact 4)
+    @staticmethod
+    def prove_equality_zk(a: int, b: int, hash_input: bytes, rng=None) -> bytes:      # snark.rs:343-374
+        out = SnarkBackend.prove_equality_zk_batch([a], [b], [hash_input], rng)
+        return out[0]
+
+    @staticmethod
+    def prove_membership_zk(value: int, set_: Sequence[int], commitment: bytes, rng=None) -> bytes:  # :405-452
+        out = SnarkBackend.prove_membership_zk_batch([value], [list(set_)], [commitment], rng)
+        return out[0]
+
+    # ---- batched: one device call for many independent proofs of one circuit
+    @staticmethod
+    def prove_equality_zk_batch(a: Sequence[int], b: Sequence[int], hash_inputs: Sequence[bytes], rng=None
+                                ) -> List[bytes]:
+        n = len(a)
+        out: List[bytes] = [b""] * n
+        live = [i for i in range(n) if a[i] == b[i] and _fr_from_commitment(bytes(hash_inputs[i])) is not None]
+        if not live:
+            return out
+        setup = SnarkBackend.get_universal_setup()
+        if not isinstance(setup, Setup):
+            return out
+        rng = rng or OsRng()
+        rs = _scalars(rng, 2 * len(live))           # r then s per proof, the order prove() draws them
+        try:
+            proofs, _, status = setup.pk.prove_equality_batch(
+                np.array([a[i] for i in live], np.uint64), np.array([b[i] for i in live], np.uint64),
+                rs[0::2], rs[1::2],
+                np.frombuffer(b"".join(bytes(hash_inputs[i]) for i in live), np.uint8).reshape(-1, 32))
+        except Exception:                           # noqa: BLE001 - any backend error -> empty Vec
+            return out
+        for k, i in enumerate(live):
+            if status[k] == 0:
+                out[i] = proofs[k].tobytes()
+        return out
+
+    @staticmethod
+    def prove_membership_zk_batch(values: Sequence[int], sets: Sequence[Sequence[int]],
+                                  commitments: Sequence[bytes], rng=None) -> List[bytes]:
+        n = len(values)
+        out: List[bytes] = [b""] * n
+        live = [i for i in range(n)
+                if 1 <= len(sets[i]) <= MAX_SET_SIZE and _fr_from_commitment(bytes(commitments[i])) is not None
+                and values[i] in sets[i]]
+        if not live:
+            return out
+        setup = SnarkBackend.get_membership_setup()
+        if not isinstance(setup, Setup):
+            return out
+        rng = rng or OsRng()
+        rs = _scalars(rng, 2 * len(live))
+        sets_arr = np.zeros((len(live), MAX_SET_SIZE), np.uint64)
+        lens = np.zeros(len(live), np.uint32)
+        for k, i in enumerate(live):
+            lens[k] = len(sets[i])
+            sets_arr[k, :lens[k]] = np.array(sets[i], np.uint64)
+        try:
+            proofs, _, status = setup.pk.prove_membership_batch(
+                np.array([values[i] for i in live], np.uint64), sets_arr, lens, rs[0::2], rs[1::2],
+                np.frombuffer(b"".join(bytes(commitments[i]) for i in live), np.uint8).reshape(-1, 32))
+        except Exception:                           # noqa: BLE001
+            return out
+        for k, i in enumerate(live):
+            if status[k] == 0:
+                out[i] = proofs[k].tobytes()
+        return out
+
+    # ---- ZkpBackend trait (src/backend/mod.rs:5-8; impl snark.rs:587-611)
+    @staticmethod
+    def prove(data: bytes) -> bytes:
+        if len(data) != 48:
+            return b""
+        a = int.from_bytes(data[0:8], "little")
+        b = int.from_bytes(data[8:16], "little")
+        return SnarkBackend.prove_equality_zk(a, b, bytes(data[16:48]))

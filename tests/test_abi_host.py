@@ -1,0 +1,184 @@
+"""CPU-side checks of the product: the C-ABI library loads and exports exactly what
+include/lzkp_b200.h declares, computing entry points fail loudly without a device, the native
+circuit synthesis / MiMC / field arithmetic agree with the oracle, and the host mirror keeps the
+reference's API behaviour (envelope, validation errors, batch registry)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, has_gpu
+
+import libzkp_b200 as zk
+from libzkp_b200 import _ffi, batch, engine, proof, snark
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "lzkp_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(lzkp_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _ffi.lib()
+    names = header_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/lzkp_b200.h but not exported"
+    assert sorted(_ffi.SIGNATURES) == names              # the Python binding covers the whole header
+    out = subprocess.run(["nm", "-D", "--defined-only", _ffi.LIB_PATH], capture_output=True, text=True).stdout
+    exported = sorted(set(re.findall(r" T (lzkp_[a-z0-9_]+)", out)))
+    assert exported == names                             # and nothing undeclared leaks out
+
+
+@pytest.mark.skipif(has_gpu(), reason="checks the no-device behaviour")
+def test_no_cpu_fallback():
+    with pytest.raises(zk.EngineError) as e:
+        engine.init()
+    assert e.value.code == _ffi.LZKP_E_NO_DEVICE
+    with pytest.raises(zk.EngineError):
+        engine.ntt(np.zeros((8, 32), np.uint8))
+    with pytest.raises(zk.EngineError):
+        engine.msm_g1(np.zeros((1, 64), np.uint8), np.zeros((1, 32), np.uint8))
+    with pytest.raises(zk.EngineError):
+        engine.ProvingKey(b"\x00" * 100)
+    # the reference's failure convention: empty Vec -> ProofGenerationFailed -> RuntimeError
+    snark.reset()
+    snark.configure(generator=lambda prefix: (b"", b""))
+    try:
+        with pytest.raises(zk.ProofGenerationFailed):
+            zk.prove_equality(5, 5)
+        assert isinstance(zk.ProofGenerationFailed("x"), RuntimeError)
+    finally:
+        snark.reset()
+        snark.configure()
+
+
+def test_commit_value_snark_known_answers(golden):
+    for v, row in golden["mimc"].items():
+        assert zk.snark_commit_value(int(v)).hex() == row["commitment"]
+    assert zk.snark_commit_value(42) != zk.snark_commit_value(43)          # snark.rs:618-623
+
+
+@pytest.mark.parametrize("kind,param,name", [(0, 110, "equality"), (1, 64, "membership"), (1, 5, "membership"),
+                                             (0, 7, "equality")])
+def test_builtin_circuit_equals_oracle(co, kind, param, name):
+    (m, n_inst, n_wit), mats = engine.builtin_circuit_csr(kind, param)
+    c = co.Circuit(name, param)
+    assert (m, n_inst, n_wit) == (c.m, c.n_inst, c.n_wit)
+    for which in range(3):
+        rowptr, col, val = c.matrix(which)
+        assert np.array_equal(mats[which][0], rowptr)
+        assert np.array_equal(mats[which][1], col)
+        assert np.array_equal(mats[which][2], val)
+
+
+@pytest.fixture(scope="module")
+def field_shim(tmp_path_factory):
+    out = tmp_path_factory.mktemp("shim") / "field_host.so"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-o", str(out),
+                    os.path.join(ROOT, "tests", "host_shim", "field_host.cpp")], check=True)
+    return C.CDLL(str(out))
+
+
+def test_device_field_composition_on_host(field_shim, po):
+    """field.cuh's Montgomery row composition (portable bodies) against big-int arithmetic."""
+    R = 1 << 256
+    rng = po.SplitMix64(77)
+    for mod, fn in ((po.R_MOD, field_shim.fr_op), (po.Q_MOD, field_shim.fq_op)):
+        def op(code, a, b=0):
+            o = (C.c_uint8 * 32)()
+            fn(code, (C.c_uint8 * 32)(*a.to_bytes(32, "little")), (C.c_uint8 * 32)(*b.to_bytes(32, "little")), o)
+            return int.from_bytes(bytes(o), "little")
+        rinv = pow(R, -1, mod)
+        vals = [0, 1, mod - 1, mod - 2, R % mod] + [rng.next_fr() % mod for _ in range(200)]
+        for i, a in enumerate(vals):
+            b = vals[(i * 7 + 3) % len(vals)]
+            assert op(0, a, b) == a * b * rinv % mod
+            assert op(7, a) == a * a * rinv % mod
+            assert op(1, a, b) == (a + b) % mod
+            assert op(2, a, b) == (a - b) % mod
+            assert op(3, a) == (-a) % mod
+            assert op(4, a) == a * R % mod
+            assert op(5, a) == a * rinv % mod
+        for a in vals[1:20]:
+            am = a * R % mod
+            assert op(6, am) == pow(a, -1, mod) * R % mod
+    assert field_shim.fq_gt((C.c_uint8 * 32)(*(5).to_bytes(32, "little")), (C.c_uint8 * 32)(*(4).to_bytes(32, "little"))) == 1
+    assert field_shim.fq_gt((C.c_uint8 * 32)(*(4).to_bytes(32, "little")), (C.c_uint8 * 32)(*(4).to_bytes(32, "little"))) == 0
+
+
+# ---------------------------------------------------------------- host mirror behaviour
+def test_envelope_layout_and_limits():
+    p = proof.Proof(2, b"\x01" * 256, b"\x02" * 32)
+    b = p.to_bytes()
+    assert len(b) == 298 and b[0] == 2 and b[1] == 2          # proof/mod.rs:23-36
+    assert b[2:6] == (256).to_bytes(4, "little") and b[6:10] == (32).to_bytes(4, "little")
+    q = proof.Proof.from_bytes(b)
+    assert (q.version, q.scheme, q.proof, q.commitment) == (2, 2, p.proof, p.commitment)
+    with pytest.raises(zk.InvalidProofFormat):
+        proof.Proof.from_bytes(b[:9])
+    with pytest.raises(zk.InvalidProofFormat):
+        proof.Proof.from_bytes(b + b"\x00")
+    with pytest.raises(TypeError):                             # PyO3 maps InvalidProofFormat -> TypeError
+        proof.Proof.from_bytes(b"\x02\x02" + (1 << 30).to_bytes(4, "little") + bytes(4))
+
+
+def test_validation_errors_match_reference():
+    with pytest.raises(ValueError, match="values are not equal"):           # validation.rs:21-26
+        zk.prove_equality(1, 2)
+    with pytest.raises(ValueError, match="set cannot be empty"):            # validation.rs:47-50
+        zk.prove_membership(1, [])
+    with pytest.raises(ValueError, match="value 9 is not in the provided set"):
+        zk.prove_membership(9, [1, 2, 3])
+    with pytest.raises(ValueError, match="set size 65 exceeds maximum allowed size 64"):
+        zk.prove_membership(1, list(range(65)))
+    with pytest.raises(OverflowError):
+        zk.prove_equality(2**64, 2**64)
+
+
+def test_batch_registry_semantics():
+    bid = zk.create_proof_batch()
+    assert bid != 0
+    zk.batch_add_equality_proof(bid, 7, 7)
+    zk.batch_add_membership_proof(bid, 2, [1, 2, 3])
+    zk.batch_add_membership_proof(bid, 1, list(range(100)))    # no size check at add time (batch.rs:92-95)
+    with pytest.raises(ValueError):
+        zk.batch_add_equality_proof(bid, 1, 2)
+    with pytest.raises(ValueError, match="Invalid batch ID"):
+        zk.batch_add_equality_proof(bid ^ 1, 1, 1)
+    st = zk.get_batch_status(bid)
+    assert st["total_operations"] == 3 and st["equality_proofs"] == 1 and st["membership_proofs"] == 2
+    assert st["range_proofs"] == 0
+    zk.clear_batch(bid)
+    zk.clear_batch(bid)                                        # unknown id is not an error (batch.rs:175-183)
+    with pytest.raises(ValueError, match="Invalid batch ID"):
+        zk.process_batch(bid)
+    assert zk.process_batch(zk.create_proof_batch()) == []     # empty batch -> empty list, id consumed
+
+
+def test_key_dir_rules(tmp_path):
+    snark.reset()
+    try:
+        with pytest.raises(TypeError):                          # ConfigError -> TypeError
+            zk.set_snark_key_dir("")
+        assert zk.set_snark_key_dir(str(tmp_path)) is True
+        assert zk.set_snark_key_dir(str(tmp_path)) is True      # same value accepted (snark.rs:158-167)
+        with pytest.raises(zk.ConfigError):
+            zk.set_snark_key_dir(str(tmp_path / "other"))
+        assert not zk.is_snark_setup_initialized()
+    finally:
+        snark.reset()
+
+
+def test_zkp_backend_trait_input_length():
+    assert zk.SnarkBackend.prove(b"\x00" * 47) == b""           # snark.rs:588-591
+    assert zk.SnarkBackend.prove_equality_zk(1, 2, bytes(32)) == b""      # a != b (snark.rs:344)
+    bad = (snark.R_MOD).to_bytes(32, "little")
+    assert zk.SnarkBackend.prove_equality_zk(1, 1, bad) == b""  # non-canonical commitment (snark.rs:348-351)
+    assert zk.SnarkBackend.prove_membership_zk(1, [], bytes(32)) == b""   # snark.rs:406
+    assert zk.SnarkBackend.prove_membership_zk(1, list(range(65)), bytes(32)) == b""
+    assert zk.SnarkBackend.prove_membership_zk(9, [1, 2], bytes(32)) == b""   # snark.rs:415-418

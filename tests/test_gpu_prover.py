@@ -1,0 +1,250 @@
+"""GPU parity tests of the batched Groth16 prover, all through the C ABI (include/lzkp_b200.h).
+Bar: bit-exact — witness-map outputs, 256-byte proofs — against the CPU oracle on the same
+seeded inputs, plus the reference's own round-trip / negative tests (snark.rs:634-641,
+tests/integration.rs:19-44,86-90, examples/demo.rs:66-105) with the oracle's pairing verifier
+standing in for ark-groth16's."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import libzkp_b200 as zk
+from libzkp_b200 import engine, snark
+
+pytestmark = pytest.mark.gpu
+
+WINDOW_BITS = int(os.environ.get("LZKP_TEST_WINDOW_BITS", "12"))   # small tables: quick to build
+
+
+@pytest.fixture(scope="module")
+def eq_pk(eq_keys):
+    pk = engine.ProvingKey(eq_keys.pk_bytes, validate=True, window_bits=WINDOW_BITS)
+    pk.circuit_builtin(engine.EQUALITY, 110)
+    yield pk
+    pk.close()
+
+
+@pytest.fixture(scope="module")
+def mb_pk(mb_keys):
+    pk = engine.ProvingKey(mb_keys.pk_bytes, validate=False, window_bits=WINDOW_BITS)
+    pk.circuit_builtin(engine.MEMBERSHIP, 64)
+    yield pk
+    pk.close()
+
+
+def test_pk_info(eq_pk, mb_pk):
+    assert (eq_pk.n_vars, eq_pk.n_inst, eq_pk.n_wit, eq_pk.n) == (334, 2, 332, 512)
+    assert (mb_pk.n_vars, mb_pk.n_inst, mb_pk.n_wit, mb_pk.n) == (653, 130, 523, 1024)
+    assert eq_pk.window_bits == WINDOW_BITS
+
+
+def test_witness_map_bit_exact(eq_pk, mb_pk, eq_keys, mb_keys, golden):
+    zs = np.stack([eq_keys.circuit.assign(a, a) for a in (5, 42, 0, 2**64 - 1, 1234567)])
+    h = eq_pk.witness_map(zs)
+    for i in range(len(zs)):
+        assert np.array_equal(h[i], eq_keys.circuit.witness_map(zs[i]))
+    for i, case in enumerate(golden["equality"]["proofs"][:4]):
+        assert hashlib.sha256(h[i].tobytes()).hexdigest() == case["h_sha256"]
+    zm = np.stack([mb_keys.circuit.assign(v, set_=s) for v, s in ((2, [1, 2, 3]), (9, list(range(64))))])
+    hm = mb_pk.witness_map(zm)
+    for i in range(len(zm)):
+        assert np.array_equal(hm[i], mb_keys.circuit.witness_map(zm[i]))
+
+
+def test_witness_map_unsatisfied_assignment(eq_pk, eq_keys):
+    # the prover does not check satisfiability (arkworks only does in debug builds): any z maps to SOME h
+    z = eq_keys.circuit.assign(5, 5).copy()
+    z[10, 0] ^= 1
+    assert np.array_equal(eq_pk.witness_map(z[None])[0], eq_keys.circuit.witness_map(z))
+
+
+def test_golden_proofs_bit_exact(eq_pk, mb_pk, eq_keys, mb_keys, co, golden):
+    cases = golden["equality"]["proofs"]
+    z = np.stack([eq_keys.circuit.assign(c["a"], c["a"]) for c in cases])
+    r = co.fr_array([int(c["r"]) for c in cases])
+    s = co.fr_array([int(c["s"]) for c in cases])
+    proofs, status = eq_pk.prove_batch(z, r, s)              # includes the r = 0 / s = 0 edge cases
+    assert not status.any()
+    for i, c in enumerate(cases):
+        assert proofs[i].tobytes().hex() == c["proof"], f"equality case {i}"
+    cases = golden["membership"]["proofs"]
+    z = np.stack([mb_keys.circuit.assign(c["value"], set_=c["set"]) for c in cases])
+    proofs, status = mb_pk.prove_batch(z, co.fr_array([int(c["r"]) for c in cases]),
+                                       co.fr_array([int(c["s"]) for c in cases]))
+    assert not status.any()
+    for i, c in enumerate(cases):
+        assert proofs[i].tobytes().hex() == c["proof"], f"membership case {i}"
+
+
+@pytest.mark.parametrize("n", [1, 3, 130, 300])
+def test_equality_batch_device_witness_vs_oracle(eq_pk, eq_keys, co, po, frs, n):
+    rng = po.SplitMix64(3)
+    a = np.array([rng.next_u64() for _ in range(n)], np.uint64)
+    b = a.copy()
+    if n > 2:
+        b[1] ^= 1                                           # a != b -> status 1, blank proof (snark.rs:344)
+    r, s = frs(4, n), frs(40, n)
+    proofs, cms, status = eq_pk.prove_equality_batch(a, b, r, s)
+    want, wstat = co.prove_batch(eq_keys.circuit, eq_keys.opk, a, b, None, None, r, s)
+    assert np.array_equal(status != 0, wstat != 0)
+    assert np.array_equal(proofs, want)
+    for i in range(min(n, 5)):
+        if status[i] == 0:
+            assert cms[i].tobytes() == co.mimc_hash(int(a[i]))
+    assert n <= 2 or (status[1] == 1 and not proofs[1].any())
+
+
+def test_equality_batch_with_supplied_commitments(eq_pk, eq_keys, co, frs):
+    # a wrong commitment still yields a proof (of a false statement); bytes must match the oracle's
+    a = np.array([11, 12], np.uint64)
+    cm = np.stack([np.frombuffer(co.mimc_hash(11), np.uint8), np.frombuffer(co.mimc_hash(99), np.uint8)])
+    r, s = frs(5, 2), frs(6, 2)
+    proofs, _, status = eq_pk.prove_equality_batch(a, a, r, s, commitments=cm)
+    assert not status.any()
+    for i in range(2):
+        z = eq_keys.circuit.assign(int(a[i]), int(a[i]), commitment=cm[i].tobytes())
+        assert proofs[i].tobytes() == co.prove(eq_keys.circuit, eq_keys.opk, z, co.fr_list(r[i])[0], co.fr_list(s[i])[0])
+
+
+def test_membership_batch_device_witness_vs_oracle(mb_pk, mb_keys, co, po, frs):
+    rng = po.SplitMix64(5)
+    n = 70
+    sets = np.zeros((n, 64), np.uint64)
+    lens = np.zeros(n, np.uint32)
+    vals = np.zeros(n, np.uint64)
+    for i in range(n):
+        L = 1 + i % 64
+        lens[i] = L
+        sets[i, :L] = [rng.next_u64() for _ in range(L)]
+        vals[i] = sets[i, i % L]
+    vals[3] = 12345                                         # not in set -> status 2 (snark.rs:415-418)
+    lens[4] = 0                                             # empty set (snark.rs:406)
+    r, s = frs(7, n), frs(8, n)
+    proofs, cms, status = mb_pk.prove_membership_batch(vals, sets, lens, r, s)
+    want, wstat = co.prove_batch(mb_keys.circuit, mb_keys.opk, vals, None, sets, lens, r, s)
+    assert status[3] == 2 and status[4] == 2
+    assert np.array_equal(status != 0, wstat != 0)
+    assert np.array_equal(proofs, want)
+
+
+def test_noncanonical_scalar_is_rejected(eq_pk, eq_keys, frs):
+    z = np.stack([eq_keys.circuit.assign(5, 5), eq_keys.circuit.assign(6, 6)])
+    z[1, 7] = 0xFF                                          # >= r
+    proofs, status = eq_pk.prove_batch(z, frs(1, 2), frs(2, 2))
+    assert status[0] == 0 and status[1] != 0 and not proofs[1].any() and proofs[0].any()
+
+
+# ---------------------------------------------------------------- the reference's own tests, mirrored
+@pytest.fixture(scope="module")
+def api(eq_keys, mb_keys):
+    keys = {"equality_mimc": (eq_keys.pk_bytes, eq_keys.vk_bytes), "membership_mimc": (mb_keys.pk_bytes, mb_keys.vk_bytes)}
+    snark.reset()
+    snark.configure(window_bits=WINDOW_BITS, generator=lambda prefix: keys[prefix])
+    yield zk
+    snark.reset()
+    snark.configure()
+
+
+def verify_equality(po, keys, proof_bytes, val1, val2):
+    """verify_equality (equality_proof.rs:50-57) with the oracle's pairing verifier."""
+    if val1 != val2:
+        return False
+    p = zk.Proof.from_bytes(proof_bytes)
+    cm = zk.snark_commit_value(val1)
+    if p.scheme != 2 or p.commitment != cm:
+        return False
+    return po.verify(po.vk_from_bytes(keys.vk_bytes), po.equality_public_inputs(int.from_bytes(cm, "little")),
+                     po.proof_from_bytes(p.proof))
+
+
+def verify_membership(po, keys, proof_bytes, set_):
+    """verify_membership (set_membership.rs:40-71)."""
+    p = zk.Proof.from_bytes(proof_bytes)
+    if p.scheme != 4:
+        return False
+    n = int.from_bytes(p.proof[:4], "little")
+    emb = [int.from_bytes(p.proof[4 + 8 * i:12 + 8 * i], "little") for i in range(n)]
+    if sorted(emb) != sorted(set_):
+        return False
+    return po.verify(po.vk_from_bytes(keys.vk_bytes),
+                     po.membership_public_inputs(int.from_bytes(p.commitment, "little"), emb),
+                     po.proof_from_bytes(p.proof[4 + 8 * n:]))
+
+
+def test_integration_equality(api, po, eq_keys):
+    proof = api.prove_equality(3, 3)                         # tests/integration.rs:19-23
+    assert len(proof) == 298
+    assert verify_equality(po, eq_keys, proof, 3, 3)
+    proof = api.prove_equality(42, 42)                       # tests/integration.rs:25-32
+    assert zk.Proof.from_bytes(proof).commitment == api.snark_commit_value(42)
+    assert verify_equality(po, eq_keys, proof, 42, 42)
+    assert not verify_equality(po, eq_keys, proof, 43, 43)   # tests/integration.rs:86-90
+    assert api.prove_equality(42, 42) != proof               # fresh r, s every call (OsRng)
+    assert api.is_snark_setup_initialized()
+
+
+def test_snark_backend_roundtrip(api, po, eq_keys):
+    # snark.rs:634-641
+    cm = api.snark_commit_value(42)
+    proof = api.SnarkBackend.prove_equality_zk(42, 42, cm)
+    assert len(proof) == 256
+    vk = po.vk_from_bytes(eq_keys.vk_bytes)
+    assert po.verify(vk, po.equality_public_inputs(int.from_bytes(cm, "little")), po.proof_from_bytes(proof))
+    wrong = api.snark_commit_value(99)
+    assert not po.verify(vk, po.equality_public_inputs(int.from_bytes(wrong, "little")), po.proof_from_bytes(proof))
+    data = (42).to_bytes(8, "little") * 2 + cm               # ZkpBackend::prove, snark.rs:587-606
+    assert len(api.SnarkBackend.prove(data)) == 256
+
+
+def test_integration_membership(api, po, mb_keys):
+    proof = api.prove_membership(2, [1, 2, 3])               # tests/integration.rs:40-44
+    assert len(proof) == 10 + 4 + 24 + 256 + 32
+    assert verify_membership(po, mb_keys, proof, [1, 2, 3])
+    assert verify_membership(po, mb_keys, proof, [3, 2, 1])  # sets compare as sorted multisets
+    assert not verify_membership(po, mb_keys, proof, [1, 2, 4])
+
+
+def test_process_batch_order_and_fail_fast(api, po, eq_keys, mb_keys):
+    bid = api.create_proof_batch()                           # examples/demo.rs:66-105 (SNARK ops only)
+    ops = [("e", 100, 100), ("m", 25, [10, 20, 25, 30, 40]), ("e", 7, 7), ("m", 1, [1]), ("e", 2**64 - 1, 2**64 - 1)]
+    for o in ops:
+        if o[0] == "e":
+            api.batch_add_equality_proof(bid, o[1], o[2])
+        else:
+            api.batch_add_membership_proof(bid, o[1], o[2])
+    out = api.process_batch(bid)
+    assert len(out) == len(ops)
+    for o, p in zip(ops, out):                               # insertion order kept
+        if o[0] == "e":
+            assert verify_equality(po, eq_keys, p, o[1], o[2])
+        else:
+            assert verify_membership(po, mb_keys, p, o[2])
+    with pytest.raises(ValueError):                          # id consumed (batch.rs:111-118)
+        api.process_batch(bid)
+    bid = api.create_proof_batch()
+    api.batch_add_equality_proof(bid, 1, 1)
+    api.batch_add_membership_proof(bid, 0, list(range(100)))  # oversized set only fails at process time
+    with pytest.raises(ValueError, match="exceeds maximum"):
+        api.process_batch(bid)
+
+
+def test_seeded_rng_gives_reproducible_bytes(api, po, eq_keys, co):
+    rng1, rng2 = po.SplitMix64(2), po.SplitMix64(2)
+    p1 = api.SnarkBackend.prove_equality_zk(5, 5, api.snark_commit_value(5), rng=rng1)
+    r, s = rng2.next_fr(), rng2.next_fr()
+    z = eq_keys.circuit.assign(5, 5)
+    assert p1 == co.prove(eq_keys.circuit, eq_keys.opk, z, r, s)
+
+
+def test_window_sizes_agree(eq_keys, co, frs):
+    a = np.arange(1, 9, dtype=np.uint64)
+    r, s = frs(31, 8), frs(32, 8)
+    want, _ = co.prove_batch(eq_keys.circuit, eq_keys.opk, a, a, None, None, r, s)
+    for c in (8, 11, 16):
+        pk = engine.ProvingKey(eq_keys.pk_bytes, window_bits=c)
+        pk.circuit_builtin(engine.EQUALITY, 110)
+        assert pk.window_bits == c
+        proofs, _, status = pk.prove_equality_batch(a, a, r, s)
+        pk.close()
+        assert not status.any() and np.array_equal(proofs, want), f"c={c}"
