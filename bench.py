@@ -1,0 +1,373 @@
+#!/usr/bin/env python3
+"""bench.py — batched Groth16/BN254 proving throughput on B200 (BASELINE.json configs[1]).
+
+A "step" is one pass of the hot path over one batch: `--batch` (default 4096) equality proofs per
+GPU — device witness generation, R1CS->QAP witness map (7 NTTs), the five MSMs over the HBM-resident
+proving key, assembly and ark-serialize output.  One process per GPU (torchrun sets RANK /
+LOCAL_RANK / WORLD_SIZE); proofs are independent, so ranks shard the batch with no collective
+("weak": every rank proves its own `--batch` proofs per step).
+
+  value   proofs/s with inputs (a, b, r, s) already resident in HBM, timed with CUDA events
+  e2e     the same through the C-ABI call lzkp_prove_equality_batch with HOST buffers
+          (H2D of inputs and D2H of proofs/status/commitments inside the timed region)
+  roofline  the dominant kernel (G1 table MSM): algorithmic IMADs / its CUDA-event time vs the
+          measured IMAD peak of this pool's B200 (profiles/r1_microbench.jsonl)
+  cpu_baseline  the CPU restatement (oracle/, C, OpenMP) on a bounded sample of the same workload
+  extra   G1 MSM points/s @2^20 and NTT elements/s @2^22 (BASELINE.json's other two metrics)
+
+`--impl reference` times the CPU restatement of the reference's prover (oracle/: the reference is
+Rust + un-vendored arkworks crates and cannot be built here, DESIGN.md "Oracle") on the same config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+R_MOD = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+IMAD_PER_MUL = 272            # 136 32x32 multiply-accumulates = 272 mad.lo/mad.hi issues
+M_MADD_G1 = 10                # XYZZ mixed add: 8M + 2S
+M_MADD_G2 = 28                # over Fq2: 8 * 3 + 2 * 2 base-field products
+IMAD_PEAK_FALLBACK = 17.25e12  # measured: tools/microbench on this pool (profiles/r1_microbench.jsonl)
+
+
+class SplitMix64:
+    def __init__(self, seed):
+        self.s = seed & 0xFFFFFFFFFFFFFFFF
+
+    def next_u64(self):
+        self.s = (self.s + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+        z = self.s
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+        return z ^ (z >> 31)
+
+    def next_fr(self):
+        while True:
+            v = 0
+            for i in range(4):
+                v |= self.next_u64() << (64 * i)
+            v &= (1 << 254) - 1
+            if v < R_MOD:
+                return v
+
+
+def fr_bytes(seed, n):
+    rng = SplitMix64(seed)
+    return np.frombuffer(b"".join(rng.next_fr().to_bytes(32, "little") for _ in range(n)), np.uint8).reshape(n, 32).copy()
+
+
+def u64s(seed, n):
+    rng = SplitMix64(seed)
+    return np.array([rng.next_u64() for _ in range(n)], np.uint64)
+
+
+def imad_peak():
+    p = os.path.join(ROOT, "profiles", "r1_microbench.jsonl")
+    best = 0.0
+    try:
+        for line in open(p):
+            d = json.loads(line)
+            if d.get("bench") == "imad_wide_independent":
+                best = max(best, d["Tops_per_s"] * 1e12)
+    except OSError:
+        pass
+    return (best, "measured (profiles/r1_microbench.jsonl, mad.wide.u32 issue rate x 1 = 32-bit IMAD pairs)") if best \
+        else (IMAD_PEAK_FALLBACK, "fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.1] or [r for _, r in self.rows[-3:]]
+        sm = sorted(int(float(r[0])) for r in rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        power = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(float(rows[0][1])) if rows else None,
+                "power_w_max": max(power) if power else None, "samples": len(rows), "reasons": reasons}
+
+
+def toxic(seed):
+    rng = SplitMix64(seed)
+    return [rng.next_fr() for _ in range(5)]
+
+
+# ----------------------------------------------------------------------------- reference arm (CPU)
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from oracle import c_oracle as co
+    co.build()
+    circ = co.Circuit("equality")
+    pk_bytes, _ = circ.setup(toxic(1))
+    opk = co.ProvingKey(pk_bytes)
+    cores = co.num_threads()
+    sample = args.ref_sample or max(cores * 4, 32)
+    a = u64s(3, sample)
+    r, s = fr_bytes(4, sample), fr_bytes(40, sample)
+    for _ in range(args.warmup):
+        co.prove_batch(circ, opk, a[:cores], a[:cores], None, None, r[:cores], s[:cores])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        proofs, status = co.prove_batch(circ, opk, a, a, None, None, r, s)
+    dt = time.perf_counter() - t0
+    assert not status.any()
+    v = sample * args.steps / dt
+    desc = f"{sample} of the {args.batch} equality proofs per step, proof-parallel over {cores} OpenMP threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "groth16_bn254_proofs_per_sec_batched", "value": v, "unit": "proofs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u256 (4x64-bit Montgomery limbs)",
+        "data": "synthetic", "config": config_dict(args, sample),
+        "cpu_baseline": {"value": v, "unit": "proofs/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": v, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "CPU restatement (C, OpenMP) of the arkworks prover the reference calls; not arkworks itself "
+                "(no Rust toolchain in this image)"}))
+
+
+def config_dict(args, per_step=None):
+    return {"workload": f"process_batch of {args.batch} prove_equality proofs per GPU (BASELINE.json configs[1]): "
+                        "MiMC-5 equality circuit, m=332 constraints, domain n=512, MSM sizes 333/333/333(G2)/332/511",
+            "batch_per_gpu": args.batch, "proofs_per_step_timed": per_step or args.batch,
+            "l2": "inputs larger than L2: every step gathers from the resident window tables "
+                  "(tens of GB at c=16) and rewrites > 126 MB of workspace"}
+
+
+# ----------------------------------------------------------------------------- our arm (GPU)
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from libzkp_b200 import engine
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    engine.init(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    P = args.batch
+
+    # proving key: device-side setup (deterministic toxic waste: synthetic benchmark key), resident tables
+    t0 = time.perf_counter()
+    pk_bytes, _ = engine.setup_builtin(engine.EQUALITY, 110, toxic(1))
+    t_setup = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    pk = engine.ProvingKey(pk_bytes, window_bits=args.window_bits, max_chunk=args.chunk)
+    pk.circuit_builtin(engine.EQUALITY, 110)
+    torch.cuda.synchronize()
+    t_load = time.perf_counter() - t0
+
+    # synthetic inputs: a_i = b_i = SplitMix64(seed 3), r_i, s_i seed 4
+    a_h = u64s(3 + 1000 * rank, P)
+    r_h, s_h = fr_bytes(4 + 1000 * rank, P), fr_bytes(40 + 1000 * rank, P)
+    as_i64 = lambda x: torch.from_numpy(x.view(np.int64))
+    d_a = as_i64(a_h).to(dev)
+    d_r, d_s = torch.from_numpy(r_h).to(dev), torch.from_numpy(s_h).to(dev)
+    d_proofs = torch.zeros((P, 256), dtype=torch.uint8, device=dev)
+    d_status = torch.zeros(P, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step():
+        pk.prove_equality_batch_device(P, d_a.data_ptr(), d_a.data_ptr(), d_r.data_ptr(), d_s.data_ptr(),
+                                       d_proofs.data_ptr(), d_status.data_ptr(), stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    assert int(d_status.abs().sum().item()) == 0
+    engine.profile_enable(True)
+    pk.profile_read(reset=True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    launches0 = engine.kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    w0 = time.time()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    w1 = time.time()
+    ms = ev0.elapsed_time(ev1)
+    launches = engine.kernel_launches() - launches0
+    clocks = sampler.stop(w0, w1)
+    regions = pk.profile_read(reset=True)
+    engine.profile_enable(False)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * P * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers (pinned), copies inside the timed region
+    pin = lambda x: torch.from_numpy(x).pin_memory().numpy()
+    a_p, r_p, s_p = as_i64(a_h).pin_memory().numpy().view(np.uint64), pin(r_h), pin(s_h)
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    pk.prove_equality_batch(a_p, a_p, r_p, s_p)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        proofs_h, cms_h, status_h = pk.prove_equality_batch(a_p, a_p, r_p, s_p)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    assert not status_h.any()
+    assert np.array_equal(proofs_h, d_proofs.cpu().numpy()), "host-buffer and device-buffer paths disagree"
+    e2e = {"value": world * P * e2e_steps / e2e_s, "unit": "proofs/s", "h2d_bytes_per_step": P * (8 + 8 + 32 + 32),
+           "d2h_bytes_per_step": P * (256 + 4 + 32), "steps": e2e_steps,
+           "api": "lzkp_prove_equality_batch (C ABI, pinned host buffers)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (G1 table MSM)
+    peak, peak_src = imad_peak()
+    W = pk.windows
+    g1_units = (333 + 333 + 332 + 511) * W          # a, b1 (incl. delta rows), l (incl. -rs*delta), h bases x windows
+    g2_units = 333 * W
+    ms_g1, n_g1 = regions["msm_g1"]
+    imad_per_launch = P * g1_units * M_MADD_G1 * IMAD_PER_MUL
+    achieved = imad_per_launch / (ms_g1 / max(n_g1, 1) * 1e-3) if ms_g1 else 0.0
+    bytes_per_launch = P * g1_units * (64 + 2)       # one 64 B table point + one int16 digit per madd
+    roofline = {
+        "bound": "imad", "kernel": "k_msm_batch<Fq> + k_msm_reduce<Fq> (G1 fixed-base table MSM)",
+        "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "T IMAD/s", "frac": achieved / peak,
+        "peak_source": peak_src, "traffic": None,
+        "algorithmic_imad_per_launch": imad_per_launch, "avg_launch_ms": ms_g1 / max(n_g1, 1),
+        "share_of_step": ms_g1 / ms,
+        "hbm": {"algorithmic_bytes_per_launch": bytes_per_launch,
+                "achieved_gbs": bytes_per_launch / (ms_g1 / max(n_g1, 1) * 1e-3) / 1e9 if ms_g1 else 0.0,
+                "peak_gbs": measured_hbm(), "note": "table gathers; the kernel is IMAD-bound, not HBM-bound"},
+        "stage_ms_per_step": {k: v[0] / args.steps for k, v in regions.items()},
+        "g2_msm": {"algorithmic_imad_per_launch": P * g2_units * M_MADD_G2 * IMAD_PER_MUL,
+                   "achieved": (P * g2_units * M_MADD_G2 * IMAD_PER_MUL) / (regions["msm_g2"][0] / max(regions["msm_g2"][1], 1) * 1e-3) / 1e12
+                   if regions["msm_g2"][0] else 0.0, "unit": "T IMAD/s"},
+    }
+
+    # ---- CPU baseline on a bounded sample (rank 0, N=1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        from oracle import c_oracle as co
+        co.build()
+        circ = co.Circuit("equality")
+        opk = co.ProvingKey(pk_bytes)
+        cores = co.num_threads()
+        sample = max(cores * 8, 64)
+        co.prove_batch(circ, opk, a_h[:cores], a_h[:cores], None, None, r_h[:cores], s_h[:cores])
+        t0 = time.perf_counter()
+        want, wstat = co.prove_batch(circ, opk, a_h[:sample], a_h[:sample], None, None, r_h[:sample], s_h[:sample])
+        dt = time.perf_counter() - t0
+        assert np.array_equal(want, proofs_h[:sample]), "GPU proofs differ from the CPU oracle's"
+        cpu = {"value": sample / dt, "unit": "proofs/s", "cores": cores, "kind": "port",
+               "sample": f"first {sample} proofs of the step's {P}, proof-parallel over {cores} OpenMP threads; "
+                         "bytes compared equal to the GPU's"}
+
+    extra = {}
+    if world == 1 and not args.no_extra:
+        extra = bench_transforms(engine, torch, dev, args)
+
+    out = {
+        "metric": "groth16_bn254_proofs_per_sec_batched", "value": value, "unit": "proofs/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u256 (8x32-bit Montgomery limbs, integer)",
+        "data": "synthetic", "config": config_dict(args), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+        "roofline": roofline, "cpu_baseline": cpu, "extra": extra,
+        "engine": {"window_bits": pk.window_bits, "windows": pk.windows, "table_gb": pk.table_bytes / 1e9,
+                   "setup_s": t_setup, "pk_load_s": t_load},
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measured_hbm():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        return 6650.0
+
+
+def bench_transforms(engine, torch, dev, args):
+    """BASELINE.json's other two metrics: G1 MSM points/s @2^20, NTT elements/s @2^22 (device-resident)."""
+    out = {}
+    try:
+        from libzkp_b200 import transforms
+    except ImportError:
+        return {"note": "large MSM / NTT device-resident entry points not built in this revision"}
+    try:
+        out.update(transforms.bench(torch, dev, imad_peak()[0], measured_hbm()))
+    except Exception as e:  # noqa: BLE001
+        out["error"] = repr(e)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--chunk", type=int, default=0, help="proofs per device pass (0 = engine default)")
+    ap.add_argument("--window-bits", type=int, default=0)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--ref-sample", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -6,6 +6,8 @@
  *
  *   lzkp_pk_load            <- ProvingKey::<Bn254>::deserialize_uncompressed, src/backend/snark.rs:64
  *                              (and the OnceLock fill at snark.rs:295-339: upload once, keep resident)
+ *   lzkp_setup /            <- Groth16::<Bn254>::circuit_specific_setup(dummy_circuit, OsRng), snark.rs:318,337
+ *   lzkp_setup_builtin         (key generation when no key files exist, snark.rs:122-139); toxic waste is an input
  *   lzkp_circuit_load /     <- ConstraintSynthesizer::generate_constraints + cs.to_matrices(), done once per
  *   lzkp_circuit_builtin       circuit instead of on every prove (snark.rs:263-290, 515-584)
  *   lzkp_prove_batch        <- Groth16::<Bn254>::prove(&pk, circuit, rng) + proof.serialize_uncompressed,
@@ -66,6 +68,19 @@ const char *lzkp_last_error(void);
 /* Number of engine kernels launched by this process so far (bench.py's gpu_launches). */
 uint64_t lzkp_kernel_launches(void);
 
+/* Optional per-stage device timing (bench.py's roofline line): when enabled, every stage of the proving
+ * pipeline is bracketed by two CUDA events on the stream it is launched on.  lzkp_profile_read waits for
+ * the recorded events and returns accumulated milliseconds and bracket counts per region. */
+#define LZKP_REGION_WITGEN 0
+#define LZKP_REGION_WITNESS_MAP 1
+#define LZKP_REGION_DIGITS 2
+#define LZKP_REGION_MSM_G1 3
+#define LZKP_REGION_MSM_G2 4
+#define LZKP_REGION_ASSEMBLE 5
+#define LZKP_PROFILE_REGIONS 8
+int lzkp_profile_enable(int on);
+int lzkp_profile_read(lzkp_pk *pk, double ms[LZKP_PROFILE_REGIONS], uint64_t count[LZKP_PROFILE_REGIONS], int reset);
+
 /* Parse an ark-serialize uncompressed ProvingKey<Bn254> (exactly the bytes snark.rs:97-101 writes),
  * upload it, and build the resident fixed-base window tables.  validate != 0 adds the on-curve and
  * subgroup checks deserialize_uncompressed performs. */
@@ -87,6 +102,20 @@ int lzkp_circuit_builtin(lzkp_pk *pk, int kind, uint32_t param);
  * nnzA, nnzB, nnzC.  Pass NULL arrays to query the shape only. */
 int lzkp_builtin_circuit_csr(int kind, uint32_t param, uint64_t shape[6], uint32_t *rowptr[3], uint32_t *col[3],
                              uint8_t *val[3]);
+
+/* Groth16 circuit-specific setup on the device.  toxic = alpha || beta || gamma || delta || tau, five
+ * canonical non-zero 32 B scalars (the reference draws them from OsRng, snark.rs:310,331; the caller
+ * must draw them from a CSPRNG and forget them).  Standard BN254 generators.  Outputs are ark-serialize
+ * uncompressed ProvingKey<Bn254> / VerifyingKey<Bn254> (what snark.rs:97-112 persists); the buffers
+ * must hold the sizes lzkp_key_sizes reports. */
+int lzkp_key_sizes(uint32_t m, uint32_t n_inst, uint32_t n_wit, size_t *pk_len, size_t *vk_len);
+int lzkp_setup(uint32_t m, uint32_t n_inst, uint32_t n_wit,
+               const uint32_t *a_rowptr, const uint32_t *a_col, const uint8_t *a_val,
+               const uint32_t *b_rowptr, const uint32_t *b_col, const uint8_t *b_val,
+               const uint32_t *c_rowptr, const uint32_t *c_col, const uint8_t *c_val,
+               const uint8_t toxic[160], uint8_t *pk_out, size_t pk_cap, uint8_t *vk_out, size_t vk_cap);
+int lzkp_setup_builtin(int kind, uint32_t param, const uint8_t toxic[160], uint8_t *pk_out, size_t pk_cap,
+                       uint8_t *vk_out, size_t vk_cap);
 
 /* n_proofs proofs from full assignments: z is n_proofs x n_vars x 32 B (z[0] = 1), r and s are
  * n_proofs x 32 B, proofs_out n_proofs x 256 B, status n_proofs ints (0 = ok). */

@@ -35,6 +35,8 @@ SIGNATURES = {
     "lzkp_shutdown": (_int, []),
     "lzkp_last_error": (C.c_char_p, []),
     "lzkp_kernel_launches": (_u64, []),
+    "lzkp_profile_enable": (_int, [_int]),
+    "lzkp_profile_read": (_int, [_vp, C.POINTER(C.c_double), C.POINTER(_u64), _int]),
     "lzkp_pk_load": (_int, [_vp, _sz, _int, C.POINTER(_vp)]),
     "lzkp_pk_load_ex": (_int, [_vp, _sz, _int, C.POINTER(PkOptions), C.POINTER(_vp)]),
     "lzkp_pk_free": (None, [_vp]),
@@ -42,6 +44,9 @@ SIGNATURES = {
     "lzkp_circuit_load": (_int, [_vp, _u32, _u32, _u32] + [_vp] * 9),
     "lzkp_circuit_builtin": (_int, [_vp, _int, _u32]),
     "lzkp_builtin_circuit_csr": (_int, [_int, _u32, C.POINTER(_u64), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    "lzkp_key_sizes": (_int, [_u32, _u32, _u32, C.POINTER(_sz), C.POINTER(_sz)]),
+    "lzkp_setup": (_int, [_u32, _u32, _u32] + [_vp] * 9 + [_vp, _vp, _sz, _vp, _sz]),
+    "lzkp_setup_builtin": (_int, [_int, _u32, _vp, _vp, _sz, _vp, _sz]),
     "lzkp_prove_batch": (_int, [_vp, _sz, _vp, _vp, _vp, _vp, _vp]),
     "lzkp_prove_equality_batch": (_int, [_vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lzkp_prove_membership_batch": (_int, [_vp, _sz, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),

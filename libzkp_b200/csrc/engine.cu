@@ -17,6 +17,7 @@
 #include "kernels_prove.cuh"
 #include "tables.h"
 #include "large.h"
+#include "setup.h"
 
 using namespace lzkp;
 using namespace lzkp::eng;
@@ -26,6 +27,7 @@ static thread_local std::string g_err;
 static std::mutex g_mu;
 static int g_device = -1;
 static bool g_mimc_uploaded = false;
+static std::atomic<int> g_profile{0};
 
 namespace lzkp {
 namespace eng {
@@ -112,7 +114,13 @@ struct lzkp_pk {
     DBuf ws_z, ws_abc, ws_h, ws_dig, ws_r, ws_s, ws_rs, ws_part1, ws_part2, ws_res1, ws_res2, ws_proofs, ws_status,
         ws_a, ws_b, ws_commit, ws_sets, ws_setlen;
     cudaStream_t stream = nullptr;
+    // optional per-region CUDA-event timing (lzkp_profile_*): pairs recorded on the launching stream
+    struct Mark { int region; cudaEvent_t a, b; };
+    std::vector<Mark> marks;
+    double prof_ms[LZKP_PROFILE_REGIONS] = {0};
+    uint64_t prof_count[LZKP_PROFILE_REGIONS] = {0};
     ~lzkp_pk() {
+        for (auto &m : marks) { cudaEventDestroy(m.a); cudaEventDestroy(m.b); }
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -402,10 +410,25 @@ static int ensure_workspace(lzkp_pk *pk, uint32_t P) {
     return LZKP_OK;
 }
 
+struct Region {           // RAII: brackets the kernels of one pipeline stage with two events when profiling is on
+    lzkp_pk *pk;
+    cudaStream_t st;
+    cudaEvent_t b = nullptr;
+    Region(lzkp_pk *pk_, int region, cudaStream_t st_) : pk(pk_), st(st_) {
+        if (!g_profile.load(std::memory_order_relaxed) || pk->marks.size() > 65536) return;
+        cudaEvent_t a;
+        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { b = nullptr; return; }
+        cudaEventRecord(a, st);
+        pk->marks.push_back({region, a, b});
+    }
+    ~Region() { if (b) cudaEventRecord(b, st); }
+};
+
 // Witness map on P assignments already in ws_z (canonical): fills ws_h (canonical).
 static int run_witness_map(lzkp_pk *pk, uint32_t P, cudaStream_t st) {
     const uint32_t n = pk->n, threads = std::max(32u, std::min(n / 2, 512u));
     const size_t smem = (size_t)32 * n;
+    Region reg(pk, LZKP_REGION_WITNESS_MAP, st);
     LAUNCH(k_spmv_abc, dim3((n + 127) / 128, P), 128, 0, st, pk->csr[0], pk->csr[1], pk->csr[2], pk->ws_z.as<Fr>(),
            pk->ws_abc.as<Fr>(), P, pk->n_vars, pk->m, pk->n_inst, n);
     LAUNCH(k_ntt_icoset, dim3(P, 3), threads, smem, st, pk->ws_abc.as<Fr>(), pk->ntt, P, pk->log_n);
@@ -419,20 +442,24 @@ static int run_prove(lzkp_pk *pk, uint32_t P, const Fr *d_r, const Fr *d_s, uint
     TRY(run_witness_map(pk, P, st));
     const uint32_t c = pk->c, W = pk->W, gx = (P + 127) / 128;
     int16_t *dig = pk->ws_dig.as<int16_t>();
+    {
+    Region reg(pk, LZKP_REGION_DIGITS, st);
     LAUNCH(k_fr_mul_canonical, gx, 128, 0, st, d_r, d_s, pk->ws_rs.as<Fr>(), P);
     LAUNCH(k_digits, dim3(gx, pk->nz), 128, 0, st, pk->ws_z.as<Fr>(), pk->n_vars, 1u, dig, 0u, P, c, W, d_status);
     LAUNCH(k_digits, dim3(gx, 1), 128, 0, st, d_r, 1u, 0u, dig, pk->nz, P, c, W, d_status);
     LAUNCH(k_digits, dim3(gx, 1), 128, 0, st, d_s, 1u, 0u, dig, pk->nz + 1, P, c, W, d_status);
     LAUNCH(k_digits, dim3(gx, 1), 128, 0, st, pk->ws_rs.as<Fr>(), 1u, 0u, dig, pk->nz + 2, P, c, W, d_status);
     LAUNCH(k_digits, dim3(gx, pk->n - 1), 128, 0, st, pk->ws_h.as<Fr>(), pk->n, 0u, dig, pk->nz + 3, P, c, W, d_status);
+    }
     // item granularity: enough blocks to fill 148 SMs even for small batches
     int v = item_variant(P);
     auto args = [&](MsmPlan &pl, void *partial, void *out) {
         return BatchMsmArgs{pl.table.p, pk->N, pl.unit_dig.as<uint32_t>(), pl.unit_tbl.as<uint32_t>(), pl.items[v].p,
                             pl.n_items[v], pl.msm_items[v].p, pl.n_msm, dig, P, partial, out};
     };
-    batch_msm_g1(args(pk->g1, pk->ws_part1.p, pk->ws_res1.p), st);
-    batch_msm_g2(args(pk->g2, pk->ws_part2.p, pk->ws_res2.p), st);
+    { Region reg(pk, LZKP_REGION_MSM_G1, st); batch_msm_g1(args(pk->g1, pk->ws_part1.p, pk->ws_res1.p), st); }
+    { Region reg(pk, LZKP_REGION_MSM_G2, st); batch_msm_g2(args(pk->g2, pk->ws_part2.p, pk->ws_res2.p), st); }
+    Region reg(pk, LZKP_REGION_ASSEMBLE, st);
     LAUNCH(k_assemble, (P + 63) / 64, 64, 0, st, pk->ws_res1.as<G1XYZZ>(), pk->ws_res2.as<G2XYZZ>(), pk->consts, d_r, d_s,
            P, d_proofs);
     return LZKP_OK;
@@ -487,6 +514,32 @@ int lzkp_init(const int *devices, int n_devices) {
 int lzkp_shutdown(void) { return LZKP_OK; }
 const char *lzkp_last_error(void) { return g_err.c_str(); }
 uint64_t lzkp_kernel_launches(void) { return g_launches.load(); }
+
+int lzkp_profile_enable(int on) {
+    g_profile.store(on ? 1 : 0);
+    return LZKP_OK;
+}
+int lzkp_profile_read(lzkp_pk *pk, double ms[LZKP_PROFILE_REGIONS], uint64_t count[LZKP_PROFILE_REGIONS], int reset) {
+    if (!pk || !ms || !count) return fail(LZKP_E_INVALID, "null argument");
+    TRY(ensure_device());
+    std::lock_guard<std::mutex> lk(pk->mu);
+    for (auto &m : pk->marks) {
+        float t = 0;
+        CUDA_TRY(cudaEventSynchronize(m.b));
+        CUDA_TRY(cudaEventElapsedTime(&t, m.a, m.b));
+        pk->prof_ms[m.region] += t;
+        pk->prof_count[m.region]++;
+        cudaEventDestroy(m.a);
+        cudaEventDestroy(m.b);
+    }
+    pk->marks.clear();
+    for (int i = 0; i < LZKP_PROFILE_REGIONS; i++) {
+        ms[i] = pk->prof_ms[i];
+        count[i] = pk->prof_count[i];
+        if (reset) { pk->prof_ms[i] = 0; pk->prof_count[i] = 0; }
+    }
+    return LZKP_OK;
+}
 
 int lzkp_pk_load_ex(const uint8_t *pk_bytes, size_t len, int validate, const lzkp_pk_options *opt, lzkp_pk **out) {
     if (!pk_bytes || !out) return fail(LZKP_E_INVALID, "null argument");
@@ -566,6 +619,54 @@ int lzkp_builtin_circuit_csr(int kind, uint32_t param, uint64_t shape[6], uint32
     return LZKP_OK;
 }
 
+int lzkp_key_sizes(uint32_t m, uint32_t n_inst, uint32_t n_wit, size_t *pk_len, size_t *vk_len) {
+    if (!pk_len || !vk_len || n_inst < 1) return fail(LZKP_E_INVALID, "bad argument");
+    uint64_t need = (uint64_t)m + n_inst, n = 2;
+    while (n < need) n <<= 1;
+    const size_t nv = (size_t)n_inst + n_wit;
+    *vk_len = 64 + 3 * 128 + 8 + 64 * (size_t)n_inst;
+    *pk_len = *vk_len + 128 + 5 * 8 + 64 * (2 * nv + (n - 1) + n_wit) + 128 * nv;
+    return LZKP_OK;
+}
+static int setup_common(uint32_t m, uint32_t n_inst, uint32_t n_wit, const uint32_t *const rp[3],
+                        const uint32_t *const cl[3], const uint8_t *const vl[3], const uint8_t *toxic, uint8_t *pk_out,
+                        size_t pk_cap, uint8_t *vk_out, size_t vk_cap) {
+    if (!toxic || !pk_out || !vk_out) return fail(LZKP_E_INVALID, "null argument");
+    size_t pl, vl_;
+    TRY(lzkp_key_sizes(m, n_inst, n_wit, &pl, &vl_));
+    if (pk_cap < pl || vk_cap < vl_) return fail(LZKP_E_INVALID, "setup: output buffer too small (see lzkp_key_sizes)");
+    TRY(ensure_device());
+    std::vector<uint8_t> pk, vk;
+    TRY(setup_run(m, n_inst, n_wit, rp, cl, vl, toxic, pk, vk));
+    if (pk.size() != pl || vk.size() != vl_) return fail(LZKP_E_STATE, "setup: size mismatch");
+    memcpy(pk_out, pk.data(), pl);
+    memcpy(vk_out, vk.data(), vl_);
+    return LZKP_OK;
+}
+int lzkp_setup(uint32_t m, uint32_t n_inst, uint32_t n_wit, const uint32_t *a_rowptr, const uint32_t *a_col,
+               const uint8_t *a_val, const uint32_t *b_rowptr, const uint32_t *b_col, const uint8_t *b_val,
+               const uint32_t *c_rowptr, const uint32_t *c_col, const uint8_t *c_val, const uint8_t toxic[160],
+               uint8_t *pk_out, size_t pk_cap, uint8_t *vk_out, size_t vk_cap) {
+    if (!a_rowptr || !b_rowptr || !c_rowptr) return fail(LZKP_E_INVALID, "null argument");
+    const uint32_t *rp[3] = {a_rowptr, b_rowptr, c_rowptr}, *cl[3] = {a_col, b_col, c_col};
+    const uint8_t *vl[3] = {a_val, b_val, c_val};
+    return setup_common(m, n_inst, n_wit, rp, cl, vl, toxic, pk_out, pk_cap, vk_out, vk_cap);
+}
+int lzkp_setup_builtin(int kind, uint32_t param, const uint8_t toxic[160], uint8_t *pk_out, size_t pk_cap,
+                       uint8_t *vk_out, size_t vk_cap) {
+    if ((kind != LZKP_CIRCUIT_EQUALITY && kind != LZKP_CIRCUIT_MEMBERSHIP) || param == 0)
+        return fail(LZKP_E_INVALID, "bad circuit kind / parameter");
+    host::R1cs cs = synth(kind, param);
+    const host::Csr *M[3] = {&cs.A, &cs.B, &cs.C};
+    const uint32_t *rp[3], *cl[3];
+    const uint8_t *vl[3];
+    for (int k = 0; k < 3; k++) {
+        rp[k] = M[k]->rowptr.data(); cl[k] = M[k]->col.data();
+        vl[k] = reinterpret_cast<const uint8_t *>(M[k]->val.data());
+    }
+    return setup_common(cs.m, cs.n_inst, cs.n_wit, rp, cl, vl, toxic, pk_out, pk_cap, vk_out, vk_cap);
+}
+
 int lzkp_prove_batch(lzkp_pk *pk, size_t n_proofs, const uint8_t *z, const uint8_t *r, const uint8_t *s,
                      uint8_t *proofs_out, int32_t *status) {
     if (!pk || (n_proofs && (!z || !r || !s || !proofs_out || !status))) return fail(LZKP_E_INVALID, "null argument");
@@ -608,9 +709,10 @@ int lzkp_prove_equality_batch(lzkp_pk *pk, size_t n_proofs, const uint64_t *a, c
         CUDA_TRY(cudaMemcpyAsync(pk->ws_s.p, s + off * 32, (size_t)P * 32, cudaMemcpyHostToDevice, st));
         if (commitments) CUDA_TRY(cudaMemcpyAsync(pk->ws_commit.p, commitments + off * 32, (size_t)P * 32, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemsetAsync(pk->ws_status.p, 0, (size_t)P * 4, st));
+        { Region reg(pk, LZKP_REGION_WITGEN, st);
         LAUNCH(k_witgen_equality, (P + 127) / 128, 128, 0, st, pk->ws_a.as<uint64_t>(), pk->ws_b.as<uint64_t>(),
                commitments ? pk->ws_commit.as<Fr>() : nullptr, pk->ws_z.as<Fr>(), pk->ws_commit.as<Fr>(),
-               pk->ws_status.as<int32_t>(), P, pk->kind_param, pk->n_vars);
+               pk->ws_status.as<int32_t>(), P, pk->kind_param, pk->n_vars); }
         TRY(run_prove(pk, P, pk->ws_r.as<Fr>(), pk->ws_s.as<Fr>(), pk->ws_proofs.as<uint8_t>(), pk->ws_status.as<int32_t>(), st));
         CUDA_TRY(cudaMemcpyAsync(proofs_out + off * 256, pk->ws_proofs.p, (size_t)P * 256, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaMemcpyAsync(status + off, pk->ws_status.p, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
@@ -670,8 +772,9 @@ int lzkp_prove_equality_batch_device(lzkp_pk *pk, size_t n_proofs, const void *d
         TRY(ensure_workspace(pk, P));
         int32_t *stat = (int32_t *)d_status + off;
         CUDA_TRY(cudaMemsetAsync(stat, 0, (size_t)P * 4, st));
+        { Region reg(pk, LZKP_REGION_WITGEN, st);
         LAUNCH(k_witgen_equality, (P + 127) / 128, 128, 0, st, (const uint64_t *)d_a + off, (const uint64_t *)d_b + off,
-               (const Fr *)nullptr, pk->ws_z.as<Fr>(), pk->ws_commit.as<Fr>(), stat, P, pk->kind_param, pk->n_vars);
+               (const Fr *)nullptr, pk->ws_z.as<Fr>(), pk->ws_commit.as<Fr>(), stat, P, pk->kind_param, pk->n_vars); }
         TRY(run_prove(pk, P, (const Fr *)d_r + off, (const Fr *)d_s + off, (uint8_t *)d_proofs + off * 256, stat, st));
     }
     CUDA_TRY(cudaGetLastError());

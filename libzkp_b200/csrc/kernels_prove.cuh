@@ -295,27 +295,9 @@ __global__ void __launch_bounds__(128) k_digits(const Fr *scalars, uint32_t stri
         s = Fr::zero();
     }
     uint32_t v[10];
-    uint64_t carry = 0;
-#pragma unroll
-    for (int i = 0; i < 9; i++) {
-        // limb i of K: bits (c*w + c - 1) that fall into [32i, 32i+32)
-        uint32_t kl = 0;
-        for (uint32_t w = 0; w < W; w++) {
-            uint32_t bit = c * w + c - 1;
-            if ((bit >> 5) == (uint32_t)i) kl |= 1u << (bit & 31);
-        }
-        uint64_t t = (uint64_t)(i < 8 ? s.l[i] : 0u) + kl + carry;
-        v[i] = (uint32_t)t;
-        carry = t >> 32;
-    }
-    v[9] = 0;
+    recode_offset(s, c, W, v);
     const size_t base = ((size_t)(row0 + j) * W) * P + p;
-    for (uint32_t w = 0; w < W; w++) {
-        uint32_t bit = c * w, li = bit >> 5, sh = bit & 31;
-        uint64_t two = ((uint64_t)v[li + 1] << 32) | v[li];
-        uint32_t u = (uint32_t)(two >> sh) & ((1u << c) - 1u);
-        dig[base + (size_t)w * P] = (int16_t)((int32_t)u - (int32_t)(1u << (c - 1)));
-    }
+    for (uint32_t w = 0; w < W; w++) dig[base + (size_t)w * P] = (int16_t)recoded_digit(v, c, w);
 }
 // rs[p] = r[p] * s[p] mod r, canonical in / out
 __global__ void k_fr_mul_canonical(const Fr *r, const Fr *s, Fr *rs, uint32_t P) {

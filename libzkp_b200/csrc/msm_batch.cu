@@ -11,13 +11,6 @@ namespace lzkp {
 // contiguous run of units of one MSM.  Thread (p, item) gathers table[unit][|d|-1] for its proof's
 // digit d of every unit in the item and accumulates in XYZZ.  Lanes of a warp are 32 different proofs
 // walking the same units, so a warp-step touches one N*sizeof(point) slab (2 MiB for G1 at c=16).
-template <class F>
-__device__ __forceinline__ Affine<F> gather_point(const Affine<F> *table, uint32_t N, uint32_t tbl_unit, int d) {
-    int mag = d < 0 ? -d : d;
-    Affine<F> pt = ldg_vec(table + (size_t)tbl_unit * N + (uint32_t)(mag - 1));
-    if (d < 0) pt.y = pt.y.neg();
-    return pt;
-}
 template <class F, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_msm_batch(const Affine<F> *__restrict__ table, uint32_t N,
                                                      const uint32_t *__restrict__ unit_dig,

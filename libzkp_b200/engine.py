@@ -37,6 +37,10 @@ def init(device: Optional[int] = None) -> None:
         check(lib().lzkp_init(arr, 1))
 
 
+def profile_enable(on: bool) -> None:
+    check(lib().lzkp_profile_enable(int(on)))
+
+
 def kernel_launches() -> int:
     return int(lib().lzkp_kernel_launches())
 
@@ -60,6 +64,40 @@ def builtin_circuit_csr(kind: int, param: int):
     vl = (C.c_void_p * 3)(*[m_[2].ctypes.data for m_ in mats])
     check(lib().lzkp_builtin_circuit_csr(kind, param, shape, rp, cl, vl))
     return (m, n_inst, n_wit), mats
+
+
+def key_sizes(m: int, n_inst: int, n_wit: int) -> Tuple[int, int]:
+    pl, vl = C.c_size_t(), C.c_size_t()
+    check(lib().lzkp_key_sizes(m, n_inst, n_wit, C.byref(pl), C.byref(vl)))
+    return int(pl.value), int(vl.value)
+
+
+def _toxic(toxic: Sequence[int]) -> np.ndarray:
+    if len(toxic) != 5:
+        raise ValueError("toxic waste = (alpha, beta, gamma, delta, tau)")
+    return np.frombuffer(b"".join(int(t).to_bytes(32, "little") for t in toxic), np.uint8).copy()
+
+
+def setup_builtin(kind: int, param: int, toxic: Sequence[int]) -> Tuple[bytes, bytes]:
+    """circuit_specific_setup for a builtin circuit on the device -> (pk_bytes, vk_bytes), ark layout."""
+    (m, n_inst, n_wit), _ = builtin_circuit_csr(kind, param)
+    pl, vl = key_sizes(m, n_inst, n_wit)
+    pk, vk, tx = np.zeros(pl, np.uint8), np.zeros(vl, np.uint8), _toxic(toxic)
+    check(lib().lzkp_setup_builtin(kind, param, _p(tx), _p(pk), pl, _p(vk), vl))
+    return pk.tobytes(), vk.tobytes()
+
+
+def setup(m: int, n_inst: int, n_wit: int, mats, toxic: Sequence[int]) -> Tuple[bytes, bytes]:
+    pl, vl = key_sizes(m, n_inst, n_wit)
+    pk, vk, tx = np.zeros(pl, np.uint8), np.zeros(vl, np.uint8), _toxic(toxic)
+    flat, keep = [], []
+    for rowptr, col, val in mats:
+        arrs = [np.ascontiguousarray(rowptr, np.uint32), np.ascontiguousarray(col, np.uint32),
+                np.ascontiguousarray(val, np.uint8)]
+        keep += arrs
+        flat += [_p(a) for a in arrs]
+    check(lib().lzkp_setup(m, n_inst, n_wit, *flat, _p(tx), _p(pk), pl, _p(vk), vl))
+    return pk.tobytes(), vk.tobytes()
 
 
 class ProvingKey:
@@ -87,6 +125,14 @@ class ProvingKey:
             self.close()
         except Exception:
             pass
+
+    REGIONS = ("witgen", "witness_map", "digits", "msm_g1", "msm_g2", "assemble")
+
+    def profile_read(self, reset: bool = True):
+        """Accumulated device milliseconds / bracket counts per pipeline stage (lzkp_profile_read)."""
+        ms, cnt = (C.c_double * 8)(), (C.c_uint64 * 8)()
+        check(lib().lzkp_profile_read(self._h, ms, cnt, int(reset)))
+        return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(self.REGIONS)}
 
     # ---- circuit binding
     def circuit_builtin(self, kind: int, param: int) -> "ProvingKey":

@@ -248,3 +248,30 @@ def test_window_sizes_agree(eq_keys, co, frs):
         proofs, _, status = pk.prove_equality_batch(a, a, r, s)
         pk.close()
         assert not status.any() and np.array_equal(proofs, want), f"c={c}"
+
+
+def test_device_setup_bit_exact(eq_keys, mb_keys, trapdoor, golden):
+    # lzkp_setup_builtin (device fixed-base multiplications) == the oracle's generate_parameters
+    pk, vk = engine.setup_builtin(engine.EQUALITY, 110, trapdoor)
+    assert hashlib.sha256(pk).hexdigest() == golden["equality"]["pk_sha256"]
+    assert pk == eq_keys.pk_bytes and vk == eq_keys.vk_bytes
+    pk, vk = engine.setup_builtin(engine.MEMBERSHIP, 64, trapdoor)
+    assert pk == mb_keys.pk_bytes and vk == mb_keys.vk_bytes
+
+
+def test_device_setup_generic_csr_and_default_keygen(eq_keys, trapdoor, po):
+    (m, n_inst, n_wit), mats = engine.builtin_circuit_csr(engine.EQUALITY, 110)
+    pk, vk = engine.setup(m, n_inst, n_wit, mats, trapdoor)
+    assert pk == eq_keys.pk_bytes and vk == eq_keys.vk_bytes
+    # default key generation (OsRng toxic waste) yields a key whose proofs verify
+    snark.reset()
+    snark.configure(window_bits=WINDOW_BITS)
+    try:
+        proof = zk.prove_equality(9, 9)
+        setup = zk.SnarkBackend.get_universal_setup()
+        p = zk.Proof.from_bytes(proof)
+        assert po.verify(po.vk_from_bytes(setup.vk_bytes),
+                         po.equality_public_inputs(int.from_bytes(p.commitment, "little")), po.proof_from_bytes(p.proof))
+    finally:
+        snark.reset()
+        snark.configure()
