@@ -117,6 +117,10 @@ int lzkp_setup(uint32_t m, uint32_t n_inst, uint32_t n_wit,
 int lzkp_setup_builtin(int kind, uint32_t param, const uint8_t toxic[160], uint8_t *pk_out, size_t pk_cap,
                        uint8_t *vk_out, size_t vk_cap);
 
+/* out[i] = scalars[i] * G for the standard generator of group 1 (G1, 64 B) or 2 (G2, 128 B): the fixed-base
+ * primitive of the setup, also used to make synthetic MSM bases. */
+int lzkp_generator_mul(int group, const uint8_t *scalars, size_t n, uint8_t *out_affine);
+
 /* n_proofs proofs from full assignments: z is n_proofs x n_vars x 32 B (z[0] = 1), r and s are
  * n_proofs x 32 B, proofs_out n_proofs x 256 B, status n_proofs ints (0 = ok). */
 int lzkp_prove_batch(lzkp_pk *pk, size_t n_proofs, const uint8_t *z, const uint8_t *r, const uint8_t *s,
@@ -144,8 +148,25 @@ int lzkp_witness_map(lzkp_pk *pk, size_t n_proofs, const uint8_t *z, uint8_t *h_
 /* Variable-base MSM over arbitrary bases (ark affine uncompressed) and canonical scalars. */
 int lzkp_msm_g1(const uint8_t *bases_affine, const uint8_t *scalars, size_t n, uint8_t *out_affine);
 int lzkp_msm_g2(const uint8_t *bases_affine, const uint8_t *scalars, size_t n, uint8_t *out_affine);
+/* MSM bases kept resident in HBM (what the prover does with the proving key's query vectors): upload once,
+ * then run any number of MSMs against them.  group: 1 = G1 (64 B points), 2 = G2 (128 B).  window_bits in
+ * [8,16], 0 = 16.  resident_windows != 0 also stores 2^(c*w) * P for every window w (W x the memory) so that
+ * all windows share one bucket set.  validate != 0 checks that every point is on the curve. */
+typedef struct lzkp_bases lzkp_bases;
+int lzkp_bases_load(int group, const uint8_t *bases_affine, size_t n, int window_bits, int resident_windows,
+                    int validate, lzkp_bases **out);
+void lzkp_bases_free(lzkp_bases *b);
+/* sum_{i<n} scalars[i] * base[i], n <= number of loaded bases; out_affine is 64 / 128 B. */
+int lzkp_msm(lzkp_bases *b, const uint8_t *scalars, size_t n, uint8_t *out_affine);
+/* Same with the scalars (n x 32 B canonical) and the output bytes in device memory; asynchronous on `stream`. */
+int lzkp_msm_device(lzkp_bases *b, const void *d_scalars, size_t n, void *d_out_affine, void *stream);
+
 /* In-place radix-2 (i)NTT over Fr on 2^log_n canonical elements, optionally on the coset 5*H. */
 int lzkp_ntt(uint8_t *data, uint32_t log_n, int inverse, int coset);
+/* Same transform on device buffers of 2^log_n x 32 B, asynchronous on `stream`: the result is written to
+ * d_out; d_in is used as workspace (clobbered) when log_n > 11.  Elements keep the caller's representation
+ * (canonical in -> canonical out, Montgomery in -> Montgomery out). */
+int lzkp_ntt_device(void *d_in, void *d_out, uint32_t log_n, int inverse, int coset, void *stream);
 
 /* MiMC-5 commitment of a u64 (commit_value_snark), 32 B canonical LE.  Host arithmetic, no device. */
 int lzkp_commit_value_snark(uint64_t value, uint8_t out[32]);

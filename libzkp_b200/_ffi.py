@@ -47,6 +47,7 @@ SIGNATURES = {
     "lzkp_key_sizes": (_int, [_u32, _u32, _u32, C.POINTER(_sz), C.POINTER(_sz)]),
     "lzkp_setup": (_int, [_u32, _u32, _u32] + [_vp] * 9 + [_vp, _vp, _sz, _vp, _sz]),
     "lzkp_setup_builtin": (_int, [_int, _u32, _vp, _vp, _sz, _vp, _sz]),
+    "lzkp_generator_mul": (_int, [_int, _vp, _sz, _vp]),
     "lzkp_prove_batch": (_int, [_vp, _sz, _vp, _vp, _vp, _vp, _vp]),
     "lzkp_prove_equality_batch": (_int, [_vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lzkp_prove_membership_batch": (_int, [_vp, _sz, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -54,7 +55,12 @@ SIGNATURES = {
     "lzkp_witness_map": (_int, [_vp, _sz, _vp, _vp]),
     "lzkp_msm_g1": (_int, [_vp, _vp, _sz, _vp]),
     "lzkp_msm_g2": (_int, [_vp, _vp, _sz, _vp]),
+    "lzkp_bases_load": (_int, [_int, _vp, _sz, _int, _int, _int, C.POINTER(_vp)]),
+    "lzkp_bases_free": (None, [_vp]),
+    "lzkp_msm": (_int, [_vp, _vp, _sz, _vp]),
+    "lzkp_msm_device": (_int, [_vp, _vp, _sz, _vp, _vp]),
     "lzkp_ntt": (_int, [_vp, _u32, _int, _int]),
+    "lzkp_ntt_device": (_int, [_vp, _vp, _u32, _int, _int, _vp]),
     "lzkp_commit_value_snark": (_int, [_u64, _vp]),
 }
 

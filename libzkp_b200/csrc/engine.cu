@@ -667,6 +667,11 @@ int lzkp_setup_builtin(int kind, uint32_t param, const uint8_t toxic[160], uint8
     return setup_common(cs.m, cs.n_inst, cs.n_wit, rp, cl, vl, toxic, pk_out, pk_cap, vk_out, vk_cap);
 }
 
+int lzkp_generator_mul(int group, const uint8_t *scalars, size_t n, uint8_t *out_affine) {
+    if ((group != 1 && group != 2) || (n && (!scalars || !out_affine))) return fail(LZKP_E_INVALID, "bad argument");
+    return generator_mul(group, scalars, n, out_affine);
+}
+
 int lzkp_prove_batch(lzkp_pk *pk, size_t n_proofs, const uint8_t *z, const uint8_t *r, const uint8_t *s,
                      uint8_t *proofs_out, int32_t *status) {
     if (!pk || (n_proofs && (!z || !r || !s || !proofs_out || !status))) return fail(LZKP_E_INVALID, "null argument");
@@ -810,11 +815,46 @@ int lzkp_msm_g2(const uint8_t *bases_affine, const uint8_t *scalars, size_t n, u
     TRY(ensure_device());
     return large_msm_g2_host(bases_affine, scalars, n, out_affine);
 }
+struct lzkp_bases { MsmBases *b; };
+int lzkp_bases_load(int group, const uint8_t *bases_affine, size_t n, int window_bits, int resident_windows,
+                    int validate, lzkp_bases **out) {
+    if (!out || (group != 1 && group != 2) || (n && !bases_affine)) return fail(LZKP_E_INVALID, "bad argument");
+    *out = nullptr;
+    TRY(ensure_device());
+    MsmBases *b = nullptr;
+    TRY(msm_bases_load(group, bases_affine, n, window_bits, resident_windows, validate, &b));
+    *out = new lzkp_bases{b};
+    return LZKP_OK;
+}
+void lzkp_bases_free(lzkp_bases *b) {
+    if (!b) return;
+    if (g_device >= 0) cudaSetDevice(g_device);
+    msm_bases_free(b->b);
+    delete b;
+}
+int lzkp_msm(lzkp_bases *b, const uint8_t *scalars, size_t n, uint8_t *out_affine) {
+    if (!b || !out_affine || (n && !scalars)) return fail(LZKP_E_INVALID, "null argument");
+    TRY(ensure_device());
+    return msm_host(b->b, scalars, n, out_affine);
+}
+int lzkp_msm_device(lzkp_bases *b, const void *d_scalars, size_t n, void *d_out_affine, void *stream) {
+    if (!b || !d_out_affine || (n && !d_scalars)) return fail(LZKP_E_INVALID, "null argument");
+    TRY(ensure_device());
+    return msm_device(b->b, d_scalars, n, d_out_affine, (cudaStream_t)stream);
+}
+
 int lzkp_ntt(uint8_t *data, uint32_t log_n, int inverse, int coset) {
     if (!data || log_n > 28) return fail(LZKP_E_INVALID, "bad argument");
     TRY(ensure_device());
-    if (log_n <= 12) return small_ntt_host(data, log_n, inverse, coset);
+    if (log_n <= 12 && !getenv("LZKP_NTT_FORCE_TILED")) return small_ntt_host(data, log_n, inverse, coset);
     return large_ntt_host(data, log_n, inverse, coset);
+}
+
+int lzkp_ntt_device(void *d_in, void *d_out, uint32_t log_n, int inverse, int coset, void *stream) {
+    if (!d_in || !d_out || log_n > 28) return fail(LZKP_E_INVALID, "bad argument");
+    if (log_n > 11 && d_in == d_out) return fail(LZKP_E_INVALID, "lzkp_ntt_device: d_out must differ from d_in above 2^11");
+    TRY(ensure_device());
+    return large_ntt_device(d_in, d_out, log_n, inverse, coset, (cudaStream_t)stream);
 }
 
 int lzkp_commit_value_snark(uint64_t value, uint8_t out[32]) {

@@ -12,6 +12,7 @@
 // multiplication of a generator, done as W table gathers + XYZZ mixed adds per scalar.
 #include <algorithm>
 #include <cstring>
+#include <mutex>
 
 #include "host_util.h"
 #include "setup.h"
@@ -54,6 +55,72 @@ void put_u64(std::vector<uint8_t> &o, uint64_t v) {
     for (int i = 0; i < 8; i++) o.push_back((uint8_t)(v >> (8 * i)));
 }
 }  // namespace
+
+namespace {
+struct GenTables {
+    DBuf t1, t2;
+    static constexpr int c = 16;
+    static constexpr uint32_t W = 16, N = 32768;
+};
+// window tables of the standard generators (built on first use, kept for the process lifetime)
+int gen_tables(GenTables **out, int need_g2) {
+    static GenTables *T = nullptr;
+    static bool have2 = false;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!T) {
+        GenTables *t = new GenTables();
+        host::G1Canon g1c;
+        g1c.x = Fq::zero(); g1c.y = Fq::zero();
+        g1c.x.l[0] = 1; g1c.y.l[0] = 2;                                 // G1 generator (1, 2)
+        G1Affine g1m{Fq::from_canonical(g1c.x), Fq::from_canonical(g1c.y)};
+        DBuf d_g1;
+        TRY(d_g1.alloc(sizeof(g1m)));
+        CUDA_TRY(cudaMemcpy(d_g1.p, &g1m, sizeof(g1m), cudaMemcpyHostToDevice));
+        TRY(t->t1.alloc((size_t)GenTables::W * GenTables::N * sizeof(G1Affine)));
+        TRY(build_table_g1(d_g1.p, 1, GenTables::c, GenTables::W, GenTables::N, t->t1.p, nullptr));
+        T = t;
+    }
+    if (need_g2 && !have2) {
+        host::G2Canon g2c;
+        for (int i = 0; i < 8; i++) {
+            g2c.x0.l[i] = FqParams::G2X0(i); g2c.x1.l[i] = FqParams::G2X1(i);
+            g2c.y0.l[i] = FqParams::G2Y0(i); g2c.y1.l[i] = FqParams::G2Y1(i);
+        }
+        G2Affine g2m{Fq2{Fq::from_canonical(g2c.x0), Fq::from_canonical(g2c.x1)},
+                     Fq2{Fq::from_canonical(g2c.y0), Fq::from_canonical(g2c.y1)}};
+        DBuf d_g2;
+        TRY(d_g2.alloc(sizeof(g2m)));
+        CUDA_TRY(cudaMemcpy(d_g2.p, &g2m, sizeof(g2m), cudaMemcpyHostToDevice));
+        TRY(T->t2.alloc((size_t)GenTables::W * GenTables::N * sizeof(G2Affine)));
+        TRY(build_table_g2(d_g2.p, 1, GenTables::c, GenTables::W, GenTables::N, T->t2.p, nullptr));
+        have2 = true;
+    }
+    *out = T;
+    return LZKP_OK;
+}
+}  // namespace
+
+// out[i] = scalars[i] * generator (ark-serialize affine bytes); scalars canonical, host buffers
+int generator_mul(int group, const uint8_t *scalars, size_t n, uint8_t *out) {
+    TRY(ensure_device());
+    GenTables *T;
+    TRY(gen_tables(&T, group == 2));
+    if (n == 0) return LZKP_OK;
+    const size_t pb = group == 1 ? 64 : 128;
+    DBuf d_s, d_o;
+    TRY(d_s.alloc(n * 32)); TRY(d_o.alloc(n * pb));
+    CUDA_TRY(cudaMemcpy(d_s.p, scalars, n * 32, cudaMemcpyHostToDevice));
+    if (group == 1)
+        LAUNCH((k_fixed_mul<Fq, 64>), (unsigned)((n + 127) / 128), 128, 0, 0, T->t1.as<G1Affine>(), GenTables::N,
+               (uint32_t)GenTables::c, GenTables::W, d_s.as<Fr>(), n, d_o.as<uint8_t>());
+    else
+        LAUNCH((k_fixed_mul<Fq2, 128>), (unsigned)((n + 127) / 128), 128, 0, 0, T->t2.as<G2Affine>(), GenTables::N,
+               (uint32_t)GenTables::c, GenTables::W, d_s.as<Fr>(), n, d_o.as<uint8_t>());
+    CUDA_TRY(cudaMemcpy(out, d_o.p, n * pb, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaGetLastError());
+    return LZKP_OK;
+}
 
 int setup_run(uint32_t m, uint32_t n_inst, uint32_t n_wit, const uint32_t *const rowptr[3],
               const uint32_t *const col[3], const uint8_t *const val[3], const uint8_t *toxic,
@@ -139,28 +206,13 @@ int setup_run(uint32_t m, uint32_t n_inst, uint32_t n_wit, const uint32_t *const
 
     // ---- device: generator tables + fixed-base multiplications
     TRY(ensure_device());
-    const int c = 16;
-    const uint32_t W = 16, N = 32768;
-    host::G1Canon g1c;
-    host::G2Canon g2c;
-    g1c.x = Fq::zero(); g1c.y = Fq::zero();
-    g1c.x.l[0] = 1; g1c.y.l[0] = 2;                                 // G1 generator (1, 2)
-    for (int i = 0; i < 8; i++) {
-        g2c.x0.l[i] = FqParams::G2X0(i); g2c.x1.l[i] = FqParams::G2X1(i);
-        g2c.y0.l[i] = FqParams::G2Y0(i); g2c.y1.l[i] = FqParams::G2Y1(i);
-    }
-    // canonical -> Montgomery on the host (12 field elements)
-    G1Affine g1m{Fq::from_canonical(g1c.x), Fq::from_canonical(g1c.y)};
-    G2Affine g2m{Fq2{Fq::from_canonical(g2c.x0), Fq::from_canonical(g2c.x1)},
-                 Fq2{Fq::from_canonical(g2c.y0), Fq::from_canonical(g2c.y1)}};
-    DBuf d_g1, d_g2, t1, t2, d_s1, d_s2, d_o1, d_o2;
-    TRY(d_g1.alloc(sizeof(g1m))); TRY(d_g2.alloc(sizeof(g2m)));
-    CUDA_TRY(cudaMemcpy(d_g1.p, &g1m, sizeof(g1m), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(d_g2.p, &g2m, sizeof(g2m), cudaMemcpyHostToDevice));
-    TRY(t1.alloc((size_t)W * N * sizeof(G1Affine))); TRY(t2.alloc((size_t)W * N * sizeof(G2Affine)));
+    GenTables *GT;
+    TRY(gen_tables(&GT, 1));
+    const int c = GenTables::c;
+    const uint32_t W = GenTables::W, N = GenTables::N;
+    DBuf &t1 = GT->t1, &t2 = GT->t2;
+    DBuf d_s1, d_s2, d_o1, d_o2;
     cudaStream_t st = nullptr;
-    TRY(build_table_g1(d_g1.p, 1, c, W, N, t1.p, st));
-    TRY(build_table_g2(d_g2.p, 1, c, W, N, t2.p, st));
     TRY(upload(d_s1, s1)); TRY(upload(d_s2, s2));
     TRY(d_o1.alloc(s1.size() * 64)); TRY(d_o2.alloc(s2.size() * 128));
     LAUNCH((k_fixed_mul<Fq, 64>), (unsigned)((s1.size() + 127) / 128), 128, 0, st, t1.as<G1Affine>(), N, (uint32_t)c, W,

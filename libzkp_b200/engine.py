@@ -228,3 +228,49 @@ def ntt(data, inverse: bool = False, coset: bool = False) -> np.ndarray:
         raise ValueError("NTT size must be a power of two")
     check(lib().lzkp_ntt(_p(a), log_n, int(inverse), int(coset)))
     return a
+
+
+def ntt_device(d_in: int, d_out: int, log_n: int, inverse: bool = False, coset: bool = False, stream: int = 0) -> None:
+    """lzkp_ntt_device on raw device pointers (asynchronous on `stream`); d_in is clobbered above 2^11."""
+    check(lib().lzkp_ntt_device(d_in, d_out, log_n, int(inverse), int(coset), stream))
+
+
+class MsmBases:
+    """MSM bases resident in HBM (lzkp_bases): group 1 = G1, 2 = G2."""
+
+    def __init__(self, group: int, bases, window_bits: int = 0, resident_windows: bool = True, validate: bool = False):
+        self.group = group
+        self.point_bytes = 64 if group == 1 else 128
+        bases = _u8(bases, self.point_bytes)
+        self.n = bases.shape[0]
+        self._h = C.c_void_p()
+        check(lib().lzkp_bases_load(group, _p(bases), self.n, window_bits, int(resident_windows), int(validate),
+                                    C.byref(self._h)))
+
+    def msm(self, scalars) -> bytes:
+        scalars = _u8(scalars, 32)
+        out = np.zeros(self.point_bytes, np.uint8)
+        check(lib().lzkp_msm(self._h, _p(scalars), scalars.shape[0], _p(out)))
+        return out.tobytes()
+
+    def msm_device(self, d_scalars: int, n: int, d_out: int, stream: int = 0) -> None:
+        check(lib().lzkp_msm_device(self._h, d_scalars, n, d_out, stream))
+
+    def close(self):
+        if self._h:
+            lib().lzkp_bases_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def generator_mul(group: int, scalars) -> np.ndarray:
+    """scalars[i] * G (standard generator of G1 / G2) as ark-serialize affine bytes."""
+    scalars = _u8(scalars, 32)
+    out = np.zeros((scalars.shape[0], 64 if group == 1 else 128), np.uint8)
+    check(lib().lzkp_generator_mul(group, _p(scalars), scalars.shape[0], _p(out)))
+    return out

@@ -95,14 +95,74 @@ def test_msm_witness_like_scalars(co, frs):
     assert engine.msm_g1(bases, sc) == co.msm_g1(bases, sc)
 
 
+def test_generator_mul_matches_oracle(co, frs):
+    ks = frs(9, 200)
+    ks[3] = 0
+    assert np.array_equal(engine.generator_mul(1, ks), co.g1_gen_mul(ks))
+    assert np.array_equal(engine.generator_mul(2, ks[:50]), co.g2_gen_mul(ks[:50]))
+
+
+@pytest.mark.parametrize("group,n,c", [(1, 3000, 16), (1, 3000, 11), (2, 700, 16), (1, 1, 16), (1, 40000, 13)])
+def test_resident_bases_msm(co, frs, group, n, c):
+    gen = co.g1_gen_mul if group == 1 else co.g2_gen_mul
+    ora = co.msm_g1 if group == 1 else co.msm_g2
+    small = frs(9, min(n, 4096))
+    pts = gen(small)
+    bases = np.concatenate([pts] * ((n + len(pts) - 1) // len(pts)))[:n]      # repeated points: P + P in a bucket
+    sc = frs(10, n)
+    B = engine.MsmBases(group, bases, window_bits=c, resident_windows=True, validate=True)
+    assert B.msm(sc) == ora(bases, sc)
+    sc2 = frs(11, n)
+    sc2[::3] = 0
+    assert B.msm(sc2) == ora(bases, sc2)                      # workspace reuse across calls
+    if n > 10:
+        assert B.msm(sc[: n // 2]) == ora(bases[: n // 2], sc[: n // 2])    # fewer scalars than bases (msm truncates)
+    B.close()
+
+
+def test_msm_skewed_scalars_long_runs(co, frs):
+    # half of the scalars equal 1 and a quarter equal r - 1: giant buckets, the k_long_run path
+    n = 1 << 16
+    pts = co.g1_gen_mul(frs(9, 2048))
+    bases = np.concatenate([pts] * (n // 2048))
+    sc = frs(10, n)
+    R = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+    sc[0::2] = np.frombuffer((1).to_bytes(32, "little"), np.uint8)
+    sc[1::4] = np.frombuffer((R - 1).to_bytes(32, "little"), np.uint8)
+    want = co.msm_g1(bases, sc)
+    for resident in (True, False):
+        B = engine.MsmBases(1, bases, resident_windows=resident)
+        assert B.msm(sc) == want
+        B.close()
+
+
+def test_msm_rejects_bad_input(co, frs):
+    bases = co.g1_gen_mul(frs(9, 16))
+    bad = bases.copy()
+    bad[3, 0] ^= 1                                            # off the curve
+    with pytest.raises(Exception):
+        engine.MsmBases(1, bad, validate=True)
+    B = engine.MsmBases(1, bases)
+    sc = frs(10, 16)
+    sc[5] = 0xFF                                              # >= r
+    with pytest.raises(Exception):
+        B.msm(sc)
+    B.close()
+
+
 def test_msm_2_20_trapdoor(co, po, frs):
-    # BASELINE size: bases k_i * G  =>  MSM == (sum k_i s_i) * G  (independent of any MSM code)
-    n = 1 << 20
-    ks, sc = frs(9, n), frs(10, n)
-    bases = co.g1_gen_mul(ks)
-    R = po.R_MOD
-    kk = np.frombuffer(ks.tobytes(), "<u8").reshape(n, 4)
-    tot = sum(k * s for k, s in zip(co.fr_list(ks), co.fr_list(sc))) % R
+    # BASELINE size.  Bases k_i * G with known k_i (2^14 distinct points tiled 64 times) =>
+    # MSM == (sum k_i s_i) * G: a check independent of any MSM code, resident and one-shot modes.
+    n, m = 1 << 20, 1 << 14
+    ks, sc = frs(9, m), frs(10, n)
+    pts = engine.generator_mul(1, ks)
+    assert np.array_equal(pts[:64], co.g1_gen_mul(ks[:64]))
+    bases = np.concatenate([pts] * (n // m))
+    kl, sl = co.fr_list(ks), co.fr_list(sc)
+    tot = sum(kl[i % m] * s for i, s in enumerate(sl)) % po.R_MOD
     want = po.g1_to_bytes(po.G1.mul(po.G1_GEN, tot))
+    B = engine.MsmBases(1, bases)
+    assert B.msm(sc) == want
+    B.close()
     assert engine.msm_g1(bases, sc) == want
     assert co.msm_g1(bases, sc) == want
