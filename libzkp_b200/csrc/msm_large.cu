@@ -33,6 +33,8 @@ namespace {
 
 constexpr uint32_t SENT = 0xFFFFFFFFu;
 constexpr int kChunk = 32;          // sorted pairs per thread in k_bucket_accum
+constexpr int kSeg = 8;             // partial slots per thread in k_seg_reduce
+constexpr int kSegLevels = 2;       // balanced partial-reduction passes before the final merge
 constexpr int kMergeCap = 48;       // partials merged serially before a run counts as "long"
 constexpr int kGroup = 16;          // buckets per running-sum group
 constexpr int kGroupLog = 4;
@@ -120,12 +122,61 @@ __global__ void __launch_bounds__(BLOCK) k_bucket_accum(const uint32_t *__restri
     }
 }
 
+// ---------------------------------------------------------------- 3b. balanced reduction of the partial sums
+// Same chunking one level up: every thread owns L consecutive partial slots (all lanes busy whatever the
+// run lengths), adds up equal keys, sends runs strictly inside its chunk to their bucket and re-emits its
+// first / last run as partials of the next level.  Each level shrinks the sequence by L / 2.
+__device__ __forceinline__ uint32_t level_slots(uint32_t M, uint32_t L1, uint32_t L2, uint32_t level) {
+    uint32_t n = 2u * ((M + L1 - 1) / L1);                 // level 1 output
+    for (uint32_t l = 1; l < level; l++) n = 2u * ((n + L2 - 1) / L2);
+    return n;
+}
+template <class F, int L>
+__global__ void __launch_bounds__(128) k_seg_reduce(const uint32_t *__restrict__ in_key, const XYZZ<F> *__restrict__ in_pt,
+                                                    const uint32_t *__restrict__ count, uint32_t L1, uint32_t level,
+                                                    XYZZ<F> *__restrict__ buckets, uint32_t *__restrict__ out_key,
+                                                    XYZZ<F> *__restrict__ out_pt) {
+    const uint32_t n_in = level_slots(count[0], L1, L, level);
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, start = t * L;
+    if (start >= n_in) return;
+    const uint32_t end = min(start + (uint32_t)L, n_in);
+    uint32_t cur = SENT;
+    int run = 0;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t j = start; j < end; j++) {
+        uint32_t k = in_key[j];
+        if (k == SENT) continue;
+        if (cur == SENT) {
+            cur = k;
+            acc = ld_vec(in_pt + j);
+            continue;
+        }
+        if (k != cur) {
+            if (run == 0) { out_key[2 * t] = cur; st_vec(out_pt + 2 * t, acc); }
+            else st_vec(buckets + cur, acc);
+            run++;
+            cur = k;
+            acc = ld_vec(in_pt + j);
+        } else {
+            acc.add(ld_vec(in_pt + j));
+        }
+    }
+    if (run == 0) {
+        out_key[2 * t] = cur;                                 // SENT if the chunk was empty
+        if (cur != SENT) st_vec(out_pt + 2 * t, acc);
+        out_key[2 * t + 1] = SENT;
+    } else {
+        out_key[2 * t + 1] = cur; st_vec(out_pt + 2 * t + 1, acc);
+    }
+}
+
 // ---------------------------------------------------------------- 4. partial merge
 template <class F>
 __global__ void __launch_bounds__(128) k_partial_merge(const uint32_t *__restrict__ pkey, const XYZZ<F> *__restrict__ ppt,
-                                                       uint32_t *__restrict__ count, uint32_t L,
-                                                       XYZZ<F> *__restrict__ buckets, uint32_t *__restrict__ long_list) {
-    const uint32_t M = count[0], n2 = 2u * ((M + L - 1) / L);
+                                                       uint32_t *__restrict__ count, uint32_t L1, uint32_t L2,
+                                                       uint32_t level, XYZZ<F> *__restrict__ buckets,
+                                                       uint32_t *__restrict__ long_list) {
+    const uint32_t n2 = level_slots(count[0], L1, L2, level);
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n2) return;
     const uint32_t key = pkey[i];
@@ -166,12 +217,13 @@ __device__ __forceinline__ void block_tree_sum(XYZZ<F> &v, XYZZ<F> *sm) {      /
 
 template <class F>
 __global__ void __launch_bounds__(128) k_long_run(const uint32_t *__restrict__ pkey, const XYZZ<F> *__restrict__ ppt,
-                                                  const uint32_t *__restrict__ count, uint32_t L,
-                                                  XYZZ<F> *__restrict__ buckets, const uint32_t *__restrict__ long_list) {
+                                                  const uint32_t *__restrict__ count, uint32_t L1, uint32_t L2,
+                                                  uint32_t level, XYZZ<F> *__restrict__ buckets,
+                                                  const uint32_t *__restrict__ long_list) {
     extern __shared__ uint4 smem_raw[];
     XYZZ<F> *sm = reinterpret_cast<XYZZ<F> *>(smem_raw);
     if (blockIdx.x >= count[1]) return;
-    const uint32_t M = count[0], n2 = 2u * ((M + L - 1) / L);
+    const uint32_t n2 = level_slots(count[0], L1, L2, level);
     const uint32_t i0 = long_list[blockIdx.x], key = pkey[i0];
     XYZZ<F> acc = XYZZ<F>::inf();
     for (uint32_t j = i0 + threadIdx.x; j < n2; j += 128) {
@@ -307,6 +359,7 @@ struct MsmBases {
         d_out, bad;
     size_t cub_bytes = 0;
     uint32_t key_bits = 0, T = 0, NG = 0, LP = 0, nblk = 0;
+    size_t lvl_off[4] = {0, 0, 0, 0}, lvl_slots[4] = {0, 0, 0, 0};
     std::mutex mu;
 };
 
@@ -362,8 +415,17 @@ static int bases_prepare(MsmBases *B, const uint8_t *bases_bytes, size_t n, int 
     TRY(B->cub_tmp.alloc(B->cub_bytes));
     TRY(B->count.alloc(16));
     TRY(B->buckets.alloc((size_t)B->sets * B->NB * sizeof(XYZZ<F>)));
-    TRY(B->pkey.alloc((size_t)2 * B->T * 4));
-    TRY(B->ppt.alloc((size_t)2 * B->T * sizeof(XYZZ<F>)));
+    // partial-sum levels: level 1 has 2T slots, every further level 2 * ceil(prev / kSeg); stored back to back
+    B->lvl_off[0] = 0;
+    size_t slots = (size_t)2 * B->T, tot_slots = 0;
+    for (int l = 0; l <= kSegLevels; l++) {
+        B->lvl_off[l] = tot_slots;
+        B->lvl_slots[l] = slots;
+        tot_slots += slots;
+        slots = 2 * ((slots + kSeg - 1) / kSeg);
+    }
+    TRY(B->pkey.alloc(tot_slots * 4));
+    TRY(B->ppt.alloc(tot_slots * sizeof(XYZZ<F>)));
     TRY(B->long_list.alloc(((size_t)2 * B->T / kMergeCap + 2) * 4));
     TRY(B->Sg.alloc((size_t)B->sets * B->NG * sizeof(XYZZ<F>)));
     TRY(B->Ag.alloc((size_t)B->sets * B->NG * sizeof(XYZZ<F>)));
@@ -408,10 +470,21 @@ static int msm_run(MsmBases *B, const Fr *d_scalars, uint32_t n_used, uint8_t *d
     LAUNCH(k_find_count, 1, 1, 0, st, keys, (uint32_t)total, count);
     LAUNCH((k_bucket_accum<F, kChunk, 128>), (B->T + 127) / 128, 128, 0, st, keys, vals, count, B->points.as<Affine<F>>(),
            B->buckets.as<X>(), B->pkey.as<uint32_t>(), B->ppt.as<X>());
-    LAUNCH((k_partial_merge<F>), (2 * B->T + 127) / 128, 128, 0, st, B->pkey.as<uint32_t>(), B->ppt.as<X>(), count,
-           (uint32_t)kChunk, B->buckets.as<X>(), B->long_list.as<uint32_t>());
-    LAUNCH((k_long_run<F>), 2 * B->T / kMergeCap + 1, 128, 128 * sizeof(X), st, B->pkey.as<uint32_t>(), B->ppt.as<X>(), count,
-           (uint32_t)kChunk, B->buckets.as<X>(), B->long_list.as<uint32_t>());
+    uint32_t *pk = B->pkey.as<uint32_t>();
+    X *pp = B->ppt.as<X>();
+    for (int l = 1; l <= kSegLevels; l++) {
+        const size_t threads = (B->lvl_slots[l - 1] + kSeg - 1) / kSeg;
+        LAUNCH((k_seg_reduce<F, kSeg>), (unsigned)((threads + 127) / 128), 128, 0, st, pk + B->lvl_off[l - 1],
+               pp + B->lvl_off[l - 1], count, (uint32_t)kChunk, (uint32_t)l, B->buckets.as<X>(), pk + B->lvl_off[l],
+               pp + B->lvl_off[l]);
+    }
+    const size_t fin = B->lvl_slots[kSegLevels];
+    LAUNCH((k_partial_merge<F>), (unsigned)((fin + 127) / 128), 128, 0, st, pk + B->lvl_off[kSegLevels],
+           pp + B->lvl_off[kSegLevels], count, (uint32_t)kChunk, (uint32_t)kSeg, (uint32_t)(kSegLevels + 1), B->buckets.as<X>(),
+           B->long_list.as<uint32_t>());
+    LAUNCH((k_long_run<F>), (unsigned)(fin / kMergeCap + 1), 128, 128 * sizeof(X), st, pk + B->lvl_off[kSegLevels],
+           pp + B->lvl_off[kSegLevels], count, (uint32_t)kChunk, (uint32_t)kSeg, (uint32_t)(kSegLevels + 1), B->buckets.as<X>(),
+           B->long_list.as<uint32_t>());
     const uint32_t ng_total = B->sets * B->NG;
     LAUNCH((k_red_groups<F>), (ng_total + 127) / 128, 128, 0, st, B->buckets.as<X>(), ng_total, B->Sg.as<X>(), B->Ag.as<X>());
     LAUNCH((k_red_planes<F>), dim3(B->nblk, B->LP + 1, B->sets), 128, 128 * sizeof(X), st, B->Sg.as<X>(), B->Ag.as<X>(), B->NG,
