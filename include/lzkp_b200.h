@@ -121,10 +121,20 @@ int lzkp_setup_builtin(int kind, uint32_t param, const uint8_t toxic[160], uint8
  * primitive of the setup, also used to make synthetic MSM bases. */
 int lzkp_generator_mul(int group, const uint8_t *scalars, size_t n, uint8_t *out_affine);
 
+/* Full assignment z = instance || witness (n_vars x 32 B canonical) of a builtin circuit, computed on the host:
+ * what generate_constraints assigns (snark.rs:263-290, 515-584).  Equality: value = a, other = b.  Membership:
+ * value in set[0..set_len).  commitment may be NULL (then MiMC5(value) is used).  LZKP_E_INVALID when the
+ * membership inputs are rejected (snark.rs:406,415-418). */
+int lzkp_builtin_witness(int kind, uint32_t param, uint64_t value, uint64_t other, const uint64_t *set,
+                         uint32_t set_len, const uint8_t *commitment, uint8_t *z_out, size_t z_cap);
+
 /* n_proofs proofs from full assignments: z is n_proofs x n_vars x 32 B (z[0] = 1), r and s are
  * n_proofs x 32 B, proofs_out n_proofs x 256 B, status n_proofs ints (0 = ok). */
 int lzkp_prove_batch(lzkp_pk *pk, size_t n_proofs, const uint8_t *z, const uint8_t *r, const uint8_t *s,
                      uint8_t *proofs_out, int32_t *status);
+/* lzkp_prove_batch with every buffer in device memory, asynchronous on `stream`. */
+int lzkp_prove_batch_device(lzkp_pk *pk, size_t n_proofs, const void *d_z, const void *d_r, const void *d_s,
+                            void *d_proofs, void *d_status, void *stream);
 /* Equality batch (prove_equality_zk x n): a, b u64; commitments n x 32 B or NULL (then MiMC5(a) is
  * computed on the device and, if commitments_out != NULL, returned).  status 1 = a != b (snark.rs:344). */
 int lzkp_prove_equality_batch(lzkp_pk *pk, size_t n_proofs, const uint64_t *a, const uint64_t *b,

@@ -91,6 +91,9 @@ struct MsmPlan {                 // one curve
 };
 static const uint32_t kUnitsPerItem[3] = {32, 128, 512};
 
+// pk->stream is a BLOCKING stream on purpose: setup-time uploads use synchronous cudaMemcpy from pageable
+// memory, whose DMA tail is only ordered against the legacy default stream and streams that synchronise
+// with it; a non-blocking stream could run the first kernel before the bytes have landed.
 struct lzkp_pk {
     std::mutex mu;
     uint32_t n_vars = 0, n_inst = 0, n_wit = 0, n = 0, log_n = 0, m = 0;
@@ -113,6 +116,10 @@ struct lzkp_pk {
     uint32_t ws_chunk = 0;
     DBuf ws_z, ws_abc, ws_h, ws_dig, ws_r, ws_s, ws_rs, ws_part1, ws_part2, ws_res1, ws_res2, ws_proofs, ws_status,
         ws_a, ws_b, ws_commit, ws_sets, ws_setlen;
+    // large mode (domain above 2^12): Pippenger MSMs over resident window-shifted bases, tiled NTTs
+    bool large = false;
+    MsmBases *L_a = nullptr, *L_b1 = nullptr, *L_b2 = nullptr, *L_l = nullptr, *L_h = nullptr;
+    DBuf L_tmp, L_sa, L_sb, L_sl;
     cudaStream_t stream = nullptr;
     // optional per-region CUDA-event timing (lzkp_profile_*): pairs recorded on the launching stream
     struct Mark { int region; cudaEvent_t a, b; };
@@ -121,6 +128,7 @@ struct lzkp_pk {
     uint64_t prof_count[LZKP_PROFILE_REGIONS] = {0};
     ~lzkp_pk() {
         for (auto &m : marks) { cudaEventDestroy(m.a); cudaEventDestroy(m.b); }
+        for (MsmBases *b : {L_a, L_b1, L_b2, L_l, L_h}) if (b) msm_bases_free(b);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -227,6 +235,52 @@ static int pk_load_impl(const uint8_t *bytes, size_t len, int validate, const lz
     pk->n_dig_rows = pk->nz + 3 + (n - 1);
     const uint32_t ROW_R = pk->nz, ROW_S = pk->nz + 1, ROW_RS = pk->nz + 2, ROW_H = pk->nz + 3;
 
+    pk->large = pk->log_n > 12 || getenv("LZKP_FORCE_LARGE") != nullptr;
+    if (pk->large) {
+        // A = alpha + a_q[0] + sum_{j>=1} z_j a_q[j] + r delta: delta rides along as one more base (scalar r / s / rs)
+        CUDA_TRY(cudaStreamCreate(&pk->stream));
+        const int wb = opt && opt->window_bits ? opt->window_bits : 0;
+        auto load1 = [&](std::vector<host::G1Canon> v, size_t skip, const host::G1Canon *extra, MsmBases **out) {
+            v.erase(v.begin(), v.begin() + skip);
+            if (extra) v.push_back(*extra);
+            return msm_bases_load(1, reinterpret_cast<const uint8_t *>(v.data()), v.size(), wb, 1, validate, out, 1);
+        };
+        host::G1Canon nd1 = neg_canon(delta_g1);
+        TRY(load1(a_q, 1, &delta_g1, &pk->L_a));
+        TRY(load1(b1_q, 1, &delta_g1, &pk->L_b1));
+        TRY(load1(l_q, 0, &nd1, &pk->L_l));
+        TRY(load1(h_q, 0, nullptr, &pk->L_h));
+        {
+            std::vector<host::G2Canon> v(b2_q.begin() + 1, b2_q.end());
+            v.push_back(delta_g2);
+            TRY(msm_bases_load(2, reinterpret_cast<const uint8_t *>(v.data()), v.size(), wb, 1, validate, &pk->L_b2, 1));
+        }
+        pk->c = wb ? wb : 16;
+        pk->W = (255 + pk->c - 1) / pk->c;
+        pk->max_chunk = 1;
+        pk->table_bytes = ((uint64_t)(a_q.size() + b1_q.size() + l_q.size() + 1 + h_q.size()) * 64 + (uint64_t)b2_q.size() * 128) * pk->W;
+        // constant terms alpha + a_q[0], beta + b_q[0] (G1 and G2)
+        std::vector<host::G1Canon> misc1 = {alpha_g1, beta_g1, a_q[0], b1_q[0]};
+        std::vector<host::G2Canon> misc2 = {beta_g2, b2_q[0]};
+        DBuf d_misc1, d_misc2, d_out1, d_out2;
+        cudaStream_t st = pk->stream;
+        TRY(upload(d_misc1, misc1)); TRY(upload(d_misc2, misc2));
+        LAUNCH(k_fq_to_mont, 1, 128, 0, st, d_misc1.as<Fq>(), misc1.size() * 2);
+        LAUNCH(k_fq_to_mont, 1, 128, 0, st, d_misc2.as<Fq>(), misc2.size() * 4);
+        TRY(d_out1.alloc(2 * sizeof(G1Affine))); TRY(d_out2.alloc(sizeof(G2Affine)));
+        LAUNCH((k_affine_add<Fq>), 1, 1, 0, st, d_misc1.as<G1Affine>() + 0, d_misc1.as<G1Affine>() + 2, d_out1.as<G1Affine>() + 0, 0);
+        LAUNCH((k_affine_add<Fq>), 1, 1, 0, st, d_misc1.as<G1Affine>() + 1, d_misc1.as<G1Affine>() + 3, d_out1.as<G1Affine>() + 1, 0);
+        LAUNCH((k_affine_add<Fq2>), 1, 1, 0, st, d_misc2.as<G2Affine>() + 0, d_misc2.as<G2Affine>() + 1, d_out2.as<G2Affine>(), 0);
+        G1Affine c1[2];
+        G2Affine c2;
+        CUDA_TRY(cudaMemcpyAsync(c1, d_out1.p, sizeof(c1), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(&c2, d_out2.p, sizeof(c2), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        pk->consts.a0 = c1[0]; pk->consts.b0 = c1[1]; pk->consts.b2 = c2;
+        CUDA_TRY(cudaGetLastError());
+        return LZKP_OK;
+    }
+
     // --- base lists (identity points are dropped: they contribute nothing to any MSM) ---
     std::vector<host::G1Canon> rows1;
     std::vector<host::G2Canon> rows2;
@@ -271,7 +325,7 @@ static int pk_load_impl(const uint8_t *bytes, size_t len, int validate, const lz
     pk->max_chunk = opt && opt->max_chunk ? opt->max_chunk : 8192;
     if (pk->max_chunk > 32768) pk->max_chunk = 32768;
 
-    CUDA_TRY(cudaStreamCreateWithFlags(&pk->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreate(&pk->stream));
     cudaStream_t st = pk->stream;
 
     // --- upload points, to Montgomery, optional validation ---
@@ -339,7 +393,7 @@ static int circuit_install(lzkp_pk *pk, uint32_t m, uint32_t n_inst, uint32_t n_
     uint32_t n = 1;
     while (n < need) n <<= 1;
     if (n != pk->n) return fail(LZKP_E_INVALID, "circuit domain size does not match the proving key's h_query");
-    if (pk->log_n > 12) return fail(LZKP_E_UNSUPPORTED, "batched witness map supports domains up to 2^12");
+    if (pk->log_n > 12 && !pk->large) return fail(LZKP_E_UNSUPPORTED, "batched witness map supports domains up to 2^12");
     cudaStream_t st = pk->stream;
     for (int k = 0; k < 3; k++) {
         uint32_t nnz = rowptr[k][m];
@@ -364,6 +418,13 @@ static int circuit_install(lzkp_pk *pk, uint32_t m, uint32_t n_inst, uint32_t n_
     Fr gn = g;
     for (uint32_t i = 0; i < pk->log_n; i++) gn = gn.sqr();
     Fr zinv = (gn - Fr::one()).inverse();
+    if (pk->large) {          // transforms come from ntt_large.cu's cached plans; only Z(g)^-1 is needed here
+        pk->ntt = NttTables{nullptr, nullptr, nullptr, nullptr, nullptr, ninv, zinv};
+        CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaGetLastError());
+        pk->has_circuit = true;
+        return LZKP_OK;
+    }
     TRY(pk->tw_fwd.alloc(sizeof(Fr) * (n / 2))); TRY(pk->tw_inv.alloc(sizeof(Fr) * (n / 2)));
     TRY(pk->coset_br.alloc(sizeof(Fr) * n)); TRY(pk->uncoset_br.alloc(sizeof(Fr) * n));
     LAUNCH(k_pow_table, (n / 2 + 127) / 128, 128, 0, st, pk->tw_fwd.as<Fr>(), w, Fr::one(), n / 2, 0u);
@@ -397,7 +458,12 @@ static int ensure_workspace(lzkp_pk *pk, uint32_t P) {
     TRY(pk->ws_z.ensure(P * nv * 32));
     TRY(pk->ws_abc.ensure(3 * P * n * 32));
     TRY(pk->ws_h.ensure(P * n * 32));
-    TRY(pk->ws_dig.ensure((size_t)pk->n_dig_rows * pk->W * P * sizeof(int16_t)));
+    if (pk->large) {
+        TRY(pk->L_tmp.ensure(n * 32));
+        TRY(pk->L_sa.ensure(nv * 32)); TRY(pk->L_sb.ensure(nv * 32)); TRY(pk->L_sl.ensure(((size_t)pk->n_wit + 1) * 32));
+    } else {
+        TRY(pk->ws_dig.ensure((size_t)pk->n_dig_rows * pk->W * P * sizeof(int16_t)));
+    }
     TRY(pk->ws_r.ensure(P * 32)); TRY(pk->ws_s.ensure(P * 32)); TRY(pk->ws_rs.ensure(P * 32));
     TRY(pk->ws_part1.ensure(part1 * sizeof(G1XYZZ)));
     TRY(pk->ws_part2.ensure(part2 * sizeof(G2XYZZ)));
@@ -429,6 +495,21 @@ static int run_witness_map(lzkp_pk *pk, uint32_t P, cudaStream_t st) {
     const uint32_t n = pk->n, threads = std::max(32u, std::min(n / 2, 512u));
     const size_t smem = (size_t)32 * n;
     Region reg(pk, LZKP_REGION_WITNESS_MAP, st);
+    if (pk->large) {
+        // a3-a7 for one proof on a large domain: SpMV, then per vector iNTT -> coset NTT (tiled passes),
+        // pointwise (ab - c) / Z(g), coset iNTT, and one conversion of h to canonical form
+        Fr *abc = pk->ws_abc.as<Fr>(), *tmp = pk->L_tmp.as<Fr>(), *h = pk->ws_h.as<Fr>();
+        LAUNCH(k_spmv_abc, dim3((n + 127) / 128, 1), 128, 0, st, pk->csr[0], pk->csr[1], pk->csr[2], pk->ws_z.as<Fr>(), abc, 1u,
+               pk->n_vars, pk->m, pk->n_inst, n);
+        for (int k = 0; k < 3; k++) {
+            TRY(large_ntt_device(abc + (size_t)k * n, tmp, pk->log_n, 1, 0, st));
+            TRY(large_ntt_device(tmp, abc + (size_t)k * n, pk->log_n, 0, 1, st));
+        }
+        LAUNCH(k_pointwise_h, (n + 127) / 128, 128, 0, st, abc, abc + n, abc + 2 * (size_t)n, tmp, pk->ntt.zinv, n);
+        TRY(large_ntt_device(tmp, h, pk->log_n, 1, 1, st));
+        LAUNCH(k_fr_to_canonical, (n + 127) / 128, 128, 0, st, h, n);
+        return LZKP_OK;
+    }
     LAUNCH(k_spmv_abc, dim3((n + 127) / 128, P), 128, 0, st, pk->csr[0], pk->csr[1], pk->csr[2], pk->ws_z.as<Fr>(),
            pk->ws_abc.as<Fr>(), P, pk->n_vars, pk->m, pk->n_inst, n);
     LAUNCH(k_ntt_icoset, dim3(P, 3), threads, smem, st, pk->ws_abc.as<Fr>(), pk->ntt, P, pk->log_n);
@@ -440,6 +521,39 @@ static int run_witness_map(lzkp_pk *pk, uint32_t P, cudaStream_t st) {
 static int run_prove(lzkp_pk *pk, uint32_t P, const Fr *d_r, const Fr *d_s, uint8_t *d_proofs, int32_t *d_status,
                      cudaStream_t st) {
     TRY(run_witness_map(pk, P, st));
+    if (pk->large) {
+        if (P != 1) return fail(LZKP_E_STATE, "large-domain proving runs one proof per pass");
+        const uint32_t nv = pk->n_vars, ni = pk->n_inst, nw = pk->n_wit;
+        const uint8_t *z = pk->ws_z.as<uint8_t>();
+        uint8_t *sa = pk->L_sa.as<uint8_t>(), *sb = pk->L_sb.as<uint8_t>(), *sl = pk->L_sl.as<uint8_t>();
+        LAUNCH(k_fr_mul_canonical, 1, 128, 0, st, d_r, d_s, pk->ws_rs.as<Fr>(), 1u);
+        LAUNCH(k_check_canonical, (nv + 127) / 128, 128, 0, st, pk->ws_z.as<Fr>(), nv, d_status);
+        LAUNCH(k_check_canonical, 1, 32, 0, st, d_r, 1u, d_status);
+        LAUNCH(k_check_canonical, 1, 32, 0, st, d_s, 1u, d_status);
+        // scalar vectors: z[1..] || r, z[1..] || s, z[n_inst..] || rs (the last entry multiplies +-delta)
+        const cudaMemcpyKind dd = cudaMemcpyDeviceToDevice;
+        CUDA_TRY(cudaMemcpyAsync(sa, z + 32, (size_t)(nv - 1) * 32, dd, st));
+        CUDA_TRY(cudaMemcpyAsync(sa + (size_t)(nv - 1) * 32, d_r, 32, dd, st));
+        CUDA_TRY(cudaMemcpyAsync(sb, z + 32, (size_t)(nv - 1) * 32, dd, st));
+        CUDA_TRY(cudaMemcpyAsync(sb + (size_t)(nv - 1) * 32, d_s, 32, dd, st));
+        CUDA_TRY(cudaMemcpyAsync(sl, z + (size_t)ni * 32, (size_t)nw * 32, dd, st));
+        CUDA_TRY(cudaMemcpyAsync(sl + (size_t)nw * 32, pk->ws_rs.p, 32, dd, st));
+        G1XYZZ *res1 = pk->ws_res1.as<G1XYZZ>();
+        {
+            Region reg(pk, LZKP_REGION_MSM_G1, st);
+            TRY(msm_device_raw(pk->L_a, sa, nv, res1 + 0, st));
+            TRY(msm_device_raw(pk->L_b1, sb, nv, res1 + 1, st));
+            TRY(msm_device_raw(pk->L_l, sl, nw + 1, res1 + 2, st));
+            TRY(msm_device_raw(pk->L_h, pk->ws_h.p, pk->n - 1, res1 + 3, st));
+        }
+        {
+            Region reg(pk, LZKP_REGION_MSM_G2, st);
+            TRY(msm_device_raw(pk->L_b2, sb, nv, pk->ws_res2.p, st));
+        }
+        Region reg(pk, LZKP_REGION_ASSEMBLE, st);
+        LAUNCH(k_assemble, 1, 64, 0, st, res1, pk->ws_res2.as<G2XYZZ>(), pk->consts, d_r, d_s, 1u, d_proofs);
+        return LZKP_OK;
+    }
     const uint32_t c = pk->c, W = pk->W, gx = (P + 127) / 128;
     int16_t *dig = pk->ws_dig.as<int16_t>();
     {
@@ -694,6 +808,41 @@ int lzkp_prove_batch(lzkp_pk *pk, size_t n_proofs, const uint8_t *z, const uint8
         CUDA_TRY(cudaGetLastError());
     }
     blank_failed(n_proofs, status, proofs_out);
+    return LZKP_OK;
+}
+
+int lzkp_prove_batch_device(lzkp_pk *pk, size_t n_proofs, const void *d_z, const void *d_r, const void *d_s,
+                            void *d_proofs, void *d_status, void *stream) {
+    if (!pk || (n_proofs && (!d_z || !d_r || !d_s || !d_proofs || !d_status))) return fail(LZKP_E_INVALID, "null argument");
+    TRY(ensure_device());
+    std::lock_guard<std::mutex> lk(pk->mu);
+    if (!pk->has_circuit) return fail(LZKP_E_STATE, "lzkp_circuit_load has not been called");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t nv = pk->n_vars;
+    for (size_t off = 0; off < n_proofs; off += pk->max_chunk) {
+        uint32_t P = (uint32_t)std::min<size_t>(pk->max_chunk, n_proofs - off);
+        TRY(ensure_workspace(pk, P));
+        int32_t *stat = (int32_t *)d_status + off;
+        CUDA_TRY(cudaMemsetAsync(stat, 0, (size_t)P * 4, st));
+        CUDA_TRY(cudaMemcpyAsync(pk->ws_z.p, (const uint8_t *)d_z + off * nv * 32, (size_t)P * nv * 32, cudaMemcpyDeviceToDevice, st));
+        TRY(run_prove(pk, P, (const Fr *)d_r + off, (const Fr *)d_s + off, (uint8_t *)d_proofs + off * 256, stat, st));
+    }
+    CUDA_TRY(cudaGetLastError());
+    return LZKP_OK;
+}
+
+int lzkp_builtin_witness(int kind, uint32_t param, uint64_t value, uint64_t other, const uint64_t *set,
+                         uint32_t set_len, const uint8_t *commitment, uint8_t *z_out, size_t z_cap) {
+    if (!z_out || param == 0) return fail(LZKP_E_INVALID, "bad argument");
+    std::vector<Fr> z;
+    if (kind == LZKP_CIRCUIT_EQUALITY) z = host::assign_equality(param, value, other, commitment);
+    else if (kind == LZKP_CIRCUIT_MEMBERSHIP) {
+        if (!set) return fail(LZKP_E_INVALID, "null set");
+        z = host::assign_membership(param, value, set, set_len, commitment);
+        if (z.empty()) return fail(LZKP_E_INVALID, "membership inputs rejected (empty / oversized set or value not in set)");
+    } else return fail(LZKP_E_INVALID, "bad circuit kind");
+    if (z_cap < z.size() * 32) return fail(LZKP_E_INVALID, "z_out too small");
+    memcpy(z_out, z.data(), z.size() * 32);
     return LZKP_OK;
 }
 

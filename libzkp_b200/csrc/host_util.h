@@ -211,5 +211,63 @@ inline R1cs synth_membership(uint32_t S) {
     return cs;
 }
 
+// ---- full assignments z = instance || witness of the builtin circuits (canonical limbs) ------------
+// Same values generate_constraints assigns (snark.rs:263-290, 515-584); used by callers that prove from
+// an explicit z (lzkp_prove_batch) and by the large synthetic MiMC-chain circuit.
+inline Fr canon_u64(uint64_t x) {
+    Fr c = Fr::zero();
+    c.l[0] = (uint32_t)x;
+    c.l[1] = (uint32_t)(x >> 32);
+    return c;
+}
+// appends t^2, t^4, t^5 per round to z; returns the chain output (Montgomery)
+inline Fr assign_mimc(std::vector<Fr> &z, uint64_t input, uint32_t rounds) {
+    static Fr cst[110];
+    static bool init = false;
+    if (!init) {
+        for (uint32_t i = 0; i < 110; i++) cst[i] = mimc_constant(i);
+        init = true;
+    }
+    Fr x = fr_from_u64(input);
+    for (uint32_t i = 0; i < rounds; i++) {
+        Fr t = x + cst[i % 110], t2 = t.sqr(), t4 = t2.sqr();
+        x = t4 * t;
+        z.push_back(t2.to_canonical()); z.push_back(t4.to_canonical()); z.push_back(x.to_canonical());
+    }
+    return x;
+}
+inline std::vector<Fr> assign_equality(uint32_t rounds, uint64_t a, uint64_t b, const uint8_t *commitment) {
+    std::vector<Fr> z;
+    z.reserve(4 + 3 * (size_t)rounds);
+    z.push_back(canon_u64(1));
+    z.push_back(Fr::zero());
+    z.push_back(canon_u64(a));
+    z.push_back(canon_u64(b));
+    Fr h = assign_mimc(z, a, rounds);
+    if (commitment) memcpy(z[1].l, commitment, 32);
+    else z[1] = h.to_canonical();
+    return z;
+}
+// returns an empty vector when the set is empty / too long / does not contain value (snark.rs:406,415-418)
+inline std::vector<Fr> assign_membership(uint32_t S, uint64_t value, const uint64_t *set, uint32_t len,
+                                         const uint8_t *commitment) {
+    std::vector<Fr> z;
+    if (len < 1 || len > S) return z;
+    uint32_t pos = S;
+    for (uint32_t i = 0; i < len; i++) if (set[i] == value) { pos = i; break; }
+    if (pos == S) return z;
+    z.push_back(canon_u64(1));
+    z.push_back(Fr::zero());
+    for (uint32_t i = 0; i < S; i++) z.push_back(i < len ? canon_u64(set[i]) : Fr::zero());
+    for (uint32_t i = 0; i < S; i++) z.push_back(i < len ? canon_u64(1) : Fr::zero());
+    z.push_back(canon_u64(value));
+    Fr h = assign_mimc(z, value, 110);
+    if (commitment) memcpy(z[1].l, commitment, 32);
+    else z[1] = h.to_canonical();
+    for (uint32_t i = 0; i < S; i++) z.push_back(i == pos ? canon_u64(1) : Fr::zero());
+    for (uint32_t i = 0; i < 2 * S; i++) z.push_back(Fr::zero());      // sel*(1-is_real), sel*(value-set): 0 when honest
+    return z;
+}
+
 }  // namespace host
 }  // namespace lzkp

@@ -281,6 +281,25 @@ __global__ void k_ntt_small(Fr *data, NttTables T, uint32_t log_n, int inverse, 
     }
 }
 
+// Large-domain witness map helpers (the transforms themselves are ntt_large.cu's tiled passes).
+// hq[i] = (a[i] * b[i] - c[i]) * zinv on the coset (Montgomery in / out)
+__global__ void k_pointwise_h(const Fr *a, const Fr *b, const Fr *c, Fr *hq, Fr zinv, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    st_vec(hq + i, (ld_vec(a + i) * ld_vec(b + i) - ld_vec(c + i)) * zinv);
+}
+__global__ void k_fr_to_canonical(Fr *v, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    st_vec(v + i, ld_vec(v + i).to_canonical());
+}
+// status[0] = 1 when any of the count scalars is not canonical (>= r)
+__global__ void k_check_canonical(const Fr *v, uint32_t count, int32_t *status) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    if (!fr_is_canonical(ld_vec(v + i))) status[0] = 1;
+}
+
 // ---------------------------------------------------------------- scalar recoding
 // Signed c-bit digits via the offset trick: s' = s + K, K = sum_w 2^(c*w + c-1); the unsigned
 // windows u_w of s' give d_w = u_w - 2^(c-1) in [-2^(c-1), 2^(c-1)), independently per window.

@@ -15,12 +15,16 @@ int large_msm_g2_host(const uint8_t *bases_affine, const uint8_t *scalars, size_
 
 // Resident MSM bases (msm_large.cu): group 1 = G1, 2 = G2; `resident` keeps 2^(c*w) * P for every window.
 struct MsmBases;
-int msm_bases_load(int group, const uint8_t *bases, size_t n, int window_bits, int resident, int validate, MsmBases **out);
+// canon_input != 0: `bases` holds parsed points (canonical limbs, x||y, (0,0) = infinity) instead of ark bytes
+int msm_bases_load(int group, const uint8_t *bases, size_t n, int window_bits, int resident, int validate, MsmBases **out,
+                   int canon_input = 0);
 void msm_bases_free(MsmBases *b);
 uint32_t msm_bases_size(const MsmBases *b);
 int msm_bases_group(const MsmBases *b);
 int msm_host(MsmBases *b, const uint8_t *scalars, size_t n_used, uint8_t *out);
 int msm_device(MsmBases *b, const void *d_scalars, size_t n_used, void *d_out, cudaStream_t st);
+int msm_device_raw(MsmBases *b, const void *d_scalars, size_t n_used, void *d_out_xyzz, cudaStream_t st);
+int msm_take_bad(MsmBases *b, cudaStream_t st, int *bad);
 
 }  // namespace eng
 }  // namespace lzkp

@@ -364,7 +364,8 @@ struct MsmBases {
 };
 
 template <class F>
-static int bases_prepare(MsmBases *B, const uint8_t *bases_bytes, size_t n, int window_bits, int resident, int validate) {
+static int bases_prepare(MsmBases *B, const uint8_t *bases_bytes, size_t n, int window_bits, int resident, int validate,
+                         int canon_input) {
     constexpr int BYTES = PointIO<F>::BYTES;
     if (n >= (1u << 27)) return fail(LZKP_E_UNSUPPORTED, "MSM size above 2^27");
     B->group = BYTES == 64 ? 1 : 2;
@@ -378,15 +379,21 @@ static int bases_prepare(MsmBases *B, const uint8_t *bases_bytes, size_t n, int 
     if ((uint64_t)B->n * B->W >= (1ull << 31)) return fail(LZKP_E_UNSUPPORTED, "MSM: n * windows must stay below 2^31");
     const uint32_t n1 = std::max<uint32_t>(B->n, 1);
     // ---- parse ark-serialize points on the host (canonical limbs, flags stripped), upload, to Montgomery
-    std::vector<uint8_t> canon((size_t)n1 * BYTES, 0);
-    for (size_t i = 0; i < n; i++) {
+    std::vector<uint8_t> canon;
+    if (!canon_input) canon.assign((size_t)n1 * BYTES, 0);
+    for (size_t i = 0; i < n && !canon_input; i++) {
         bool ok;
         if constexpr (BYTES == 64) ok = host::read_g1(bases_bytes + i * 64, *reinterpret_cast<host::G1Canon *>(canon.data() + i * 64));
         else ok = host::read_g2(bases_bytes + i * 128, *reinterpret_cast<host::G2Canon *>(canon.data() + i * 128));
         if (!ok) return fail(LZKP_E_INVALID, "MSM base " + std::to_string(i) + ": non-canonical coordinate");
     }
     TRY(B->points.alloc((size_t)n1 * (B->resident ? B->W : 1) * BYTES));
-    CUDA_TRY(cudaMemcpy(B->points.p, canon.data(), canon.size(), cudaMemcpyHostToDevice));
+    if (canon_input) {      // already parsed: canonical limbs, (0,0) = infinity
+        CUDA_TRY(cudaMemset(B->points.p, 0, (size_t)n1 * BYTES));
+        if (n) CUDA_TRY(cudaMemcpy(B->points.p, bases_bytes, n * BYTES, cudaMemcpyHostToDevice));
+    } else {
+        CUDA_TRY(cudaMemcpy(B->points.p, canon.data(), canon.size(), cudaMemcpyHostToDevice));
+    }
     const size_t n_fq = (size_t)n1 * BYTES / 32;
     LAUNCH(k_fq_array_to_mont, (unsigned)((n_fq + 255) / 256), 256, 0, 0, B->points.as<Fq>(), n_fq);
     TRY(B->bad.alloc(sizeof(int)));
@@ -440,14 +447,16 @@ static int bases_prepare(MsmBases *B, const uint8_t *bases_bytes, size_t n, int 
 
 // scalars: device, canonical, n_used <= B->n of them.  out: device, ark-serialize affine bytes.
 template <class F>
-static int msm_run(MsmBases *B, const Fr *d_scalars, uint32_t n_used, uint8_t *d_out, cudaStream_t st) {
+// raw != 0: d_out receives the XYZZ sum (sizeof(XYZZ<F>) bytes) instead of ark-serialize affine bytes
+static int msm_run(MsmBases *B, const Fr *d_scalars, uint32_t n_used, uint8_t *d_out, cudaStream_t st, int raw) {
     constexpr int BYTES = PointIO<F>::BYTES;
     using X = XYZZ<F>;
     const uint32_t n = B->n;
     if (n_used > n) return fail(LZKP_E_INVALID, "MSM: more scalars than resident bases");
     if (n_used == 0) {                    // empty sum: the point at infinity
         CUDA_TRY(cudaMemsetAsync(B->R.p, 0, sizeof(X), st));
-        LAUNCH((k_finish<F, BYTES>), 1, 1, 0, st, B->R.as<X>(), d_out);
+        if (raw) CUDA_TRY(cudaMemcpyAsync(d_out, B->R.p, sizeof(X), cudaMemcpyDeviceToDevice, st));
+        else LAUNCH((k_finish<F, BYTES>), 1, 1, 0, st, B->R.as<X>(), d_out);
         return LZKP_OK;
     }
     CUDA_TRY(cudaMemsetAsync(B->buckets.p, 0, (size_t)B->sets * B->NB * sizeof(X), st));
@@ -491,16 +500,18 @@ static int msm_run(MsmBases *B, const Fr *d_scalars, uint32_t n_used, uint8_t *d
            B->LP, B->out1.as<X>());
     LAUNCH((k_red_finish<F>), B->sets, 32, 32 * sizeof(X), st, B->out1.as<X>(), B->nblk, B->LP, B->R.as<X>());
     if (B->sets > 1) LAUNCH((k_horner<F>), 1, 1, 0, st, B->R.as<X>(), B->sets, B->c);
-    LAUNCH((k_finish<F, BYTES>), 1, 1, 0, st, B->R.as<X>(), d_out);
+    if (raw) CUDA_TRY(cudaMemcpyAsync(d_out, B->R.p, sizeof(X), cudaMemcpyDeviceToDevice, st));
+    else LAUNCH((k_finish<F, BYTES>), 1, 1, 0, st, B->R.as<X>(), d_out);
     CUDA_TRY(cudaGetLastError());
     return LZKP_OK;
 }
 
-int msm_bases_load(int group, const uint8_t *bases, size_t n, int window_bits, int resident, int validate, MsmBases **out) {
+int msm_bases_load(int group, const uint8_t *bases, size_t n, int window_bits, int resident, int validate, MsmBases **out,
+                   int canon_input) {
     MsmBases *B = new (std::nothrow) MsmBases();
     if (!B) return fail(LZKP_E_NOMEM, "host allocation failed");
-    int rc = group == 1 ? bases_prepare<Fq>(B, bases, n, window_bits, resident, validate)
-                        : bases_prepare<Fq2>(B, bases, n, window_bits, resident, validate);
+    int rc = group == 1 ? bases_prepare<Fq>(B, bases, n, window_bits, resident, validate, canon_input)
+                        : bases_prepare<Fq2>(B, bases, n, window_bits, resident, validate, canon_input);
     if (rc != LZKP_OK) {
         delete B;
         return rc;
@@ -518,14 +529,26 @@ void msm_bases_free(MsmBases *B) { delete B; }
 uint32_t msm_bases_size(const MsmBases *B) { return B->n; }
 int msm_bases_group(const MsmBases *B) { return B->group; }
 
-static int msm_device_nolock(MsmBases *B, const void *d_scalars, size_t n_used, void *d_out, cudaStream_t st) {
-    return B->group == 1 ? msm_run<Fq>(B, (const Fr *)d_scalars, (uint32_t)n_used, (uint8_t *)d_out, st)
-                         : msm_run<Fq2>(B, (const Fr *)d_scalars, (uint32_t)n_used, (uint8_t *)d_out, st);
+static int msm_device_nolock(MsmBases *B, const void *d_scalars, size_t n_used, void *d_out, cudaStream_t st, int raw = 0) {
+    return B->group == 1 ? msm_run<Fq>(B, (const Fr *)d_scalars, (uint32_t)n_used, (uint8_t *)d_out, st, raw)
+                         : msm_run<Fq2>(B, (const Fr *)d_scalars, (uint32_t)n_used, (uint8_t *)d_out, st, raw);
 }
 
 int msm_device(MsmBases *B, const void *d_scalars, size_t n_used, void *d_out, cudaStream_t st) {
     std::lock_guard<std::mutex> lk(B->mu);
     return msm_device_nolock(B, d_scalars, n_used, d_out, st);
+}
+
+int msm_device_raw(MsmBases *B, const void *d_scalars, size_t n_used, void *d_out_xyzz, cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(B->mu);
+    return msm_device_nolock(B, d_scalars, n_used, d_out_xyzz, st, 1);
+}
+// number of non-canonical scalars seen since the last call (device flag; synchronises the stream)
+int msm_take_bad(MsmBases *B, cudaStream_t st, int *bad) {
+    CUDA_TRY(cudaMemcpyAsync(bad, B->bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaMemsetAsync(B->bad.p, 0, sizeof(int), st));
+    return LZKP_OK;
 }
 
 int msm_host(MsmBases *B, const uint8_t *scalars, size_t n_used, uint8_t *out) {

@@ -100,6 +100,24 @@ def setup(m: int, n_inst: int, n_wit: int, mats, toxic: Sequence[int]) -> Tuple[
     return pk.tobytes(), vk.tobytes()
 
 
+def builtin_witness(kind: int, param: int, value: int, other: int = 0, set_: Optional[Sequence[int]] = None,
+                    commitment: Optional[bytes] = None) -> np.ndarray:
+    """Full assignment z (n_vars x 32 B canonical) of a builtin circuit (lzkp_builtin_witness, host arithmetic)."""
+    (_, n_inst, n_wit), _ = (builtin_circuit_shape(kind, param), None)
+    z = np.zeros((n_inst + n_wit, 32), np.uint8)
+    sa = None if set_ is None else np.asarray(list(set_), np.uint64)
+    cm = None if commitment is None else np.frombuffer(commitment, np.uint8).copy()
+    check(lib().lzkp_builtin_witness(kind, param, int(value), int(other), _p(sa), 0 if sa is None else len(sa), _p(cm),
+                                     _p(z), z.size))
+    return z
+
+
+def builtin_circuit_shape(kind: int, param: int) -> Tuple[int, int, int]:
+    shape = (C.c_uint64 * 6)()
+    check(lib().lzkp_builtin_circuit_csr(kind, param, shape, None, None, None))
+    return int(shape[0]), int(shape[1]), int(shape[2])
+
+
 class ProvingKey:
     """A proving key resident in HBM (lzkp_pk): the object the reference keeps in its OnceLock
     (src/backend/snark.rs:295-339), plus the circuit's R1CS matrices and NTT tables."""
@@ -162,6 +180,11 @@ class ProvingKey:
         status = np.zeros(n, np.int32)
         check(lib().lzkp_prove_batch(self._h, n, _p(z), _p(r), _p(s), _p(proofs), _p(status)))
         return proofs, status
+
+    def prove_batch_device(self, n: int, d_z: int, d_r: int, d_s: int, d_proofs: int, d_status: int,
+                           stream: int = 0) -> None:
+        """lzkp_prove_batch_device: all arguments are device pointers (ints); asynchronous on `stream`."""
+        check(lib().lzkp_prove_batch_device(self._h, n, d_z, d_r, d_s, d_proofs, d_status, stream))
 
     def prove_equality_batch(self, a, b, r, s, commitments=None):
         a = np.ascontiguousarray(a, np.uint64)

@@ -182,3 +182,20 @@ def test_zkp_backend_trait_input_length():
     assert zk.SnarkBackend.prove_membership_zk(1, [], bytes(32)) == b""   # snark.rs:406
     assert zk.SnarkBackend.prove_membership_zk(1, list(range(65)), bytes(32)) == b""
     assert zk.SnarkBackend.prove_membership_zk(9, [1, 2], bytes(32)) == b""   # snark.rs:415-418
+
+
+def test_builtin_witness_equals_oracle(co):
+    c = co.Circuit("equality")
+    for a in (0, 5, 2**64 - 1):
+        assert np.array_equal(engine.builtin_witness(engine.EQUALITY, 110, a, a), c.assign(a, a))
+    wrong = co.mimc_hash(99)
+    assert np.array_equal(engine.builtin_witness(engine.EQUALITY, 110, 7, 7, commitment=wrong),
+                          c.assign(7, 7, commitment=wrong))
+    chain = co.Circuit("equality", 300)                       # the synthetic MiMC-chain circuit (config 4 shape)
+    assert np.array_equal(engine.builtin_witness(engine.EQUALITY, 300, 12345, 12345), chain.assign(12345, 12345,
+                          commitment=engine.builtin_witness(engine.EQUALITY, 300, 12345, 12345)[1].tobytes()))
+    m = co.Circuit("membership")
+    for v, s in ((2, [1, 2, 3]), (9, list(range(64))), (2**64 - 1, [2**64 - 1])):
+        assert np.array_equal(engine.builtin_witness(engine.MEMBERSHIP, 64, v, set_=s), m.assign(v, set_=s))
+    with pytest.raises(zk.EngineError):
+        engine.builtin_witness(engine.MEMBERSHIP, 64, 7, set_=[1, 2, 3])
