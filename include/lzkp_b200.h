@@ -59,7 +59,11 @@ typedef struct lzkp_pk_options {
     int window_bits;          /* fixed-base table window c in [8,16]; 0 = choose from the memory budget */
     uint64_t table_budget_bytes; /* cap for the resident window tables; 0 = 60% of free device memory */
     uint32_t max_chunk;       /* proofs per device pass; 0 = default (8192) */
+    /* Single-proof sharding over several GPUs (large domains only): this process keeps only shard
+     * `shard_index` of `shard_count` cost-weighted point ranges of the five queries.  0 / 1 = unsharded. */
+    uint32_t shard_index, shard_count;
 } lzkp_pk_options;
+#define LZKP_PARTIAL_BYTES 768   /* 4 G1 XYZZ sums (a, b1, l, h) + 1 G2 XYZZ sum (b2), opaque device format */
 
 /* Select the CUDA device(s) this process drives (one process per GPU: n_devices == 1). Idempotent. */
 int lzkp_init(const int *devices, int n_devices);
@@ -154,6 +158,17 @@ int lzkp_prove_equality_batch_device(lzkp_pk *pk, size_t n_proofs, const void *d
 
 /* a3-a7 only: h_out is n_proofs x n x 32 B canonical. */
 int lzkp_witness_map(lzkp_pk *pk, size_t n_proofs, const uint8_t *z, uint8_t *h_out);
+
+/* Device-resident pieces of ONE large-domain proof, for splitting it across GPUs (one process per GPU):
+ *   lzkp_witness_map_device    z -> h on the rank that holds the circuit (then broadcast h, e.g. ncclBroadcast)
+ *   lzkp_prove_partial_device  every rank: the five MSMs over ITS point ranges -> LZKP_PARTIAL_BYTES
+ *   lzkp_prove_combine_device  one rank: add the gathered partial sums, assemble and serialize the proof
+ * All pointers are device pointers; calls are asynchronous on `stream`. */
+int lzkp_witness_map_device(lzkp_pk *pk, const void *d_z, void *d_h, void *stream);
+int lzkp_prove_partial_device(lzkp_pk *pk, const void *d_z, const void *d_r, const void *d_s, const void *d_h,
+                              void *d_partial, void *d_status, void *stream);
+int lzkp_prove_combine_device(lzkp_pk *pk, const void *d_partials, int n_partials, const void *d_r, const void *d_s,
+                              void *d_proof, void *stream);
 
 /* Variable-base MSM over arbitrary bases (ark affine uncompressed) and canonical scalars. */
 int lzkp_msm_g1(const uint8_t *bases_affine, const uint8_t *scalars, size_t n, uint8_t *out_affine);

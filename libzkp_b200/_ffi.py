@@ -21,10 +21,12 @@ LZKP_E_NOMEM = -5
 LZKP_E_UNSUPPORTED = -6
 LZKP_CIRCUIT_EQUALITY = 0
 LZKP_CIRCUIT_MEMBERSHIP = 1
+LZKP_PARTIAL_BYTES = 768
 
 
 class PkOptions(C.Structure):
-    _fields_ = [("window_bits", C.c_int), ("table_budget_bytes", C.c_uint64), ("max_chunk", C.c_uint32)]
+    _fields_ = [("window_bits", C.c_int), ("table_budget_bytes", C.c_uint64), ("max_chunk", C.c_uint32),
+                ("shard_index", C.c_uint32), ("shard_count", C.c_uint32)]
 
 
 # name -> (restype, argtypes); kept in one table so tests can check it against the header.
@@ -55,6 +57,9 @@ SIGNATURES = {
     "lzkp_prove_membership_batch": (_int, [_vp, _sz, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lzkp_prove_equality_batch_device": (_int, [_vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lzkp_witness_map": (_int, [_vp, _sz, _vp, _vp]),
+    "lzkp_witness_map_device": (_int, [_vp, _vp, _vp, _vp]),
+    "lzkp_prove_partial_device": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lzkp_prove_combine_device": (_int, [_vp, _vp, _int, _vp, _vp, _vp, _vp]),
     "lzkp_msm_g1": (_int, [_vp, _vp, _sz, _vp]),
     "lzkp_msm_g2": (_int, [_vp, _vp, _sz, _vp]),
     "lzkp_bases_load": (_int, [_int, _vp, _sz, _int, _int, _int, C.POINTER(_vp)]),

@@ -69,6 +69,11 @@ def process_batch(batch_id: int, rng=None) -> List[bytes]:   # batch.rs:110-140
         ops = _registry.pop(batch_id, None)
     if ops is None:
         raise InvalidInput(f"Invalid batch ID: {batch_id}")
+    return prove_operations(ops, rng)
+
+
+def prove_operations(ops: Sequence[Tuple], rng=None) -> List[bytes]:
+    """Grouped proving of a list of operations: one device call per circuit, results in input order."""
     out: List[bytes] = [b""] * len(ops)
     eq = [i for i, o in enumerate(ops) if o[0] == "equality"]
     mb = [i for i, o in enumerate(ops) if o[0] == "membership"]

@@ -120,6 +120,10 @@ struct lzkp_pk {
     bool large = false;
     MsmBases *L_a = nullptr, *L_b1 = nullptr, *L_b2 = nullptr, *L_l = nullptr, *L_h = nullptr;
     DBuf L_tmp, L_sa, L_sb, L_sl;
+    // single-proof sharding across GPUs: this rank's point range [lo, lo + cnt) of each query,
+    // in the order a, b1, l, h, b2 (extras +-delta included); unsharded = the full ranges
+    uint32_t shard_index = 0, shard_count = 1;
+    uint32_t L_lo[5] = {0, 0, 0, 0, 0}, L_cnt[5] = {0, 0, 0, 0, 0};
     cudaStream_t stream = nullptr;
     // optional per-region CUDA-event timing (lzkp_profile_*): pairs recorded on the launching stream
     struct Mark { int region; cudaEvent_t a, b; };
@@ -240,20 +244,42 @@ static int pk_load_impl(const uint8_t *bytes, size_t len, int validate, const lz
         // A = alpha + a_q[0] + sum_{j>=1} z_j a_q[j] + r delta: delta rides along as one more base (scalar r / s / rs)
         CUDA_TRY(cudaStreamCreate(&pk->stream));
         const int wb = opt && opt->window_bits ? opt->window_bits : 0;
-        auto load1 = [&](std::vector<host::G1Canon> v, size_t skip, const host::G1Canon *extra, MsmBases **out) {
+        pk->shard_count = opt && opt->shard_count > 1 ? opt->shard_count : 1;
+        pk->shard_index = pk->shard_count > 1 ? opt->shard_index : 0;
+        if (pk->shard_index >= pk->shard_count) return fail(LZKP_E_INVALID, "shard_index >= shard_count");
+        // cost-weighted split of the concatenation a | b1 | l | h | b2 (a G2 point costs ~2.8 G1 points)
+        const uint64_t sizes[5] = {nv, nv, (uint64_t)pk->n_wit + 1, (uint64_t)n - 1, nv}, wts[5] = {10, 10, 10, 10, 28};
+        uint64_t wtot = 0;
+        for (int q = 0; q < 5; q++) wtot += sizes[q] * wts[q];
+        const uint64_t w_lo = wtot * pk->shard_index / pk->shard_count, w_hi = wtot * (pk->shard_index + 1) / pk->shard_count;
+        uint64_t acc_w = 0;
+        for (int q = 0; q < 5; q++) {
+            // points of query q whose weighted start lies in [w_lo, w_hi)
+            auto first_at = [&](uint64_t w) -> uint64_t {        // smallest i with acc_w + i * wts >= w, clamped
+                if (w <= acc_w) return 0;
+                uint64_t i = (w - acc_w + wts[q] - 1) / wts[q];
+                return std::min<uint64_t>(i, sizes[q]);
+            };
+            uint64_t lo = first_at(w_lo), hi = first_at(w_hi);
+            if (pk->shard_index + 1 == pk->shard_count) hi = sizes[q];
+            pk->L_lo[q] = (uint32_t)lo;
+            pk->L_cnt[q] = (uint32_t)(hi - lo);
+            acc_w += sizes[q] * wts[q];
+        }
+        auto load1 = [&](std::vector<host::G1Canon> v, size_t skip, const host::G1Canon *extra, int q, MsmBases **out) {
             v.erase(v.begin(), v.begin() + skip);
             if (extra) v.push_back(*extra);
-            return msm_bases_load(1, reinterpret_cast<const uint8_t *>(v.data()), v.size(), wb, 1, validate, out, 1);
+            return msm_bases_load(1, reinterpret_cast<const uint8_t *>(v.data() + pk->L_lo[q]), pk->L_cnt[q], wb, 1, validate, out, 1);
         };
         host::G1Canon nd1 = neg_canon(delta_g1);
-        TRY(load1(a_q, 1, &delta_g1, &pk->L_a));
-        TRY(load1(b1_q, 1, &delta_g1, &pk->L_b1));
-        TRY(load1(l_q, 0, &nd1, &pk->L_l));
-        TRY(load1(h_q, 0, nullptr, &pk->L_h));
+        TRY(load1(a_q, 1, &delta_g1, 0, &pk->L_a));
+        TRY(load1(b1_q, 1, &delta_g1, 1, &pk->L_b1));
+        TRY(load1(l_q, 0, &nd1, 2, &pk->L_l));
+        TRY(load1(h_q, 0, nullptr, 3, &pk->L_h));
         {
             std::vector<host::G2Canon> v(b2_q.begin() + 1, b2_q.end());
             v.push_back(delta_g2);
-            TRY(msm_bases_load(2, reinterpret_cast<const uint8_t *>(v.data()), v.size(), wb, 1, validate, &pk->L_b2, 1));
+            TRY(msm_bases_load(2, reinterpret_cast<const uint8_t *>(v.data() + pk->L_lo[4]), pk->L_cnt[4], wb, 1, validate, &pk->L_b2, 1));
         }
         pk->c = wb ? wb : 16;
         pk->W = (255 + pk->c - 1) / pk->c;
@@ -519,8 +545,8 @@ static int run_witness_map(lzkp_pk *pk, uint32_t P, cudaStream_t st) {
 
 // From ws_z, r, s (device, canonical) to proofs (device).  status must be initialised by the caller.
 static int run_prove(lzkp_pk *pk, uint32_t P, const Fr *d_r, const Fr *d_s, uint8_t *d_proofs, int32_t *d_status,
-                     cudaStream_t st) {
-    TRY(run_witness_map(pk, P, st));
+                     cudaStream_t st, bool have_h = false) {
+    if (!have_h) TRY(run_witness_map(pk, P, st));
     if (pk->large) {
         if (P != 1) return fail(LZKP_E_STATE, "large-domain proving runs one proof per pass");
         const uint32_t nv = pk->n_vars, ni = pk->n_inst, nw = pk->n_wit;
@@ -539,17 +565,19 @@ static int run_prove(lzkp_pk *pk, uint32_t P, const Fr *d_r, const Fr *d_s, uint
         CUDA_TRY(cudaMemcpyAsync(sl, z + (size_t)ni * 32, (size_t)nw * 32, dd, st));
         CUDA_TRY(cudaMemcpyAsync(sl + (size_t)nw * 32, pk->ws_rs.p, 32, dd, st));
         G1XYZZ *res1 = pk->ws_res1.as<G1XYZZ>();
+        const uint32_t *lo = pk->L_lo, *cnt = pk->L_cnt;
         {
             Region reg(pk, LZKP_REGION_MSM_G1, st);
-            TRY(msm_device_raw(pk->L_a, sa, nv, res1 + 0, st));
-            TRY(msm_device_raw(pk->L_b1, sb, nv, res1 + 1, st));
-            TRY(msm_device_raw(pk->L_l, sl, nw + 1, res1 + 2, st));
-            TRY(msm_device_raw(pk->L_h, pk->ws_h.p, pk->n - 1, res1 + 3, st));
+            TRY(msm_device_raw(pk->L_a, sa + (size_t)lo[0] * 32, cnt[0], res1 + 0, st));
+            TRY(msm_device_raw(pk->L_b1, sb + (size_t)lo[1] * 32, cnt[1], res1 + 1, st));
+            TRY(msm_device_raw(pk->L_l, sl + (size_t)lo[2] * 32, cnt[2], res1 + 2, st));
+            TRY(msm_device_raw(pk->L_h, pk->ws_h.as<uint8_t>() + (size_t)lo[3] * 32, cnt[3], res1 + 3, st));
         }
         {
             Region reg(pk, LZKP_REGION_MSM_G2, st);
-            TRY(msm_device_raw(pk->L_b2, sb, nv, pk->ws_res2.p, st));
+            TRY(msm_device_raw(pk->L_b2, sb + (size_t)lo[4] * 32, cnt[4], pk->ws_res2.p, st));
         }
+        if (!d_proofs) return LZKP_OK;           // partial sums only (sharded proving): the caller combines
         Region reg(pk, LZKP_REGION_ASSEMBLE, st);
         LAUNCH(k_assemble, 1, 64, 0, st, res1, pk->ws_res2.as<G2XYZZ>(), pk->consts, d_r, d_s, 1u, d_proofs);
         return LZKP_OK;
@@ -681,6 +709,7 @@ int lzkp_pk_info(const lzkp_pk *pk, uint64_t info[8]) {
     if (!pk || !info) return fail(LZKP_E_INVALID, "null argument");
     info[0] = pk->n_vars; info[1] = pk->n_inst; info[2] = pk->n_wit; info[3] = pk->n;
     info[4] = (uint64_t)pk->c; info[5] = pk->W; info[6] = pk->table_bytes; info[7] = pk->max_chunk;
+    if (pk->large) info[7] = 1;
     return LZKP_OK;
 }
 
@@ -951,6 +980,53 @@ int lzkp_witness_map(lzkp_pk *pk, size_t n_proofs, const uint8_t *z, uint8_t *h_
         CUDA_TRY(cudaStreamSynchronize(st));
         CUDA_TRY(cudaGetLastError());
     }
+    return LZKP_OK;
+}
+
+int lzkp_witness_map_device(lzkp_pk *pk, const void *d_z, void *d_h, void *stream) {
+    if (!pk || !d_z || !d_h) return fail(LZKP_E_INVALID, "null argument");
+    TRY(ensure_device());
+    std::lock_guard<std::mutex> lk(pk->mu);
+    if (!pk->has_circuit) return fail(LZKP_E_STATE, "lzkp_circuit_load has not been called");
+    cudaStream_t st = (cudaStream_t)stream;
+    TRY(ensure_workspace(pk, 1));
+    CUDA_TRY(cudaMemcpyAsync(pk->ws_z.p, d_z, (size_t)pk->n_vars * 32, cudaMemcpyDeviceToDevice, st));
+    TRY(run_witness_map(pk, 1, st));
+    CUDA_TRY(cudaMemcpyAsync(d_h, pk->ws_h.p, (size_t)pk->n * 32, cudaMemcpyDeviceToDevice, st));
+    return LZKP_OK;
+}
+
+int lzkp_prove_partial_device(lzkp_pk *pk, const void *d_z, const void *d_r, const void *d_s, const void *d_h,
+                              void *d_partial, void *d_status, void *stream) {
+    if (!pk || !d_z || !d_r || !d_s || !d_h || !d_partial || !d_status) return fail(LZKP_E_INVALID, "null argument");
+    TRY(ensure_device());
+    std::lock_guard<std::mutex> lk(pk->mu);
+    if (!pk->large) return fail(LZKP_E_STATE, "sharded proving needs a large-domain proving key");
+    cudaStream_t st = (cudaStream_t)stream;
+    TRY(ensure_workspace(pk, 1));
+    CUDA_TRY(cudaMemsetAsync(d_status, 0, 4, st));
+    CUDA_TRY(cudaMemcpyAsync(pk->ws_z.p, d_z, (size_t)pk->n_vars * 32, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(pk->ws_h.p, d_h, (size_t)pk->n * 32, cudaMemcpyDeviceToDevice, st));
+    TRY(run_prove(pk, 1, (const Fr *)d_r, (const Fr *)d_s, nullptr, (int32_t *)d_status, st, true));
+    uint8_t *out = (uint8_t *)d_partial;
+    CUDA_TRY(cudaMemcpyAsync(out, pk->ws_res1.p, 4 * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(out + 4 * sizeof(G1XYZZ), pk->ws_res2.p, sizeof(G2XYZZ), cudaMemcpyDeviceToDevice, st));
+    return LZKP_OK;
+}
+
+int lzkp_prove_combine_device(lzkp_pk *pk, const void *d_partials, int n_partials, const void *d_r, const void *d_s,
+                              void *d_proof, void *stream) {
+    if (!pk || !d_partials || n_partials < 1 || !d_r || !d_s || !d_proof) return fail(LZKP_E_INVALID, "bad argument");
+    TRY(ensure_device());
+    std::lock_guard<std::mutex> lk(pk->mu);
+    if (!pk->large) return fail(LZKP_E_STATE, "sharded proving needs a large-domain proving key");
+    cudaStream_t st = (cudaStream_t)stream;
+    TRY(ensure_workspace(pk, 1));
+    LAUNCH(k_sum_partials, 1, 32, 0, st, (const uint8_t *)d_partials, (uint32_t)n_partials, pk->ws_res1.as<G1XYZZ>(),
+           pk->ws_res2.as<G2XYZZ>());
+    LAUNCH(k_assemble, 1, 64, 0, st, pk->ws_res1.as<G1XYZZ>(), pk->ws_res2.as<G2XYZZ>(), pk->consts, (const Fr *)d_r,
+           (const Fr *)d_s, 1u, (uint8_t *)d_proof);
+    CUDA_TRY(cudaGetLastError());
     return LZKP_OK;
 }
 

@@ -352,6 +352,24 @@ __global__ void __launch_bounds__(64) k_assemble(const G1XYZZ *g1, const G2XYZZ 
     write_g2(out + 64, B2.to_affine());
 }
 
+// Sharded single proof: partial[i] = 4 G1 XYZZ sums (a, b1, l, h) then 1 G2 XYZZ sum (b2) of rank i's point ranges.
+// Thread q < 4 adds up slot q over the ranks, thread 4 the G2 slot.
+constexpr uint32_t kPartialBytes = 4 * sizeof(G1XYZZ) + sizeof(G2XYZZ);
+__global__ void k_sum_partials(const uint8_t *partials, uint32_t n, G1XYZZ *g1, G2XYZZ *g2) {
+    const uint32_t q = threadIdx.x;
+    if (q < 4) {
+        G1XYZZ acc = G1XYZZ::inf();
+        for (uint32_t i = 0; i < n; i++)
+            acc.add_cold(ld_vec(reinterpret_cast<const G1XYZZ *>(partials + (size_t)i * kPartialBytes) + q));
+        st_vec(g1 + q, acc);
+    } else if (q == 4) {
+        G2XYZZ acc = G2XYZZ::inf();
+        for (uint32_t i = 0; i < n; i++)
+            acc.add_cold(ld_vec(reinterpret_cast<const G2XYZZ *>(partials + (size_t)i * kPartialBytes + 4 * sizeof(G1XYZZ))));
+        st_vec(g2, acc);
+    }
+}
+
 // ---------------------------------------------------------------- pk-load helpers
 // out = a + b (affine), one thread
 template <class F>

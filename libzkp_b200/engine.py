@@ -123,10 +123,10 @@ class ProvingKey:
     (src/backend/snark.rs:295-339), plus the circuit's R1CS matrices and NTT tables."""
 
     def __init__(self, pk_bytes: bytes, validate: bool = False, window_bits: int = 0,
-                 table_budget_bytes: int = 0, max_chunk: int = 0):
+                 table_budget_bytes: int = 0, max_chunk: int = 0, shard_index: int = 0, shard_count: int = 0):
         self._h = C.c_void_p()
         buf = np.frombuffer(pk_bytes, dtype=np.uint8)
-        opt = _ffi.PkOptions(window_bits, table_budget_bytes, max_chunk)
+        opt = _ffi.PkOptions(window_bits, table_budget_bytes, max_chunk, shard_index, shard_count)
         check(lib().lzkp_pk_load_ex(_p(buf), len(pk_bytes), int(validate), C.byref(opt), C.byref(self._h)))
         info = (C.c_uint64 * 8)()
         check(lib().lzkp_pk_info(self._h, info))
@@ -185,6 +185,18 @@ class ProvingKey:
                            stream: int = 0) -> None:
         """lzkp_prove_batch_device: all arguments are device pointers (ints); asynchronous on `stream`."""
         check(lib().lzkp_prove_batch_device(self._h, n, d_z, d_r, d_s, d_proofs, d_status, stream))
+
+    # ---- single large proof split across GPUs (device pointers, asynchronous on `stream`)
+    def witness_map_device(self, d_z: int, d_h: int, stream: int = 0) -> None:
+        check(lib().lzkp_witness_map_device(self._h, d_z, d_h, stream))
+
+    def prove_partial_device(self, d_z: int, d_r: int, d_s: int, d_h: int, d_partial: int, d_status: int,
+                             stream: int = 0) -> None:
+        check(lib().lzkp_prove_partial_device(self._h, d_z, d_r, d_s, d_h, d_partial, d_status, stream))
+
+    def prove_combine_device(self, d_partials: int, n_partials: int, d_r: int, d_s: int, d_proof: int,
+                             stream: int = 0) -> None:
+        check(lib().lzkp_prove_combine_device(self._h, d_partials, n_partials, d_r, d_s, d_proof, stream))
 
     def prove_equality_batch(self, a, b, r, s, commitments=None):
         a = np.ascontiguousarray(a, np.uint64)

@@ -94,3 +94,51 @@ def test_config4_2_20_constraints_proof_verifies(po, trapdoor, frs, co):
     h = pk.witness_map(z)
     assert not h[0, -1].any() and h[0, -2].any()
     pk.close()
+
+
+@pytest.mark.parametrize("shards", [2, 3, 8])
+def test_sharded_single_proof_partials_combine(co, trapdoor, frs, shards):
+    # §8e single-proof split, emulated on one GPU: every "rank" is a pk holding only its point ranges;
+    # partial sums of all shards are combined by shard 0.  Bit-exact against the oracle's proof.
+    import torch
+    rounds = 2730
+    circ = co.Circuit("equality", rounds)
+    pk_bytes, _ = circ.setup(trapdoor)
+    z = engine.builtin_witness(engine.EQUALITY, rounds, 77, 77)
+    r, s = frs(4, 1), frs(40, 1)
+    want = co.prove(circ, co.ProvingKey(pk_bytes), z, co.fr_list(r)[0], co.fr_list(s)[0])
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d_z, d_r, d_s = t(z), t(r[0]), t(s[0])
+    pks = [engine.ProvingKey(pk_bytes, shard_index=i, shard_count=shards) for i in range(shards)]
+    pks[0].circuit_builtin(engine.EQUALITY, rounds)
+    d_h = torch.zeros((circ.n, 32), dtype=torch.uint8, device=dev)
+    pks[0].witness_map_device(d_z.data_ptr(), d_h.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(d_h.cpu().numpy(), circ.witness_map(z))
+    partials = torch.zeros((shards, 768), dtype=torch.uint8, device=dev)
+    status = torch.zeros(shards, dtype=torch.int32, device=dev)
+    for i, pk in enumerate(pks):
+        pk.prove_partial_device(d_z.data_ptr(), d_r.data_ptr(), d_s.data_ptr(), d_h.data_ptr(), partials[i].data_ptr(),
+                                status[i:].data_ptr())
+    proof = torch.zeros(256, dtype=torch.uint8, device=dev)
+    pks[0].prove_combine_device(partials.data_ptr(), shards, d_r.data_ptr(), d_s.data_ptr(), proof.data_ptr())
+    torch.cuda.synchronize()
+    assert not status.any()
+    assert proof.cpu().numpy().tobytes() == want
+    for pk in pks:
+        pk.close()
+
+
+def test_sharded_prover_world_1(co, trapdoor, frs):
+    import torch
+    from libzkp_b200.multi import ShardedProver
+    rounds = 2730
+    circ = co.Circuit("equality", rounds)
+    pk_bytes, _ = circ.setup(trapdoor)
+    z = engine.builtin_witness(engine.EQUALITY, rounds, 5, 5)
+    r, s = frs(4, 1), frs(40, 1)
+    sp = ShardedProver(pk_bytes, engine.EQUALITY, rounds, 0, 1, torch.device("cuda", 0))
+    got = sp.prove(z, r[0].tobytes(), s[0].tobytes())
+    assert got == co.prove(circ, co.ProvingKey(pk_bytes), z, co.fr_list(r)[0], co.fr_list(s)[0])
+    sp.close()
