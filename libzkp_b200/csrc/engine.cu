@@ -471,6 +471,8 @@ static int circuit_install(lzkp_pk *pk, uint32_t m, uint32_t n_inst, uint32_t n_
 
 // ------------------------------------------------------------------------ proving pipeline
 static inline int item_variant(uint32_t P) { return P >= 2048 ? 2 : (P >= 256 ? 1 : 0); }
+// G2 runs 64-thread CTAs at 255 registers: finer items keep every SM partition supplied with warps
+static inline int item_variant_g2(uint32_t P) { return P >= 2048 ? 1 : 0; }
 static int ensure_workspace(lzkp_pk *pk, uint32_t P) {
     if (P <= pk->ws_chunk) return LZKP_OK;
     size_t part1 = 0, part2 = 0;       // worst case over the batch sizes <= P
@@ -478,7 +480,7 @@ static int ensure_workspace(lzkp_pk *pk, uint32_t P) {
         if (q > P) break;
         uint32_t pp = q == 1u ? std::min(P, 255u) : (q == 256u ? std::min(P, 2047u) : P);
         part1 = std::max(part1, (size_t)pk->g1.n_items[item_variant(pp)] * pp);
-        part2 = std::max(part2, (size_t)pk->g2.n_items[item_variant(pp)] * pp);
+        part2 = std::max(part2, (size_t)pk->g2.n_items[item_variant_g2(pp)] * pp);
     }
     const size_t nv = pk->n_vars, n = pk->n;
     TRY(pk->ws_z.ensure(P * nv * 32));
@@ -579,7 +581,7 @@ static int run_prove(lzkp_pk *pk, uint32_t P, const Fr *d_r, const Fr *d_s, uint
         }
         if (!d_proofs) return LZKP_OK;           // partial sums only (sharded proving): the caller combines
         Region reg(pk, LZKP_REGION_ASSEMBLE, st);
-        LAUNCH(k_assemble, 1, 64, 0, st, res1, pk->ws_res2.as<G2XYZZ>(), pk->consts, d_r, d_s, 1u, d_proofs);
+        LAUNCH(k_assemble, 1, 128, 0, st, res1, pk->ws_res2.as<G2XYZZ>(), pk->consts, d_r, d_s, 1u, d_proofs);
         return LZKP_OK;
     }
     const uint32_t c = pk->c, W = pk->W, gx = (P + 127) / 128;
@@ -595,14 +597,14 @@ static int run_prove(lzkp_pk *pk, uint32_t P, const Fr *d_r, const Fr *d_s, uint
     }
     // item granularity: enough blocks to fill 148 SMs even for small batches
     int v = item_variant(P);
-    auto args = [&](MsmPlan &pl, void *partial, void *out) {
-        return BatchMsmArgs{pl.table.p, pk->N, pl.unit_dig.as<uint32_t>(), pl.unit_tbl.as<uint32_t>(), pl.items[v].p,
-                            pl.n_items[v], pl.msm_items[v].p, pl.n_msm, dig, P, partial, out};
+    auto args = [&](MsmPlan &pl, int iv, void *partial, void *out) {
+        return BatchMsmArgs{pl.table.p, pk->N, pl.unit_dig.as<uint32_t>(), pl.unit_tbl.as<uint32_t>(), pl.items[iv].p,
+                            pl.n_items[iv], pl.msm_items[iv].p, pl.n_msm, dig, P, partial, out};
     };
-    { Region reg(pk, LZKP_REGION_MSM_G1, st); batch_msm_g1(args(pk->g1, pk->ws_part1.p, pk->ws_res1.p), st); }
-    { Region reg(pk, LZKP_REGION_MSM_G2, st); batch_msm_g2(args(pk->g2, pk->ws_part2.p, pk->ws_res2.p), st); }
+    { Region reg(pk, LZKP_REGION_MSM_G1, st); batch_msm_g1(args(pk->g1, v, pk->ws_part1.p, pk->ws_res1.p), st); }
+    { Region reg(pk, LZKP_REGION_MSM_G2, st); batch_msm_g2(args(pk->g2, item_variant_g2(P), pk->ws_part2.p, pk->ws_res2.p), st); }
     Region reg(pk, LZKP_REGION_ASSEMBLE, st);
-    LAUNCH(k_assemble, (P + 63) / 64, 64, 0, st, pk->ws_res1.as<G1XYZZ>(), pk->ws_res2.as<G2XYZZ>(), pk->consts, d_r, d_s,
+    LAUNCH(k_assemble, (P + 31) / 32, 128, 0, st, pk->ws_res1.as<G1XYZZ>(), pk->ws_res2.as<G2XYZZ>(), pk->consts, d_r, d_s,
            P, d_proofs);
     return LZKP_OK;
 }
@@ -1024,7 +1026,7 @@ int lzkp_prove_combine_device(lzkp_pk *pk, const void *d_partials, int n_partial
     TRY(ensure_workspace(pk, 1));
     LAUNCH(k_sum_partials, 1, 32, 0, st, (const uint8_t *)d_partials, (uint32_t)n_partials, pk->ws_res1.as<G1XYZZ>(),
            pk->ws_res2.as<G2XYZZ>());
-    LAUNCH(k_assemble, 1, 64, 0, st, pk->ws_res1.as<G1XYZZ>(), pk->ws_res2.as<G2XYZZ>(), pk->consts, (const Fr *)d_r,
+    LAUNCH(k_assemble, 1, 128, 0, st, pk->ws_res1.as<G1XYZZ>(), pk->ws_res2.as<G2XYZZ>(), pk->consts, (const Fr *)d_r,
            (const Fr *)d_s, 1u, (uint8_t *)d_proof);
     CUDA_TRY(cudaGetLastError());
     return LZKP_OK;

@@ -332,24 +332,42 @@ struct ProofConsts {
     G2Affine b2;        // beta_g2 + b_g2_query[0]
 };
 // g1[q * P + p]: q = 0 A-sum (incl. r*delta), 1 B1-sum (incl. s*delta), 2 L-sum (incl. -rs*delta), 3 H-sum.
-__global__ void __launch_bounds__(64) k_assemble(const G1XYZZ *g1, const G2XYZZ *g2, ProofConsts K, const Fr *r,
-                                                 const Fr *s, uint32_t P, uint8_t *proofs) {
-    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P) return;
-    G1XYZZ A = ld_vec(g1 + p);
-    A.madd_cold(K.a0);
-    G1XYZZ B1 = ld_vec(g1 + (size_t)P + p);
-    B1.madd_cold(K.b0);
-    G1XYZZ Cc = scalar_mul(A, ld_vec(s + p));
-    Cc.add_cold(scalar_mul(B1, ld_vec(r + p)));
-    Cc.add_cold(ld_vec(g1 + 2 * (size_t)P + p));
-    Cc.add_cold(ld_vec(g1 + 3 * (size_t)P + p));
+// The stage is a chain of ~4000 dependent field products per proof (two 254-bit scalar multiplications,
+// three inversions), so it is latency-bound: the four independent strands of a proof run on four warps of
+// the CTA (warp-uniform roles, lane = proof) and meet once in shared memory.
+//   warp 0: s * A, then C = s*A + r*B1 + L + H -> affine -> bytes      warp 2: A -> affine -> bytes
+//   warp 1: r * B1                                                     warp 3: B (G2) -> affine -> bytes
+__global__ void __launch_bounds__(128) k_assemble(const G1XYZZ *g1, const G2XYZZ *g2, ProofConsts K, const Fr *r,
+                                                  const Fr *s, uint32_t P, uint8_t *proofs) {
+    __shared__ uint4 sm_raw[32 * sizeof(G1XYZZ) / 16];
+    G1XYZZ *sm = reinterpret_cast<G1XYZZ *>(sm_raw);
+    const uint32_t role = threadIdx.x >> 5, lane = threadIdx.x & 31, p = blockIdx.x * 32 + lane;
+    const bool live = p < P;
     uint8_t *out = proofs + (size_t)p * 256;
-    write_g1(out, A.to_affine());
-    write_g1(out + 192, Cc.to_affine());
-    G2XYZZ B2 = ld_vec(g2 + p);
-    B2.madd_cold(K.b2);
-    write_g2(out + 64, B2.to_affine());
+    G1XYZZ acc = G1XYZZ::inf();
+    if (live) {
+        if (role == 0 || role == 2) {
+            G1XYZZ A = ld_vec(g1 + p);
+            A.madd_cold(K.a0);
+            if (role == 2) write_g1(out, A.to_affine());
+            else acc = scalar_mul(A, ld_vec(s + p));
+        } else if (role == 1) {
+            G1XYZZ B1 = ld_vec(g1 + (size_t)P + p);
+            B1.madd_cold(K.b0);
+            st_vec(sm + lane, scalar_mul(B1, ld_vec(r + p)));
+        } else {
+            G2XYZZ B2 = ld_vec(g2 + p);
+            B2.madd_cold(K.b2);
+            write_g2(out + 64, B2.to_affine());
+        }
+    }
+    __syncthreads();
+    if (role == 0 && live) {
+        acc.add_cold(ld_vec(sm + lane));
+        acc.add_cold(ld_vec(g1 + 2 * (size_t)P + p));
+        acc.add_cold(ld_vec(g1 + 3 * (size_t)P + p));
+        write_g1(out + 192, acc.to_affine());
+    }
 }
 
 // Sharded single proof: partial[i] = 4 G1 XYZZ sums (a, b1, l, h) then 1 G2 XYZZ sum (b2) of rank i's point ranges.
