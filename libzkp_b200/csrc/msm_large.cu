@@ -288,6 +288,52 @@ __global__ void __launch_bounds__(32) k_red_finish(const XYZZ<F> *__restrict__ o
     if (threadIdx.x == 0) st_vec(R + set, v);
 }
 
+// Resident mode (one bucket set): sum_b (b+1) B[b] straight from bit planes of (b+1).
+// plane p: sum of B[b] over buckets with bit p of (b+1) set.  Every thread first adds up kRedSer masked
+// buckets serially (all lanes busy), only then does the CTA run a tree.  grid (NB / (128 * kRedSer), c)
+constexpr uint32_t kRedSer = 16;
+template <class F>
+__global__ void __launch_bounds__(128) k_red_direct1(const XYZZ<F> *__restrict__ buckets, uint32_t NB,
+                                                     XYZZ<F> *__restrict__ out1) {
+    extern __shared__ uint4 smem_raw[];
+    XYZZ<F> *sm = reinterpret_cast<XYZZ<F> *>(smem_raw);
+    const uint32_t p = blockIdx.y, b0 = blockIdx.x * (128 * kRedSer) + threadIdx.x;
+    XYZZ<F> v = XYZZ<F>::inf();
+#pragma unroll 1
+    for (uint32_t j = 0; j < kRedSer; j++) {
+        const uint32_t b = b0 + j * 128;
+        if (b < NB && (((b + 1) >> p) & 1u)) v.add_cold(ld_vec(buckets + b));
+    }
+    block_tree_sum<F, 128>(v, sm);
+    if (threadIdx.x == 0) st_vec(out1 + (size_t)p * gridDim.x + blockIdx.x, v);
+}
+// per plane: tree over the nblk partial sums, then p doublings.  grid (c), 128 threads
+template <class F>
+__global__ void __launch_bounds__(128) k_red_direct2(const XYZZ<F> *__restrict__ out1, uint32_t nblk,
+                                                     XYZZ<F> *__restrict__ out2) {
+    extern __shared__ uint4 smem_raw[];
+    XYZZ<F> *sm = reinterpret_cast<XYZZ<F> *>(smem_raw);
+    const uint32_t p = blockIdx.x;
+    XYZZ<F> v = XYZZ<F>::inf();
+    for (uint32_t i = threadIdx.x; i < nblk; i += 128) v.add_cold(ld_vec(out1 + (size_t)p * nblk + i));
+    block_tree_sum<F, 128>(v, sm);
+    if (threadIdx.x == 0) {
+#pragma unroll 1
+        for (uint32_t d = 0; d < p; d++) v.dbl_cold();
+        st_vec(out2 + p, v);
+    }
+}
+// R[0] = sum over the planes.  32 threads
+template <class F>
+__global__ void __launch_bounds__(32) k_red_direct3(const XYZZ<F> *__restrict__ out2, uint32_t planes, XYZZ<F> *__restrict__ R) {
+    extern __shared__ uint4 smem_raw[];
+    XYZZ<F> *sm = reinterpret_cast<XYZZ<F> *>(smem_raw);
+    XYZZ<F> v = XYZZ<F>::inf();
+    if (threadIdx.x < planes) v = ld_vec(out2 + threadIdx.x);
+    block_tree_sum<F, 32>(v, sm);
+    if (threadIdx.x == 0) st_vec(R, v);
+}
+
 // ---------------------------------------------------------------- 6. window combination, output
 // generic mode: result = sum_w 2^(c*w) R[w]
 template <class F>
@@ -436,7 +482,7 @@ static int bases_prepare(MsmBases *B, const uint8_t *bases_bytes, size_t n, int 
     TRY(B->long_list.alloc(((size_t)2 * B->T / kMergeCap + 2) * 4));
     TRY(B->Sg.alloc((size_t)B->sets * B->NG * sizeof(XYZZ<F>)));
     TRY(B->Ag.alloc((size_t)B->sets * B->NG * sizeof(XYZZ<F>)));
-    TRY(B->out1.alloc((size_t)B->sets * (B->LP + 1) * B->nblk * sizeof(XYZZ<F>)));
+    TRY(B->out1.alloc(std::max((size_t)B->sets * (B->LP + 1) * B->nblk, (size_t)B->c * ((B->NB + 127) / 128)) * sizeof(XYZZ<F>)));
     TRY(B->R.alloc((size_t)B->sets * sizeof(XYZZ<F>)));
     TRY(B->d_scalars.alloc((size_t)n1 * 32));
     TRY(B->d_out.alloc(BYTES));
@@ -494,12 +540,19 @@ static int msm_run(MsmBases *B, const Fr *d_scalars, uint32_t n_used, uint8_t *d
     LAUNCH((k_long_run<F>), (unsigned)(fin / kMergeCap + 1), 128, 128 * sizeof(X), st, pk + B->lvl_off[kSegLevels],
            pp + B->lvl_off[kSegLevels], count, (uint32_t)kChunk, (uint32_t)kSeg, (uint32_t)(kSegLevels + 1), B->buckets.as<X>(),
            B->long_list.as<uint32_t>());
+    if (B->sets == 1) {
+        const uint32_t nb1 = (B->NB + 128 * kRedSer - 1) / (128 * kRedSer);
+        LAUNCH((k_red_direct1<F>), dim3(nb1, B->c), 128, 128 * sizeof(X), st, B->buckets.as<X>(), B->NB, B->out1.as<X>());
+        LAUNCH((k_red_direct2<F>), B->c, 128, 128 * sizeof(X), st, B->out1.as<X>(), nb1, B->Sg.as<X>());
+        LAUNCH((k_red_direct3<F>), 1, 32, 32 * sizeof(X), st, B->Sg.as<X>(), B->c, B->R.as<X>());
+    } else {
     const uint32_t ng_total = B->sets * B->NG;
     LAUNCH((k_red_groups<F>), (ng_total + 127) / 128, 128, 0, st, B->buckets.as<X>(), ng_total, B->Sg.as<X>(), B->Ag.as<X>());
     LAUNCH((k_red_planes<F>), dim3(B->nblk, B->LP + 1, B->sets), 128, 128 * sizeof(X), st, B->Sg.as<X>(), B->Ag.as<X>(), B->NG,
            B->LP, B->out1.as<X>());
     LAUNCH((k_red_finish<F>), B->sets, 32, 32 * sizeof(X), st, B->out1.as<X>(), B->nblk, B->LP, B->R.as<X>());
-    if (B->sets > 1) LAUNCH((k_horner<F>), 1, 1, 0, st, B->R.as<X>(), B->sets, B->c);
+    LAUNCH((k_horner<F>), 1, 1, 0, st, B->R.as<X>(), B->sets, B->c);
+    }
     if (raw) CUDA_TRY(cudaMemcpyAsync(d_out, B->R.p, sizeof(X), cudaMemcpyDeviceToDevice, st));
     else LAUNCH((k_finish<F, BYTES>), 1, 1, 0, st, B->R.as<X>(), d_out);
     CUDA_TRY(cudaGetLastError());
@@ -520,6 +573,8 @@ int msm_bases_load(int group, const uint8_t *bases, size_t n, int window_bits, i
     if (!attr) {
         cudaFuncSetAttribute(k_long_run<Fq2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * (int)sizeof(G2XYZZ));
         cudaFuncSetAttribute(k_red_planes<Fq2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * (int)sizeof(G2XYZZ));
+        cudaFuncSetAttribute(k_red_direct1<Fq2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * (int)sizeof(G2XYZZ));
+        cudaFuncSetAttribute(k_red_direct2<Fq2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * (int)sizeof(G2XYZZ));
         attr = true;
     }
     *out = B;

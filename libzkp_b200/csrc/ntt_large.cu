@@ -100,16 +100,38 @@ __global__ void __launch_bounds__(1024) k_ntt_pass(const Fr *__restrict__ in, Fr
     }
     __syncthreads();
 
-    // ---- n_q-point decimation-in-frequency NTT per column: natural in, bit-reversed out
-    for (uint32_t lh = b; lh-- > 0;) {
-        const uint32_t h = 1u << lh;
+    // ---- n_q-point decimation-in-frequency NTT per column: natural in, bit-reversed out.
+    // Two stages per shared-memory round trip (radix-4 in registers): a thread owns the four elements
+    // i, i+Q, i+2Q, i+3Q (Q = quarter span), runs the span-2Q butterflies then the span-Q ones.
+    int lh = (int)b;
+    while (lh >= 2) {
+        const uint32_t H = 1u << (lh - 1), Q = H >> 1;                 // half-distances of the two stages
+        for (uint32_t t = threadIdx.x; t < E / 4; t += blockDim.x) {
+            const uint32_t c = t >> (b - 2), tt = t & ((nq >> 2) - 1);
+            const uint32_t low = tt & (Q - 1), i = (c << b) + (((tt >> (lh - 2)) << lh) | low);
+            Fr x0 = s.get(i), x1 = s.get(i + Q), x2 = s.get(i + H), x3 = s.get(i + H + Q);
+            // stage with half-distance H: twiddle exponent (index mod H) << (b - lh)
+            const uint32_t k0 = low, k1 = low + Q;
+            Fr y0 = x0 + x2, y2 = x0 - x2, y1 = x1 + x3, y3 = x1 - x3;
+            if (k0) y2 = y2 * ldg_vec(A.tile_tw + ((k0 << (b - lh)) << A.tw_shift));
+            y3 = y3 * ldg_vec(A.tile_tw + ((k1 << (b - lh)) << A.tw_shift));
+            // stage with half-distance Q: twiddle exponent (index mod Q) << (b - lh + 1), shared by both pairs
+            Fr z0 = y0 + y1, z1 = y0 - y1, z2 = y2 + y3, z3 = y2 - y3;
+            if (lh > 2 && low) {
+                Fr w = ldg_vec(A.tile_tw + ((low << (b - lh + 1)) << A.tw_shift));
+                z1 = z1 * w;
+                z3 = z3 * w;
+            }
+            s.put(i, z0); s.put(i + Q, z1); s.put(i + H, z2); s.put(i + H + Q, z3);
+        }
+        __syncthreads();
+        lh -= 2;
+    }
+    if (lh == 1) {                                                       // odd number of stages: last radix-2, no twiddle
         for (uint32_t bf = threadIdx.x; bf < E / 2; bf += blockDim.x) {
-            uint32_t c = bf >> (b - 1), t = bf & ((nq >> 1) - 1);
-            uint32_t k = t & (h - 1), i = (c << b) + (((t >> lh) << (lh + 1)) | k);
-            Fr x = s.get(i), y = s.get(i + h);
-            s.put(i, x + y);
-            Fr d = x - y;
-            s.put(i + h, lh == 0 ? d : d * ldg_vec(A.tile_tw + ((k << (b - 1 - lh)) << A.tw_shift)));
+            Fr x = s.get(2 * bf), y = s.get(2 * bf + 1);
+            s.put(2 * bf, x + y);
+            s.put(2 * bf + 1, x - y);
         }
         __syncthreads();
     }
@@ -230,7 +252,7 @@ int large_ntt_device(void *d_in, void *d_out, uint32_t log_n, int inverse, int c
         A.log_cols = log_stride >= 1 ? 1 : 0;
         A.tw_shift = P->tile_max - b;
         const uint32_t E = 1u << (b + A.log_cols);
-        const uint32_t threads = std::max(32u, std::min(1024u, E / 2));
+        const uint32_t threads = std::max(32u, std::min(1024u, E / 4));
         const size_t tiles = ((size_t)1 << log_n) >> (b + A.log_cols);
         const bool last = q + 1 == P->n_pass;
         LAUNCH(k_ntt_pass, (unsigned)tiles, threads, (size_t)32 * E, st, (const Fr *)d_in, (Fr *)(last ? d_out : d_in), A);

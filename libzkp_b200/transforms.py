@@ -77,9 +77,82 @@ def bench_ntt(torch, dev, imad_peak, hbm_gbs, log_n=22, iters=10, inverse=False,
             "hbm_frac_of_measured_peak": 64 * n / (ms * 1e-3) / 1e9 / hbm_gbs}
 
 
+def _toxic(seed=1):
+    # SplitMix64 -> five canonical non-zero scalars (synthetic benchmark key; never use a seeded key in production)
+    st = [seed & 0xFFFFFFFFFFFFFFFF]
+
+    def nxt():
+        st[0] = (st[0] + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+        z = st[0]
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+        return z ^ (z >> 31)
+    out = []
+    while len(out) < 5:
+        v = sum(nxt() << (64 * i) for i in range(4)) & ((1 << 254) - 1)
+        if 0 < v < R_MOD:
+            out.append(v)
+    return out
+
+
+def bench_large_proof(torch, dev, rounds=349524, iters=5):
+    """BASELINE.json configs[3]: one proof of the 2^20-constraint MiMC-chain circuit, inputs resident in HBM."""
+    import time
+    t0 = time.perf_counter()
+    pk_bytes, _ = engine.setup_builtin(engine.EQUALITY, rounds, _toxic(1))
+    t_setup = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    pk = engine.ProvingKey(pk_bytes)
+    pk.circuit_builtin(engine.EQUALITY, rounds)
+    torch.cuda.synchronize()
+    t_load = time.perf_counter() - t0
+    z = torch.from_numpy(engine.builtin_witness(engine.EQUALITY, rounds, 6, 6)).to(dev)
+    rs = _uniform_fr(torch, dev, 2, 4)
+    proof = torch.zeros(256, dtype=torch.uint8, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    engine.profile_enable(True)
+    ms = _time(torch, lambda: pk.prove_batch_device(1, z.data_ptr(), rs[0].data_ptr(), rs[1].data_ptr(), proof.data_ptr(),
+                                                    status.data_ptr(), stream), iters, warmup=2)
+    reg = pk.profile_read(reset=True)
+    engine.profile_enable(False)
+    out = {"constraints": 3 * rounds + 2, "domain": pk.n, "ms_per_proof": ms, "proofs_per_s": 1e3 / ms,
+           "stage_ms": {k: v[0] / max(v[1], 1) for k, v in reg.items() if v[1]}, "setup_s": t_setup, "pk_load_s": t_load,
+           "pk_mib": len(pk_bytes) / 2**20, "resident_bases_gib": pk.table_bytes / 2**30, "status": int(status.item())}
+    pk.close()
+    return out
+
+
+def bench_membership(torch, dev, n=1024, iters=5):
+    """BASELINE.json configs[2] at the reference's MAX_SET_SIZE = 64 (the 1024-slot variant is not runnable on the
+    reference, SURVEY.md headline fact 6): batch of 1024 membership proofs through the host-buffer C ABI."""
+    import time
+    pk_bytes, _ = engine.setup_builtin(engine.MEMBERSHIP, 64, _toxic(1))
+    pk = engine.ProvingKey(pk_bytes)
+    pk.circuit_builtin(engine.MEMBERSHIP, 64)
+    rng = np.random.default_rng(5)
+    sets = rng.integers(0, 2**63, size=(n, 64), dtype=np.uint64)
+    lens = np.full(n, 64, np.uint32)
+    vals = sets[np.arange(n), np.arange(n) % 64].copy()
+    r = _uniform_fr(torch, dev, n, 7).cpu().numpy().view(np.uint8).reshape(n, 32)
+    s = _uniform_fr(torch, dev, n, 8).cpu().numpy().view(np.uint8).reshape(n, 32)
+    for _ in range(2):
+        proofs, _, status = pk.prove_membership_batch(vals, sets, lens, r, s)
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        proofs, _, status = pk.prove_membership_batch(vals, sets, lens, r, s)
+    dt = (time.perf_counter() - t0) / iters
+    out = {"batch": n, "set_slots": 64, "ms_per_batch": 1e3 * dt, "proofs_per_s_e2e": n / dt, "failed": int((status != 0).sum()),
+           "table_gb": pk.table_bytes / 1e9, "window_bits": pk.window_bits}
+    pk.close()
+    return out
+
+
 def bench(torch, dev, imad_peak, hbm_gbs):
     return {"msm_g1_2^20": bench_msm(torch, dev, imad_peak, 20, 1),
             "msm_g2_2^18": bench_msm(torch, dev, imad_peak, 18, 2, iters=5),
             "ntt_2^22": bench_ntt(torch, dev, imad_peak, hbm_gbs, 22),
             "ntt_2^22_coset_inverse": bench_ntt(torch, dev, imad_peak, hbm_gbs, 22, inverse=True, coset=True),
-            "ntt_2^20": bench_ntt(torch, dev, imad_peak, hbm_gbs, 20)}
+            "ntt_2^20": bench_ntt(torch, dev, imad_peak, hbm_gbs, 20),
+            "membership_batch_1024": bench_membership(torch, dev),
+            "proof_2^20_constraints": bench_large_proof(torch, dev)}
