@@ -88,8 +88,35 @@ struct MsmPlan {                 // one curve
     uint32_t n_items[3] = {0, 0, 0};
     uint32_t n_units = 0, n_rows = 0, n_msm = 0;
     std::vector<uint32_t> msm_unit_begin;   // host: first unit of each MSM (+ end)
+    std::vector<uint2> msm_items_host[3];   // host copy of msm_items per granularity
 };
 static const uint32_t kUnitsPerItem[3] = {32, 128, 512};
+
+// Host memory the device can DMA to without an intermediate copy (results of a chunk land here asynchronously).
+struct HBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t n) {
+        if (n <= bytes) return LZKP_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        bytes = 0;
+        cudaError_t err = cudaMallocHost(&p, n);
+        if (err != cudaSuccess) { p = nullptr; cudaGetLastError(); return fail(LZKP_E_NOMEM, "cudaMallocHost failed"); }
+        bytes = n;
+        return LZKP_OK;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+    ~HBuf() { if (p) cudaFreeHost(p); }
+};
+// Per-chunk device workspace.  A proving key owns two, so that two chunks of a batch are in flight on two
+// streams: the latency-bound stages of one chunk (witness generation, witness map, recoding, assembly)
+// run under the MSM kernels of the other.
+struct Workspace {
+    uint32_t chunk = 0;            // proofs the buffers are sized for
+    DBuf z, abc, h, dig, r, s, rs, part1, part2, res1, res2, proofs, status, a, b, commit, sets, setlen;
+    HBuf h_proofs, h_status, h_commit;
+};
 
 // pk->stream is a BLOCKING stream on purpose: setup-time uploads use synchronous cudaMemcpy from pageable
 // memory, whose DMA tail is only ordered against the legacy default stream and streams that synchronise
@@ -112,10 +139,7 @@ struct lzkp_pk {
     CsrDev csr[3];
     DBuf tw_fwd, tw_inv, coset_br, uncoset_br;
     NttTables ntt;
-    // workspace (sized for ws_chunk proofs)
-    uint32_t ws_chunk = 0;
-    DBuf ws_z, ws_abc, ws_h, ws_dig, ws_r, ws_s, ws_rs, ws_part1, ws_part2, ws_res1, ws_res2, ws_proofs, ws_status,
-        ws_a, ws_b, ws_commit, ws_sets, ws_setlen;
+    Workspace ws[2];
     // large mode (domain above 2^12): Pippenger MSMs over resident window-shifted bases, tiled NTTs
     bool large = false;
     MsmBases *L_a = nullptr, *L_b1 = nullptr, *L_b2 = nullptr, *L_l = nullptr, *L_h = nullptr;
@@ -124,7 +148,9 @@ struct lzkp_pk {
     // in the order a, b1, l, h, b2 (extras +-delta included); unsharded = the full ranges
     uint32_t shard_index = 0, shard_count = 1;
     uint32_t L_lo[5] = {0, 0, 0, 0, 0}, L_cnt[5] = {0, 0, 0, 0, 0};
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;      // chunk i of a batch runs on streams[i & 1]
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    cudaStream_t chunk_stream(int i) const { return (i & 1) ? stream2 : stream; }
     // optional per-region CUDA-event timing (lzkp_profile_*): pairs recorded on the launching stream
     struct Mark { int region; cudaEvent_t a, b; };
     std::vector<Mark> marks;
@@ -133,6 +159,9 @@ struct lzkp_pk {
     ~lzkp_pk() {
         for (auto &m : marks) { cudaEventDestroy(m.a); cudaEventDestroy(m.b); }
         for (MsmBases *b : {L_a, L_b1, L_b2, L_l, L_h}) if (b) msm_bases_free(b);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        for (auto ev : ev_join) if (ev) cudaEventDestroy(ev);
+        if (stream2) cudaStreamDestroy(stream2);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -164,6 +193,7 @@ static int finish_plan(MsmPlan &pl, const std::vector<std::vector<BaseRef>> &msm
             mi.push_back(make_uint2(first, (uint32_t)items.size()));
         }
         pl.n_items[v] = (uint32_t)items.size();
+        pl.msm_items_host[v] = mi;
         TRY(upload(pl.items[v], items));
         TRY(upload(pl.msm_items[v], mi));
     }
@@ -243,6 +273,9 @@ static int pk_load_impl(const uint8_t *bytes, size_t len, int validate, const lz
     if (pk->large) {
         // A = alpha + a_q[0] + sum_{j>=1} z_j a_q[j] + r delta: delta rides along as one more base (scalar r / s / rs)
         CUDA_TRY(cudaStreamCreate(&pk->stream));
+    CUDA_TRY(cudaStreamCreate(&pk->stream2));
+    CUDA_TRY(cudaEventCreateWithFlags(&pk->ev_fork, cudaEventDisableTiming));
+    for (auto &ev : pk->ev_join) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         const int wb = opt && opt->window_bits ? opt->window_bits : 0;
         pk->shard_count = opt && opt->shard_count > 1 ? opt->shard_count : 1;
         pk->shard_index = pk->shard_count > 1 ? opt->shard_index : 0;
@@ -352,6 +385,9 @@ static int pk_load_impl(const uint8_t *bytes, size_t len, int validate, const lz
     if (pk->max_chunk > 32768) pk->max_chunk = 32768;
 
     CUDA_TRY(cudaStreamCreate(&pk->stream));
+    CUDA_TRY(cudaStreamCreate(&pk->stream2));
+    CUDA_TRY(cudaEventCreateWithFlags(&pk->ev_fork, cudaEventDisableTiming));
+    for (auto &ev : pk->ev_join) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     cudaStream_t st = pk->stream;
 
     // --- upload points, to Montgomery, optional validation ---
@@ -470,11 +506,13 @@ static int circuit_install(lzkp_pk *pk, uint32_t m, uint32_t n_inst, uint32_t n_
 }
 
 // ------------------------------------------------------------------------ proving pipeline
-static inline int item_variant(uint32_t P) { return P >= 2048 ? 2 : (P >= 256 ? 1 : 0); }
+// Item granularity: many more CTAs than the 148 x 3 resident ones, so the last wave of a launch is a small
+// fraction of the kernel (measured: 512-unit items left the G1 kernel at 3.4 waves = 0.87 of peak).
+static inline int item_variant(uint32_t P) { return P >= 256 ? 1 : 0; }
 // G2 runs 64-thread CTAs at 255 registers: finer items keep every SM partition supplied with warps
 static inline int item_variant_g2(uint32_t P) { return P >= 2048 ? 1 : 0; }
-static int ensure_workspace(lzkp_pk *pk, uint32_t P) {
-    if (P <= pk->ws_chunk) return LZKP_OK;
+static int ensure_workspace(lzkp_pk *pk, Workspace &ws, uint32_t P) {
+    if (P <= ws.chunk) return LZKP_OK;
     size_t part1 = 0, part2 = 0;       // worst case over the batch sizes <= P
     for (uint32_t q : {1u, 256u, 2048u}) {
         if (q > P) break;
@@ -483,24 +521,24 @@ static int ensure_workspace(lzkp_pk *pk, uint32_t P) {
         part2 = std::max(part2, (size_t)pk->g2.n_items[item_variant_g2(pp)] * pp);
     }
     const size_t nv = pk->n_vars, n = pk->n;
-    TRY(pk->ws_z.ensure(P * nv * 32));
-    TRY(pk->ws_abc.ensure(3 * P * n * 32));
-    TRY(pk->ws_h.ensure(P * n * 32));
+    TRY(ws.z.ensure(P * nv * 32));
+    TRY(ws.abc.ensure(3 * P * n * 32));
+    TRY(ws.h.ensure(P * n * 32));
     if (pk->large) {
         TRY(pk->L_tmp.ensure(n * 32));
         TRY(pk->L_sa.ensure(nv * 32)); TRY(pk->L_sb.ensure(nv * 32)); TRY(pk->L_sl.ensure(((size_t)pk->n_wit + 1) * 32));
     } else {
-        TRY(pk->ws_dig.ensure((size_t)pk->n_dig_rows * pk->W * P * sizeof(int16_t)));
+        TRY(ws.dig.ensure((size_t)pk->n_dig_rows * pk->W * P * sizeof(int16_t)));
     }
-    TRY(pk->ws_r.ensure(P * 32)); TRY(pk->ws_s.ensure(P * 32)); TRY(pk->ws_rs.ensure(P * 32));
-    TRY(pk->ws_part1.ensure(part1 * sizeof(G1XYZZ)));
-    TRY(pk->ws_part2.ensure(part2 * sizeof(G2XYZZ)));
-    TRY(pk->ws_res1.ensure((size_t)4 * P * sizeof(G1XYZZ)));
-    TRY(pk->ws_res2.ensure((size_t)P * sizeof(G2XYZZ)));
-    TRY(pk->ws_proofs.ensure((size_t)P * 256));
-    TRY(pk->ws_status.ensure((size_t)P * sizeof(int32_t)));
-    TRY(pk->ws_a.ensure(P * 8)); TRY(pk->ws_b.ensure(P * 8)); TRY(pk->ws_commit.ensure(P * 32));
-    pk->ws_chunk = P;
+    TRY(ws.r.ensure(P * 32)); TRY(ws.s.ensure(P * 32)); TRY(ws.rs.ensure(P * 32));
+    TRY(ws.part1.ensure(part1 * sizeof(G1XYZZ)));
+    TRY(ws.part2.ensure(part2 * sizeof(G2XYZZ)));
+    TRY(ws.res1.ensure((size_t)4 * P * sizeof(G1XYZZ)));
+    TRY(ws.res2.ensure((size_t)P * sizeof(G2XYZZ)));
+    TRY(ws.proofs.ensure((size_t)P * 256));
+    TRY(ws.status.ensure((size_t)P * sizeof(int32_t)));
+    TRY(ws.a.ensure(P * 8)); TRY(ws.b.ensure(P * 8)); TRY(ws.commit.ensure(P * 32));
+    ws.chunk = P;
     return LZKP_OK;
 }
 
@@ -519,15 +557,15 @@ struct Region {           // RAII: brackets the kernels of one pipeline stage wi
 };
 
 // Witness map on P assignments already in ws_z (canonical): fills ws_h (canonical).
-static int run_witness_map(lzkp_pk *pk, uint32_t P, cudaStream_t st) {
+static int run_witness_map(lzkp_pk *pk, Workspace &ws, uint32_t P, cudaStream_t st) {
     const uint32_t n = pk->n, threads = std::max(32u, std::min(n / 2, 512u));
     const size_t smem = (size_t)32 * n;
     Region reg(pk, LZKP_REGION_WITNESS_MAP, st);
     if (pk->large) {
         // a3-a7 for one proof on a large domain: SpMV, then per vector iNTT -> coset NTT (tiled passes),
         // pointwise (ab - c) / Z(g), coset iNTT, and one conversion of h to canonical form
-        Fr *abc = pk->ws_abc.as<Fr>(), *tmp = pk->L_tmp.as<Fr>(), *h = pk->ws_h.as<Fr>();
-        LAUNCH(k_spmv_abc, dim3((n + 127) / 128, 1), 128, 0, st, pk->csr[0], pk->csr[1], pk->csr[2], pk->ws_z.as<Fr>(), abc, 1u,
+        Fr *abc = ws.abc.as<Fr>(), *tmp = pk->L_tmp.as<Fr>(), *h = ws.h.as<Fr>();
+        LAUNCH(k_spmv_abc, dim3((n + 127) / 128, 1), 128, 0, st, pk->csr[0], pk->csr[1], pk->csr[2], ws.z.as<Fr>(), abc, 1u,
                pk->n_vars, pk->m, pk->n_inst, n);
         for (int k = 0; k < 3; k++) {
             TRY(large_ntt_device(abc + (size_t)k * n, tmp, pk->log_n, 1, 0, st));
@@ -538,24 +576,24 @@ static int run_witness_map(lzkp_pk *pk, uint32_t P, cudaStream_t st) {
         LAUNCH(k_fr_to_canonical, (n + 127) / 128, 128, 0, st, h, n);
         return LZKP_OK;
     }
-    LAUNCH(k_spmv_abc, dim3((n + 127) / 128, P), 128, 0, st, pk->csr[0], pk->csr[1], pk->csr[2], pk->ws_z.as<Fr>(),
-           pk->ws_abc.as<Fr>(), P, pk->n_vars, pk->m, pk->n_inst, n);
-    LAUNCH(k_ntt_icoset, dim3(P, 3), threads, smem, st, pk->ws_abc.as<Fr>(), pk->ntt, P, pk->log_n);
-    LAUNCH(k_ntt_final, P, threads, smem, st, pk->ws_abc.as<Fr>(), pk->ws_h.as<Fr>(), pk->ntt, P, pk->log_n);
+    LAUNCH(k_spmv_abc, dim3((n + 127) / 128, P), 128, 0, st, pk->csr[0], pk->csr[1], pk->csr[2], ws.z.as<Fr>(),
+           ws.abc.as<Fr>(), P, pk->n_vars, pk->m, pk->n_inst, n);
+    LAUNCH(k_ntt_icoset, dim3(P, 3), threads, smem, st, ws.abc.as<Fr>(), pk->ntt, P, pk->log_n);
+    LAUNCH(k_ntt_final, P, threads, smem, st, ws.abc.as<Fr>(), ws.h.as<Fr>(), pk->ntt, P, pk->log_n);
     return LZKP_OK;
 }
 
 // From ws_z, r, s (device, canonical) to proofs (device).  status must be initialised by the caller.
-static int run_prove(lzkp_pk *pk, uint32_t P, const Fr *d_r, const Fr *d_s, uint8_t *d_proofs, int32_t *d_status,
-                     cudaStream_t st, bool have_h = false) {
-    if (!have_h) TRY(run_witness_map(pk, P, st));
+static int run_prove(lzkp_pk *pk, Workspace &ws, uint32_t P, const Fr *d_r, const Fr *d_s, uint8_t *d_proofs,
+                     int32_t *d_status, cudaStream_t st, bool have_h = false) {
     if (pk->large) {
+        if (!have_h) TRY(run_witness_map(pk, ws, P, st));
         if (P != 1) return fail(LZKP_E_STATE, "large-domain proving runs one proof per pass");
         const uint32_t nv = pk->n_vars, ni = pk->n_inst, nw = pk->n_wit;
-        const uint8_t *z = pk->ws_z.as<uint8_t>();
+        const uint8_t *z = ws.z.as<uint8_t>();
         uint8_t *sa = pk->L_sa.as<uint8_t>(), *sb = pk->L_sb.as<uint8_t>(), *sl = pk->L_sl.as<uint8_t>();
-        LAUNCH(k_fr_mul_canonical, 1, 128, 0, st, d_r, d_s, pk->ws_rs.as<Fr>(), 1u);
-        LAUNCH(k_check_canonical, (nv + 127) / 128, 128, 0, st, pk->ws_z.as<Fr>(), nv, d_status);
+        LAUNCH(k_fr_mul_canonical, 1, 128, 0, st, d_r, d_s, ws.rs.as<Fr>(), 1u);
+        LAUNCH(k_check_canonical, (nv + 127) / 128, 128, 0, st, ws.z.as<Fr>(), nv, d_status);
         LAUNCH(k_check_canonical, 1, 32, 0, st, d_r, 1u, d_status);
         LAUNCH(k_check_canonical, 1, 32, 0, st, d_s, 1u, d_status);
         // scalar vectors: z[1..] || r, z[1..] || s, z[n_inst..] || rs (the last entry multiplies +-delta)
@@ -565,47 +603,50 @@ static int run_prove(lzkp_pk *pk, uint32_t P, const Fr *d_r, const Fr *d_s, uint
         CUDA_TRY(cudaMemcpyAsync(sb, z + 32, (size_t)(nv - 1) * 32, dd, st));
         CUDA_TRY(cudaMemcpyAsync(sb + (size_t)(nv - 1) * 32, d_s, 32, dd, st));
         CUDA_TRY(cudaMemcpyAsync(sl, z + (size_t)ni * 32, (size_t)nw * 32, dd, st));
-        CUDA_TRY(cudaMemcpyAsync(sl + (size_t)nw * 32, pk->ws_rs.p, 32, dd, st));
-        G1XYZZ *res1 = pk->ws_res1.as<G1XYZZ>();
+        CUDA_TRY(cudaMemcpyAsync(sl + (size_t)nw * 32, ws.rs.p, 32, dd, st));
+        G1XYZZ *res1 = ws.res1.as<G1XYZZ>();
         const uint32_t *lo = pk->L_lo, *cnt = pk->L_cnt;
         {
             Region reg(pk, LZKP_REGION_MSM_G1, st);
             TRY(msm_device_raw(pk->L_a, sa + (size_t)lo[0] * 32, cnt[0], res1 + 0, st));
             TRY(msm_device_raw(pk->L_b1, sb + (size_t)lo[1] * 32, cnt[1], res1 + 1, st));
             TRY(msm_device_raw(pk->L_l, sl + (size_t)lo[2] * 32, cnt[2], res1 + 2, st));
-            TRY(msm_device_raw(pk->L_h, pk->ws_h.as<uint8_t>() + (size_t)lo[3] * 32, cnt[3], res1 + 3, st));
+            TRY(msm_device_raw(pk->L_h, ws.h.as<uint8_t>() + (size_t)lo[3] * 32, cnt[3], res1 + 3, st));
         }
         {
             Region reg(pk, LZKP_REGION_MSM_G2, st);
-            TRY(msm_device_raw(pk->L_b2, sb + (size_t)lo[4] * 32, cnt[4], pk->ws_res2.p, st));
+            TRY(msm_device_raw(pk->L_b2, sb + (size_t)lo[4] * 32, cnt[4], ws.res2.p, st));
         }
         if (!d_proofs) return LZKP_OK;           // partial sums only (sharded proving): the caller combines
         Region reg(pk, LZKP_REGION_ASSEMBLE, st);
-        LAUNCH(k_assemble, 1, 128, 0, st, res1, pk->ws_res2.as<G2XYZZ>(), pk->consts, d_r, d_s, 1u, d_proofs);
+        LAUNCH(k_assemble, 1, 128, 0, st, res1, ws.res2.as<G2XYZZ>(), pk->consts, d_r, d_s, 1u, d_proofs, 0u);
         return LZKP_OK;
     }
     const uint32_t c = pk->c, W = pk->W, gx = (P + 127) / 128;
-    int16_t *dig = pk->ws_dig.as<int16_t>();
+    int16_t *dig = ws.dig.as<int16_t>();
+    // One stream, stage after stage.  (Measured on B200: running the witness map and the G1 half of the assembly on
+    // a side stream underneath the MSM kernels gains < 2 % without stream priority - their CTAs only get SMs in the
+    // MSM kernel's last wave - and LOSES 2 % with priority, because a latency-bound CTA that holds 17k registers
+    // displaces a quarter of an SM's MSM warps while issuing almost nothing.  Overlap happens across chunks instead.)
+    if (!have_h) TRY(run_witness_map(pk, ws, P, st));
     {
     Region reg(pk, LZKP_REGION_DIGITS, st);
-    LAUNCH(k_fr_mul_canonical, gx, 128, 0, st, d_r, d_s, pk->ws_rs.as<Fr>(), P);
-    LAUNCH(k_digits, dim3(gx, pk->nz), 128, 0, st, pk->ws_z.as<Fr>(), pk->n_vars, 1u, dig, 0u, P, c, W, d_status);
+    LAUNCH(k_fr_mul_canonical, gx, 128, 0, st, d_r, d_s, ws.rs.as<Fr>(), P);
+    LAUNCH(k_digits, dim3(gx, pk->nz), 128, 0, st, ws.z.as<Fr>(), pk->n_vars, 1u, dig, 0u, P, c, W, d_status);
     LAUNCH(k_digits, dim3(gx, 1), 128, 0, st, d_r, 1u, 0u, dig, pk->nz, P, c, W, d_status);
     LAUNCH(k_digits, dim3(gx, 1), 128, 0, st, d_s, 1u, 0u, dig, pk->nz + 1, P, c, W, d_status);
-    LAUNCH(k_digits, dim3(gx, 1), 128, 0, st, pk->ws_rs.as<Fr>(), 1u, 0u, dig, pk->nz + 2, P, c, W, d_status);
-    LAUNCH(k_digits, dim3(gx, pk->n - 1), 128, 0, st, pk->ws_h.as<Fr>(), pk->n, 0u, dig, pk->nz + 3, P, c, W, d_status);
+    LAUNCH(k_digits, dim3(gx, 1), 128, 0, st, ws.rs.as<Fr>(), 1u, 0u, dig, pk->nz + 2, P, c, W, d_status);
+    LAUNCH(k_digits, dim3(gx, pk->n - 1), 128, 0, st, ws.h.as<Fr>(), pk->n, 0u, dig, pk->nz + 3, P, c, W, d_status);
     }
-    // item granularity: enough blocks to fill 148 SMs even for small batches
-    int v = item_variant(P);
     auto args = [&](MsmPlan &pl, int iv, void *partial, void *out) {
         return BatchMsmArgs{pl.table.p, pk->N, pl.unit_dig.as<uint32_t>(), pl.unit_tbl.as<uint32_t>(), pl.items[iv].p,
                             pl.n_items[iv], pl.msm_items[iv].p, pl.n_msm, dig, P, partial, out};
     };
-    { Region reg(pk, LZKP_REGION_MSM_G1, st); batch_msm_g1(args(pk->g1, v, pk->ws_part1.p, pk->ws_res1.p), st); }
-    { Region reg(pk, LZKP_REGION_MSM_G2, st); batch_msm_g2(args(pk->g2, item_variant_g2(P), pk->ws_part2.p, pk->ws_res2.p), st); }
+    { Region reg(pk, LZKP_REGION_MSM_G1, st); batch_msm_g1(args(pk->g1, item_variant(P), ws.part1.p, ws.res1.p), st); }
+    { Region reg(pk, LZKP_REGION_MSM_G2, st); batch_msm_g2(args(pk->g2, item_variant_g2(P), ws.part2.p, ws.res2.p), st); }
     Region reg(pk, LZKP_REGION_ASSEMBLE, st);
-    LAUNCH(k_assemble, (P + 31) / 32, 128, 0, st, pk->ws_res1.as<G1XYZZ>(), pk->ws_res2.as<G2XYZZ>(), pk->consts, d_r, d_s,
-           P, d_proofs);
+    LAUNCH(k_assemble, (P + 31) / 32, 128, 0, st, ws.res1.as<G1XYZZ>(), ws.res2.as<G2XYZZ>(), pk->consts, d_r, d_s, P, d_proofs,
+           0u);
     return LZKP_OK;
 }
 
@@ -644,6 +685,97 @@ static int small_ntt_host(uint8_t *data, uint32_t log_n, int inverse, int coset)
 }
 
 // ------------------------------------------------------------------------ C ABI
+// ---- chunked, double-buffered batches
+// A batch is cut into chunks; chunk i uses workspace i & 1 on stream i & 1, so two chunks are in flight.
+static uint32_t chunk_size(const lzkp_pk *pk, size_t n) {
+    if (pk->large) return 1;
+    uint32_t c = pk->max_chunk;
+    static const int split = getenv("LZKP_BATCH_SPLIT") ? atoi(getenv("LZKP_BATCH_SPLIT")) : 1;
+    if (split > 1 && n >= 1024) {         // cut one batch into `split` chunks so that two are in flight
+        uint32_t q = (uint32_t)((n + split - 1) / split);
+        q = (q + 127) / 128 * 128;
+        c = std::min(c, std::max(256u, q));
+    }
+    return c;
+}
+struct HostOut { uint8_t *proofs; int32_t *status; uint8_t *commit; };
+// Host-buffer batch: `prep(ws, off, P, st)` enqueues the chunk's input copies and witness generation.
+template <class Prep>
+static int run_batch_host(lzkp_pk *pk, size_t n, const uint8_t *r, const uint8_t *s, HostOut out, Prep prep) {
+    const uint32_t C = chunk_size(pk, n);
+    struct Pending { size_t off; uint32_t P; int w; };
+    std::vector<Pending> pend;
+    auto drain = [&](int w) -> int {       // copy finished chunks of workspace w from pinned staging to the caller
+        CUDA_TRY(cudaStreamSynchronize(pk->chunk_stream(w)));
+        for (auto it = pend.begin(); it != pend.end();) {
+            if (it->w != w) { ++it; continue; }
+            Workspace &ws = pk->ws[w];
+            memcpy(out.proofs + it->off * 256, ws.h_proofs.p, (size_t)it->P * 256);
+            memcpy(out.status + it->off, ws.h_status.p, (size_t)it->P * 4);
+            if (out.commit) memcpy(out.commit + it->off * 32, ws.h_commit.p, (size_t)it->P * 32);
+            it = pend.erase(it);
+        }
+        return LZKP_OK;
+    };
+    int i = 0;
+    for (size_t off = 0; off < n; off += C, i++) {
+        const int w = pk->large ? 0 : (i & 1);
+        const uint32_t P = (uint32_t)std::min<size_t>(C, n - off);
+        Workspace &ws = pk->ws[w];
+        cudaStream_t st = pk->chunk_stream(w);
+        TRY(drain(w));                                    // the staging buffers of this workspace are free again
+        TRY(ensure_workspace(pk, ws, P));
+        TRY(ws.h_proofs.ensure((size_t)ws.chunk * 256)); TRY(ws.h_status.ensure((size_t)ws.chunk * 4));
+        TRY(ws.h_commit.ensure((size_t)ws.chunk * 32));
+        CUDA_TRY(cudaMemcpyAsync(ws.r.p, r + off * 32, (size_t)P * 32, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(ws.s.p, s + off * 32, (size_t)P * 32, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemsetAsync(ws.status.p, 0, (size_t)P * 4, st));
+        TRY(prep(ws, off, P, st));
+        TRY(run_prove(pk, ws, P, ws.r.as<Fr>(), ws.s.as<Fr>(), ws.proofs.as<uint8_t>(), ws.status.as<int32_t>(), st));
+        CUDA_TRY(cudaMemcpyAsync(ws.h_proofs.p, ws.proofs.p, (size_t)P * 256, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(ws.h_status.p, ws.status.p, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
+        if (out.commit) CUDA_TRY(cudaMemcpyAsync(ws.h_commit.p, ws.commit.p, (size_t)P * 32, cudaMemcpyDeviceToHost, st));
+        pend.push_back({off, P, w});
+    }
+    TRY(drain(0));
+    TRY(drain(1));
+    CUDA_TRY(cudaGetLastError());
+    blank_failed(n, out.status, out.proofs);
+    return LZKP_OK;
+}
+// Device-buffer batch on the caller's stream: fork to the two engine streams, join back.
+template <class Prep>
+static int run_batch_device(lzkp_pk *pk, size_t n, const void *d_r, const void *d_s, void *d_proofs, void *d_status,
+                            cudaStream_t caller, Prep prep) {
+    const uint32_t C = chunk_size(pk, n);
+    const bool fork = !pk->large && n > C;               // a single chunk runs directly on the caller's stream
+    if (fork) {
+        CUDA_TRY(cudaEventRecord(pk->ev_fork, caller));
+        CUDA_TRY(cudaStreamWaitEvent(pk->stream, pk->ev_fork, 0));
+        CUDA_TRY(cudaStreamWaitEvent(pk->stream2, pk->ev_fork, 0));
+    }
+    int i = 0;
+    for (size_t off = 0; off < n; off += C, i++) {
+        const int w = fork ? (i & 1) : 0;
+        const uint32_t P = (uint32_t)std::min<size_t>(C, n - off);
+        Workspace &ws = pk->ws[w];
+        cudaStream_t st = fork ? pk->chunk_stream(w) : caller;
+        TRY(ensure_workspace(pk, ws, P));
+        int32_t *stat = (int32_t *)d_status + off;
+        CUDA_TRY(cudaMemsetAsync(stat, 0, (size_t)P * 4, st));
+        TRY(prep(ws, off, P, stat, st));
+        TRY(run_prove(pk, ws, P, (const Fr *)d_r + off, (const Fr *)d_s + off, (uint8_t *)d_proofs + off * 256, stat, st));
+    }
+    if (fork) {
+        for (int w = 0; w < 2; w++) {
+            CUDA_TRY(cudaEventRecord(pk->ev_join[w], pk->chunk_stream(w)));
+            CUDA_TRY(cudaStreamWaitEvent(caller, pk->ev_join[w], 0));
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
+    return LZKP_OK;
+}
+
 #pragma GCC visibility push(default)
 extern "C" {
 
@@ -823,23 +955,12 @@ int lzkp_prove_batch(lzkp_pk *pk, size_t n_proofs, const uint8_t *z, const uint8
     TRY(ensure_device());
     std::lock_guard<std::mutex> lk(pk->mu);
     if (!pk->has_circuit) return fail(LZKP_E_STATE, "lzkp_circuit_load has not been called");
-    cudaStream_t st = pk->stream;
     const size_t nv = pk->n_vars;
-    for (size_t off = 0; off < n_proofs; off += pk->max_chunk) {
-        uint32_t P = (uint32_t)std::min<size_t>(pk->max_chunk, n_proofs - off);
-        TRY(ensure_workspace(pk, P));
-        CUDA_TRY(cudaMemcpyAsync(pk->ws_z.p, z + off * nv * 32, (size_t)P * nv * 32, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(pk->ws_r.p, r + off * 32, (size_t)P * 32, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(pk->ws_s.p, s + off * 32, (size_t)P * 32, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemsetAsync(pk->ws_status.p, 0, (size_t)P * 4, st));
-        TRY(run_prove(pk, P, pk->ws_r.as<Fr>(), pk->ws_s.as<Fr>(), pk->ws_proofs.as<uint8_t>(), pk->ws_status.as<int32_t>(), st));
-        CUDA_TRY(cudaMemcpyAsync(proofs_out + off * 256, pk->ws_proofs.p, (size_t)P * 256, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(status + off, pk->ws_status.p, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
-        CUDA_TRY(cudaGetLastError());
-    }
-    blank_failed(n_proofs, status, proofs_out);
-    return LZKP_OK;
+    return run_batch_host(pk, n_proofs, r, s, HostOut{proofs_out, status, nullptr},
+                          [&](Workspace &ws, size_t off, uint32_t P, cudaStream_t st) -> int {
+        CUDA_TRY(cudaMemcpyAsync(ws.z.p, z + off * nv * 32, (size_t)P * nv * 32, cudaMemcpyHostToDevice, st));
+        return LZKP_OK;
+    });
 }
 
 int lzkp_prove_batch_device(lzkp_pk *pk, size_t n_proofs, const void *d_z, const void *d_r, const void *d_s,
@@ -848,18 +969,12 @@ int lzkp_prove_batch_device(lzkp_pk *pk, size_t n_proofs, const void *d_z, const
     TRY(ensure_device());
     std::lock_guard<std::mutex> lk(pk->mu);
     if (!pk->has_circuit) return fail(LZKP_E_STATE, "lzkp_circuit_load has not been called");
-    cudaStream_t st = (cudaStream_t)stream;
     const size_t nv = pk->n_vars;
-    for (size_t off = 0; off < n_proofs; off += pk->max_chunk) {
-        uint32_t P = (uint32_t)std::min<size_t>(pk->max_chunk, n_proofs - off);
-        TRY(ensure_workspace(pk, P));
-        int32_t *stat = (int32_t *)d_status + off;
-        CUDA_TRY(cudaMemsetAsync(stat, 0, (size_t)P * 4, st));
-        CUDA_TRY(cudaMemcpyAsync(pk->ws_z.p, (const uint8_t *)d_z + off * nv * 32, (size_t)P * nv * 32, cudaMemcpyDeviceToDevice, st));
-        TRY(run_prove(pk, P, (const Fr *)d_r + off, (const Fr *)d_s + off, (uint8_t *)d_proofs + off * 256, stat, st));
-    }
-    CUDA_TRY(cudaGetLastError());
-    return LZKP_OK;
+    return run_batch_device(pk, n_proofs, d_r, d_s, d_proofs, d_status, (cudaStream_t)stream,
+                            [&](Workspace &ws, size_t off, uint32_t P, int32_t *, cudaStream_t st) -> int {
+        CUDA_TRY(cudaMemcpyAsync(ws.z.p, (const uint8_t *)d_z + off * nv * 32, (size_t)P * nv * 32, cudaMemcpyDeviceToDevice, st));
+        return LZKP_OK;
+    });
 }
 
 int lzkp_builtin_witness(int kind, uint32_t param, uint64_t value, uint64_t other, const uint64_t *set,
@@ -884,29 +999,17 @@ int lzkp_prove_equality_batch(lzkp_pk *pk, size_t n_proofs, const uint64_t *a, c
     TRY(ensure_device());
     std::lock_guard<std::mutex> lk(pk->mu);
     if (!pk->has_circuit || pk->kind != LZKP_CIRCUIT_EQUALITY) return fail(LZKP_E_STATE, "pk is not bound to the builtin equality circuit");
-    cudaStream_t st = pk->stream;
-    for (size_t off = 0; off < n_proofs; off += pk->max_chunk) {
-        uint32_t P = (uint32_t)std::min<size_t>(pk->max_chunk, n_proofs - off);
-        TRY(ensure_workspace(pk, P));
-        CUDA_TRY(cudaMemcpyAsync(pk->ws_a.p, a + off, (size_t)P * 8, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(pk->ws_b.p, b + off, (size_t)P * 8, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(pk->ws_r.p, r + off * 32, (size_t)P * 32, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(pk->ws_s.p, s + off * 32, (size_t)P * 32, cudaMemcpyHostToDevice, st));
-        if (commitments) CUDA_TRY(cudaMemcpyAsync(pk->ws_commit.p, commitments + off * 32, (size_t)P * 32, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemsetAsync(pk->ws_status.p, 0, (size_t)P * 4, st));
-        { Region reg(pk, LZKP_REGION_WITGEN, st);
-        LAUNCH(k_witgen_equality, (P + 127) / 128, 128, 0, st, pk->ws_a.as<uint64_t>(), pk->ws_b.as<uint64_t>(),
-               commitments ? pk->ws_commit.as<Fr>() : nullptr, pk->ws_z.as<Fr>(), pk->ws_commit.as<Fr>(),
-               pk->ws_status.as<int32_t>(), P, pk->kind_param, pk->n_vars); }
-        TRY(run_prove(pk, P, pk->ws_r.as<Fr>(), pk->ws_s.as<Fr>(), pk->ws_proofs.as<uint8_t>(), pk->ws_status.as<int32_t>(), st));
-        CUDA_TRY(cudaMemcpyAsync(proofs_out + off * 256, pk->ws_proofs.p, (size_t)P * 256, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(status + off, pk->ws_status.p, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
-        if (commitments_out) CUDA_TRY(cudaMemcpyAsync(commitments_out + off * 32, pk->ws_commit.p, (size_t)P * 32, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
-        CUDA_TRY(cudaGetLastError());
-    }
-    blank_failed(n_proofs, status, proofs_out);
-    return LZKP_OK;
+    return run_batch_host(pk, n_proofs, r, s, HostOut{proofs_out, status, commitments_out},
+                          [&](Workspace &ws, size_t off, uint32_t P, cudaStream_t st) -> int {
+        CUDA_TRY(cudaMemcpyAsync(ws.a.p, a + off, (size_t)P * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(ws.b.p, b + off, (size_t)P * 8, cudaMemcpyHostToDevice, st));
+        if (commitments) CUDA_TRY(cudaMemcpyAsync(ws.commit.p, commitments + off * 32, (size_t)P * 32, cudaMemcpyHostToDevice, st));
+        Region reg(pk, LZKP_REGION_WITGEN, st);
+        LAUNCH(k_witgen_equality, (P + 127) / 128, 128, 0, st, ws.a.as<uint64_t>(), ws.b.as<uint64_t>(),
+               commitments ? ws.commit.as<Fr>() : nullptr, ws.z.as<Fr>(), ws.commit.as<Fr>(), ws.status.as<int32_t>(), P,
+               pk->kind_param, pk->n_vars);
+        return LZKP_OK;
+    });
 }
 
 int lzkp_prove_membership_batch(lzkp_pk *pk, size_t n_proofs, const uint64_t *value, const uint64_t *sets,
@@ -918,31 +1021,20 @@ int lzkp_prove_membership_batch(lzkp_pk *pk, size_t n_proofs, const uint64_t *va
     TRY(ensure_device());
     std::lock_guard<std::mutex> lk(pk->mu);
     if (!pk->has_circuit || pk->kind != LZKP_CIRCUIT_MEMBERSHIP) return fail(LZKP_E_STATE, "pk is not bound to the builtin membership circuit");
-    cudaStream_t st = pk->stream;
-    for (size_t off = 0; off < n_proofs; off += pk->max_chunk) {
-        uint32_t P = (uint32_t)std::min<size_t>(pk->max_chunk, n_proofs - off);
-        TRY(ensure_workspace(pk, P));
-        TRY(pk->ws_sets.ensure((size_t)P * set_stride * 8));
-        TRY(pk->ws_setlen.ensure((size_t)P * 4));
-        CUDA_TRY(cudaMemcpyAsync(pk->ws_a.p, value + off, (size_t)P * 8, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(pk->ws_sets.p, sets + off * set_stride, (size_t)P * set_stride * 8, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(pk->ws_setlen.p, set_len + off, (size_t)P * 4, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(pk->ws_r.p, r + off * 32, (size_t)P * 32, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(pk->ws_s.p, s + off * 32, (size_t)P * 32, cudaMemcpyHostToDevice, st));
-        if (commitments) CUDA_TRY(cudaMemcpyAsync(pk->ws_commit.p, commitments + off * 32, (size_t)P * 32, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemsetAsync(pk->ws_status.p, 0, (size_t)P * 4, st));
-        LAUNCH(k_witgen_membership, (P + 127) / 128, 128, 0, st, pk->ws_a.as<uint64_t>(), pk->ws_sets.as<uint64_t>(),
-               pk->ws_setlen.as<uint32_t>(), set_stride, commitments ? pk->ws_commit.as<Fr>() : nullptr, pk->ws_z.as<Fr>(),
-               pk->ws_commit.as<Fr>(), pk->ws_status.as<int32_t>(), P, pk->kind_param, pk->n_vars);
-        TRY(run_prove(pk, P, pk->ws_r.as<Fr>(), pk->ws_s.as<Fr>(), pk->ws_proofs.as<uint8_t>(), pk->ws_status.as<int32_t>(), st));
-        CUDA_TRY(cudaMemcpyAsync(proofs_out + off * 256, pk->ws_proofs.p, (size_t)P * 256, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(status + off, pk->ws_status.p, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
-        if (commitments_out) CUDA_TRY(cudaMemcpyAsync(commitments_out + off * 32, pk->ws_commit.p, (size_t)P * 32, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
-        CUDA_TRY(cudaGetLastError());
-    }
-    blank_failed(n_proofs, status, proofs_out);
-    return LZKP_OK;
+    return run_batch_host(pk, n_proofs, r, s, HostOut{proofs_out, status, commitments_out},
+                          [&](Workspace &ws, size_t off, uint32_t P, cudaStream_t st) -> int {
+        TRY(ws.sets.ensure((size_t)ws.chunk * set_stride * 8));
+        TRY(ws.setlen.ensure((size_t)ws.chunk * 4));
+        CUDA_TRY(cudaMemcpyAsync(ws.a.p, value + off, (size_t)P * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(ws.sets.p, sets + off * set_stride, (size_t)P * set_stride * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(ws.setlen.p, set_len + off, (size_t)P * 4, cudaMemcpyHostToDevice, st));
+        if (commitments) CUDA_TRY(cudaMemcpyAsync(ws.commit.p, commitments + off * 32, (size_t)P * 32, cudaMemcpyHostToDevice, st));
+        Region reg(pk, LZKP_REGION_WITGEN, st);
+        LAUNCH(k_witgen_membership, (P + 127) / 128, 128, 0, st, ws.a.as<uint64_t>(), ws.sets.as<uint64_t>(),
+               ws.setlen.as<uint32_t>(), set_stride, commitments ? ws.commit.as<Fr>() : nullptr, ws.z.as<Fr>(),
+               ws.commit.as<Fr>(), ws.status.as<int32_t>(), P, pk->kind_param, pk->n_vars);
+        return LZKP_OK;
+    });
 }
 
 int lzkp_prove_equality_batch_device(lzkp_pk *pk, size_t n_proofs, const void *d_a, const void *d_b, const void *d_r,
@@ -951,19 +1043,13 @@ int lzkp_prove_equality_batch_device(lzkp_pk *pk, size_t n_proofs, const void *d
     TRY(ensure_device());
     std::lock_guard<std::mutex> lk(pk->mu);
     if (!pk->has_circuit || pk->kind != LZKP_CIRCUIT_EQUALITY) return fail(LZKP_E_STATE, "pk is not bound to the builtin equality circuit");
-    cudaStream_t st = (cudaStream_t)stream;
-    for (size_t off = 0; off < n_proofs; off += pk->max_chunk) {
-        uint32_t P = (uint32_t)std::min<size_t>(pk->max_chunk, n_proofs - off);
-        TRY(ensure_workspace(pk, P));
-        int32_t *stat = (int32_t *)d_status + off;
-        CUDA_TRY(cudaMemsetAsync(stat, 0, (size_t)P * 4, st));
-        { Region reg(pk, LZKP_REGION_WITGEN, st);
+    return run_batch_device(pk, n_proofs, d_r, d_s, d_proofs, d_status, (cudaStream_t)stream,
+                            [&](Workspace &ws, size_t off, uint32_t P, int32_t *stat, cudaStream_t st) -> int {
+        Region reg(pk, LZKP_REGION_WITGEN, st);
         LAUNCH(k_witgen_equality, (P + 127) / 128, 128, 0, st, (const uint64_t *)d_a + off, (const uint64_t *)d_b + off,
-               (const Fr *)nullptr, pk->ws_z.as<Fr>(), pk->ws_commit.as<Fr>(), stat, P, pk->kind_param, pk->n_vars); }
-        TRY(run_prove(pk, P, (const Fr *)d_r + off, (const Fr *)d_s + off, (uint8_t *)d_proofs + off * 256, stat, st));
-    }
-    CUDA_TRY(cudaGetLastError());
-    return LZKP_OK;
+               (const Fr *)nullptr, ws.z.as<Fr>(), ws.commit.as<Fr>(), stat, P, pk->kind_param, pk->n_vars);
+        return LZKP_OK;
+    });
 }
 
 int lzkp_witness_map(lzkp_pk *pk, size_t n_proofs, const uint8_t *z, uint8_t *h_out) {
@@ -972,13 +1058,14 @@ int lzkp_witness_map(lzkp_pk *pk, size_t n_proofs, const uint8_t *z, uint8_t *h_
     std::lock_guard<std::mutex> lk(pk->mu);
     if (!pk->has_circuit) return fail(LZKP_E_STATE, "lzkp_circuit_load has not been called");
     cudaStream_t st = pk->stream;
+    Workspace &ws = pk->ws[0];
     const size_t nv = pk->n_vars, n = pk->n;
     for (size_t off = 0; off < n_proofs; off += pk->max_chunk) {
         uint32_t P = (uint32_t)std::min<size_t>(pk->max_chunk, n_proofs - off);
-        TRY(ensure_workspace(pk, P));
-        CUDA_TRY(cudaMemcpyAsync(pk->ws_z.p, z + off * nv * 32, (size_t)P * nv * 32, cudaMemcpyHostToDevice, st));
-        TRY(run_witness_map(pk, P, st));
-        CUDA_TRY(cudaMemcpyAsync(h_out + off * n * 32, pk->ws_h.p, (size_t)P * n * 32, cudaMemcpyDeviceToHost, st));
+        TRY(ensure_workspace(pk, ws, P));
+        CUDA_TRY(cudaMemcpyAsync(ws.z.p, z + off * nv * 32, (size_t)P * nv * 32, cudaMemcpyHostToDevice, st));
+        TRY(run_witness_map(pk, ws, P, st));
+        CUDA_TRY(cudaMemcpyAsync(h_out + off * n * 32, ws.h.p, (size_t)P * n * 32, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
         CUDA_TRY(cudaGetLastError());
     }
@@ -991,10 +1078,11 @@ int lzkp_witness_map_device(lzkp_pk *pk, const void *d_z, void *d_h, void *strea
     std::lock_guard<std::mutex> lk(pk->mu);
     if (!pk->has_circuit) return fail(LZKP_E_STATE, "lzkp_circuit_load has not been called");
     cudaStream_t st = (cudaStream_t)stream;
-    TRY(ensure_workspace(pk, 1));
-    CUDA_TRY(cudaMemcpyAsync(pk->ws_z.p, d_z, (size_t)pk->n_vars * 32, cudaMemcpyDeviceToDevice, st));
-    TRY(run_witness_map(pk, 1, st));
-    CUDA_TRY(cudaMemcpyAsync(d_h, pk->ws_h.p, (size_t)pk->n * 32, cudaMemcpyDeviceToDevice, st));
+    Workspace &ws = pk->ws[0];
+    TRY(ensure_workspace(pk, ws, 1));
+    CUDA_TRY(cudaMemcpyAsync(ws.z.p, d_z, (size_t)pk->n_vars * 32, cudaMemcpyDeviceToDevice, st));
+    TRY(run_witness_map(pk, ws, 1, st));
+    CUDA_TRY(cudaMemcpyAsync(d_h, ws.h.p, (size_t)pk->n * 32, cudaMemcpyDeviceToDevice, st));
     return LZKP_OK;
 }
 
@@ -1005,14 +1093,15 @@ int lzkp_prove_partial_device(lzkp_pk *pk, const void *d_z, const void *d_r, con
     std::lock_guard<std::mutex> lk(pk->mu);
     if (!pk->large) return fail(LZKP_E_STATE, "sharded proving needs a large-domain proving key");
     cudaStream_t st = (cudaStream_t)stream;
-    TRY(ensure_workspace(pk, 1));
+    Workspace &ws = pk->ws[0];
+    TRY(ensure_workspace(pk, ws, 1));
     CUDA_TRY(cudaMemsetAsync(d_status, 0, 4, st));
-    CUDA_TRY(cudaMemcpyAsync(pk->ws_z.p, d_z, (size_t)pk->n_vars * 32, cudaMemcpyDeviceToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(pk->ws_h.p, d_h, (size_t)pk->n * 32, cudaMemcpyDeviceToDevice, st));
-    TRY(run_prove(pk, 1, (const Fr *)d_r, (const Fr *)d_s, nullptr, (int32_t *)d_status, st, true));
+    CUDA_TRY(cudaMemcpyAsync(ws.z.p, d_z, (size_t)pk->n_vars * 32, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ws.h.p, d_h, (size_t)pk->n * 32, cudaMemcpyDeviceToDevice, st));
+    TRY(run_prove(pk, ws, 1, (const Fr *)d_r, (const Fr *)d_s, nullptr, (int32_t *)d_status, st, true));
     uint8_t *out = (uint8_t *)d_partial;
-    CUDA_TRY(cudaMemcpyAsync(out, pk->ws_res1.p, 4 * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(out + 4 * sizeof(G1XYZZ), pk->ws_res2.p, sizeof(G2XYZZ), cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(out, ws.res1.p, 4 * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(out + 4 * sizeof(G1XYZZ), ws.res2.p, sizeof(G2XYZZ), cudaMemcpyDeviceToDevice, st));
     return LZKP_OK;
 }
 
@@ -1023,11 +1112,12 @@ int lzkp_prove_combine_device(lzkp_pk *pk, const void *d_partials, int n_partial
     std::lock_guard<std::mutex> lk(pk->mu);
     if (!pk->large) return fail(LZKP_E_STATE, "sharded proving needs a large-domain proving key");
     cudaStream_t st = (cudaStream_t)stream;
-    TRY(ensure_workspace(pk, 1));
-    LAUNCH(k_sum_partials, 1, 32, 0, st, (const uint8_t *)d_partials, (uint32_t)n_partials, pk->ws_res1.as<G1XYZZ>(),
-           pk->ws_res2.as<G2XYZZ>());
-    LAUNCH(k_assemble, 1, 128, 0, st, pk->ws_res1.as<G1XYZZ>(), pk->ws_res2.as<G2XYZZ>(), pk->consts, (const Fr *)d_r,
-           (const Fr *)d_s, 1u, (uint8_t *)d_proof);
+    Workspace &ws = pk->ws[0];
+    TRY(ensure_workspace(pk, ws, 1));
+    LAUNCH(k_sum_partials, 1, 32, 0, st, (const uint8_t *)d_partials, (uint32_t)n_partials, ws.res1.as<G1XYZZ>(),
+           ws.res2.as<G2XYZZ>());
+    LAUNCH(k_assemble, 1, 128, 0, st, ws.res1.as<G1XYZZ>(), ws.res2.as<G2XYZZ>(), pk->consts, (const Fr *)d_r,
+           (const Fr *)d_s, 1u, (uint8_t *)d_proof, 0u);
     CUDA_TRY(cudaGetLastError());
     return LZKP_OK;
 }

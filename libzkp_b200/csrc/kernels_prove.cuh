@@ -337,11 +337,14 @@ struct ProofConsts {
 // the CTA (warp-uniform roles, lane = proof) and meet once in shared memory.
 //   warp 0: s * A, then C = s*A + r*B1 + L + H -> affine -> bytes      warp 2: A -> affine -> bytes
 //   warp 1: r * B1                                                     warp 3: B (G2) -> affine -> bytes
+// Launch with 128 threads and role0 = 0 for all four strands, or as two launches - 96 threads / role0 = 0 (the G1
+// strands, which only need the G1 sums) and 32 threads / role0 = 3 (the G2 strand) - so that the G1 part can run
+// on a side stream underneath the G2 MSM.
 __global__ void __launch_bounds__(128) k_assemble(const G1XYZZ *g1, const G2XYZZ *g2, ProofConsts K, const Fr *r,
-                                                  const Fr *s, uint32_t P, uint8_t *proofs) {
+                                                  const Fr *s, uint32_t P, uint8_t *proofs, uint32_t role0) {
     __shared__ uint4 sm_raw[32 * sizeof(G1XYZZ) / 16];
     G1XYZZ *sm = reinterpret_cast<G1XYZZ *>(sm_raw);
-    const uint32_t role = threadIdx.x >> 5, lane = threadIdx.x & 31, p = blockIdx.x * 32 + lane;
+    const uint32_t role = role0 + (threadIdx.x >> 5), lane = threadIdx.x & 31, p = blockIdx.x * 32 + lane;
     const bool live = p < P;
     uint8_t *out = proofs + (size_t)p * 256;
     G1XYZZ acc = G1XYZZ::inf();

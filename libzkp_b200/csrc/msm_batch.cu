@@ -52,12 +52,19 @@ __global__ void __launch_bounds__(128) k_msm_reduce(const XYZZ<F> *partial, cons
 
 namespace eng {
 
+// gather + accumulate the items [item0, item0 + count) (partial sums land at their global item index)
+void batch_msm_g1_items(const BatchMsmArgs &a, uint32_t item0, uint32_t count, cudaStream_t st) {
+    if (!count) return;
+    LAUNCH((k_msm_batch<Fq, 128>), dim3((a.P + 127) / 128, count), 128, 0, st, (const G1Affine *)a.table, a.N, a.unit_dig,
+           a.unit_tbl, (const uint2 *)a.items + item0, a.dig, a.P, (G1XYZZ *)a.partial + (size_t)item0 * a.P);
+}
+void batch_msm_g1_reduce(const BatchMsmArgs &a, cudaStream_t st) {
+    LAUNCH((k_msm_reduce<Fq>), dim3((a.P + 127) / 128, a.n_msm), 128, 0, st, (const G1XYZZ *)a.partial,
+           (const uint2 *)a.msm_items, a.P, (G1XYZZ *)a.out);
+}
 void batch_msm_g1(const BatchMsmArgs &a, cudaStream_t st) {
-    const uint32_t gx = (a.P + 127) / 128;
-    LAUNCH((k_msm_batch<Fq, 128>), dim3(gx, a.n_items), 128, 0, st, (const G1Affine *)a.table, a.N, a.unit_dig,
-           a.unit_tbl, (const uint2 *)a.items, a.dig, a.P, (G1XYZZ *)a.partial);
-    LAUNCH((k_msm_reduce<Fq>), dim3(gx, a.n_msm), 128, 0, st, (const G1XYZZ *)a.partial, (const uint2 *)a.msm_items,
-           a.P, (G1XYZZ *)a.out);
+    batch_msm_g1_items(a, 0, a.n_items, st);
+    batch_msm_g1_reduce(a, st);
 }
 void batch_msm_g2(const BatchMsmArgs &a, cudaStream_t st) {
     LAUNCH((k_msm_batch<Fq2, 64>), dim3((a.P + 63) / 64, a.n_items), 64, 0, st, (const G2Affine *)a.table, a.N,

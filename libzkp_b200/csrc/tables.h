@@ -25,6 +25,8 @@ struct BatchMsmArgs {
     void *out;                    // XYZZ<F>[n_msm * P]
 };
 void batch_msm_g1(const BatchMsmArgs &a, cudaStream_t st);
+void batch_msm_g1_items(const BatchMsmArgs &a, uint32_t item0, uint32_t count, cudaStream_t st);
+void batch_msm_g1_reduce(const BatchMsmArgs &a, cudaStream_t st);
 void batch_msm_g2(const BatchMsmArgs &a, cudaStream_t st);
 
 }  // namespace eng
