@@ -18,6 +18,7 @@
 //
 // Roofline: (n/2) log2 n butterflies x 1 Montgomery product (272 IMAD) + ~2n twiddle products per
 // pass boundary; 64 B/element/pass of HBM traffic.  IMAD-bound by ~8x.
+#include <cstdlib>
 #include <map>
 #include <mutex>
 
@@ -61,6 +62,7 @@ struct PassArgs {
     uint32_t log_cols;      // columns per tile (1 << log_cols <= M_q)
     uint32_t tw_shift;      // tile twiddle table is for 2^tile_max points: index shift for smaller tiles
     const Fr *tile_tw;      // rho^k, k < 2^(tile_max-1)
+    const Fr *cross;        // cross twiddle of this pass by output position (n entries), or null: two-level powers
     PowTable w;             // powers of the n-th root (forward or inverse)
     PowTable g;             // powers of the coset generator (forward) or its inverse times n^-1 (inverse)
     Fr ninv;                // n^-1 (Montgomery), plain inverse only
@@ -79,6 +81,15 @@ __global__ void k_ntt_pow_table(Fr *out, Fr base, Fr scale, uint32_t count, uint
         e >>= 1;
     }
     st_vec(out + k, acc * scale);
+}
+
+// cross[pos] = w^(P_q * r * k) for the element that pass q stores at `pos` (digit q holds k, r = pos mod M_q)
+__global__ void k_ntt_cross_table(Fr *cross, PowTable w, uint32_t log_n, uint32_t b, uint32_t log_stride) {
+    const size_t pos = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >> log_n) return;
+    const uint32_t r = (uint32_t)pos & ((1u << log_stride) - 1u), k = ((uint32_t)pos >> log_stride) & ((1u << b) - 1u);
+    const uint32_t e = (r * k) << (log_n - b - log_stride);
+    st_vec(cross + pos, e ? w.pow(e) : Fr::one());
 }
 
 __global__ void __launch_bounds__(1024) k_ntt_pass(const Fr *__restrict__ in, Fr *__restrict__ out, PassArgs A) {
@@ -143,9 +154,10 @@ __global__ void __launch_bounds__(1024) k_ntt_pass(const Fr *__restrict__ in, Fr
         for (uint32_t idx = threadIdx.x; idx < E; idx += blockDim.x) {
             uint32_t k = idx >> A.log_cols, c = idx & (cols - 1);
             Fr v = s.get((c << b) + bitrev(k, b));
+            const size_t pos = base + ((size_t)k << A.log_stride) + c;
             uint32_t e = ((lo0 + c) * k) << p_log;
-            if (e) v = v * A.w.pow(e);
-            st_vec(out + base + ((size_t)k << A.log_stride) + c, v);
+            if (e) v = v * (A.cross ? ldg_vec(A.cross + pos) : A.w.pow(e));
+            st_vec(out + pos, v);
         }
     } else {
         // final index: digits of `hi` (k_0 most significant) reversed, k_{p-1} on top
@@ -169,7 +181,7 @@ __global__ void __launch_bounds__(1024) k_ntt_pass(const Fr *__restrict__ in, Fr
 // ---------------------------------------------------------------- plans (device tables per size/direction)
 struct NttPlan {
     uint32_t log_n = 0, n_pass = 0, bits[3] = {0, 0, 0}, tile_max = 0, lb = 0;
-    eng::DBuf tile_tw, w_lo, w_hi, g_lo, g_hi;
+    eng::DBuf tile_tw, w_lo, w_hi, g_lo, g_hi, cross[2];   // cross[q]: per-position twiddles after pass q (optional)
     Fr ninv;
 };
 std::mutex g_plan_mu;
@@ -191,7 +203,12 @@ static int get_plan(uint32_t log_n, int inverse, cudaStream_t st, NttPlan **out)
     if (it != g_plans.end()) { *out = it->second; return LZKP_OK; }
     NttPlan *P = new NttPlan();
     P->log_n = log_n;
-    P->n_pass = std::max(1u, (log_n + kMaxTileBits - 1) / kMaxTileBits);
+    // Measured on B200: tiles of <= 2^10 points run at the full 64 G products/s (several CTAs per SM hide the
+    // barriers), 2^11-point tiles at ~78 % of it; an extra pass costs one product per element (cross twiddle table).
+    static const uint32_t tile_bits = getenv("LZKP_NTT_TILE_BITS") ? (uint32_t)atoi(getenv("LZKP_NTT_TILE_BITS")) : 10u;
+    const uint32_t tb = std::min(std::max(tile_bits, 4u), kMaxTileBits);
+    P->n_pass = std::max(1u, (log_n + tb - 1) / tb);
+    if (P->n_pass > 3) P->n_pass = 3;
     for (uint32_t q = 0; q < P->n_pass; q++) P->bits[q] = log_n / P->n_pass + (q < log_n % P->n_pass ? 1 : 0);
     P->tile_max = P->bits[0];
     P->lb = (log_n + 1) / 2;
@@ -214,6 +231,17 @@ static int get_plan(uint32_t log_n, int inverse, cudaStream_t st, NttPlan **out)
     LAUNCH(k_ntt_pow_table, (n_hi + 127) / 128, 128, 0, st, P->w_hi.as<Fr>(), w, Fr::one(), n_hi, P->lb);
     LAUNCH(k_ntt_pow_table, (n_lo + 127) / 128, 128, 0, st, P->g_lo.as<Fr>(), g, Fr::one(), n_lo, 0u);
     LAUNCH(k_ntt_pow_table, (n_hi + 127) / 128, 128, 0, st, P->g_hi.as<Fr>(), g, inverse ? P->ninv : Fr::one(), n_hi, P->lb);
+    // per-position cross twiddles (one product per element instead of two) while they stay below 1 GiB
+    static const bool cross_off = getenv("LZKP_NTT_NO_CROSS_TABLE") != nullptr;
+    if (!cross_off && P->n_pass > 1 && ((size_t)32 << log_n) * (P->n_pass - 1) <= ((size_t)1 << 30)) {
+        uint32_t log_stride = log_n;
+        for (uint32_t q = 0; q + 1 < P->n_pass; q++) {
+            log_stride -= P->bits[q];
+            TRY(P->cross[q].alloc((size_t)32 << log_n));
+            LAUNCH(k_ntt_cross_table, (unsigned)((((size_t)1 << log_n) + 255) / 256), 256, 0, st, P->cross[q].as<Fr>(),
+                   PowTable{P->w_lo.as<Fr>(), P->w_hi.as<Fr>(), P->lb}, log_n, P->bits[q], log_stride);
+        }
+    }
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
     static bool attr_set = false;
@@ -249,7 +277,10 @@ int large_ntt_device(void *d_in, void *d_out, uint32_t log_n, int inverse, int c
         A.q = q;
         A.log_stride = log_stride;
         // two columns per tile (64 contiguous bytes) while the tile still fits 128 KB of shared memory
-        A.log_cols = log_stride >= 1 ? 1 : 0;
+        // two adjacent columns per CTA (64 contiguous bytes) for small tiles; one column for 2^10+ tiles so that
+        // several CTAs share an SM and their load / compute / store phases overlap
+        A.log_cols = (log_stride >= 1 && b <= 9) ? 1 : 0;
+        A.cross = (q + 1 < P->n_pass && q < 2) ? P->cross[q].as<Fr>() : nullptr;
         A.tw_shift = P->tile_max - b;
         const uint32_t E = 1u << (b + A.log_cols);
         const uint32_t threads = std::max(32u, std::min(1024u, E / 4));
