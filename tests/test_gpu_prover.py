@@ -275,3 +275,32 @@ def test_device_setup_generic_csr_and_default_keygen(eq_keys, trapdoor, po):
     finally:
         snark.reset()
         snark.configure()
+
+
+def test_empty_and_single_batches(eq_pk, mb_pk, frs):
+    e = np.zeros((0, 32), np.uint8)
+    proofs, cms, status = eq_pk.prove_equality_batch(np.zeros(0, np.uint64), np.zeros(0, np.uint64), e, e)
+    assert proofs.shape == (0, 256) and status.shape == (0,)
+    proofs, status = eq_pk.prove_batch(np.zeros((0, eq_pk.n_vars * 32), np.uint8), e, e)
+    assert proofs.shape == (0, 256)
+    proofs, _, status = mb_pk.prove_membership_batch(np.zeros(0, np.uint64), np.zeros((0, 64), np.uint64),
+                                                     np.zeros(0, np.uint32), e, e)
+    assert proofs.shape == (0, 256)
+
+
+def test_multi_chunk_batch_matches_oracle(eq_keys, co, po, frs):
+    # more proofs than one device pass: chunks alternate between the two workspaces / streams; order is kept
+    pk = engine.ProvingKey(eq_keys.pk_bytes, window_bits=WINDOW_BITS, max_chunk=64)
+    pk.circuit_builtin(engine.EQUALITY, 110)
+    n = 64 * 5 + 17
+    rng = po.SplitMix64(33)
+    a = np.array([rng.next_u64() for _ in range(n)], np.uint64)
+    b = a.copy()
+    b[100] ^= 1
+    r, s = frs(34, n), frs(35, n)
+    proofs, cms, status = pk.prove_equality_batch(a, b, r, s)
+    want, wstat = co.prove_batch(eq_keys.circuit, eq_keys.opk, a, b, None, None, r, s)
+    assert np.array_equal(status != 0, wstat != 0) and status[100] == 1
+    assert np.array_equal(proofs, want)
+    assert cms[n - 1].tobytes() == co.mimc_hash(int(a[n - 1]))
+    pk.close()
