@@ -99,12 +99,13 @@ def prove_membership(value: int, set_: Sequence[int], rng=None) -> bytes:   # se
 
 
 def prove_equality_many(pairs: Sequence[Sequence[int]], rng=None) -> List[bytes]:
-    """The grouped fast path behind process_batch: same results as [prove_equality(a, b) ...]."""
+    """The grouped fast path behind process_batch: same results as [prove_equality(a, b) ...], with the MiMC
+    commitments computed on the device beside the witnesses instead of one host call per proof."""
     for a, b in pairs:
         _check_u64(a, b)
         validate_equality_params(a, b)
-    cms = [commit_value_snark(a) for a, _ in pairs]
-    proofs = SnarkBackend.prove_equality_zk_batch([p[0] for p in pairs], [p[1] for p in pairs], cms, rng)
+    proofs, cms = SnarkBackend.prove_equality_zk_batch([p[0] for p in pairs], [p[1] for p in pairs], None, rng,
+                                                       return_commitments=True)
     return [_wrap_equality(p, c) for p, c in zip(proofs, cms)]
 
 
@@ -113,6 +114,6 @@ def prove_membership_many(items: Sequence, rng=None) -> List[bytes]:
         _check_u64(v, *s)
         validate_membership_params(v, s)
         validate_set_size(s, MAX_SET_SIZE)
-    cms = [commit_value_snark(v) for v, _ in items]
-    proofs = SnarkBackend.prove_membership_zk_batch([v for v, _ in items], [list(s) for _, s in items], cms, rng)
+    proofs, cms = SnarkBackend.prove_membership_zk_batch([v for v, _ in items], [list(s) for _, s in items], None, rng,
+                                                         return_commitments=True)
     return [_wrap_membership(p, list(s), c) for p, (_, s), c in zip(proofs, items, cms)]

@@ -40,6 +40,24 @@ class OsRng:
     def next_fr(self) -> int:
         return secrets.randbelow(R_MOD)
 
+    def scalars(self, n: int) -> np.ndarray:
+        """n uniform canonical scalars as an (n, 32) byte array: OS entropy, 254-bit mask, rejection of values
+        >= r (the sampling rule arkworks' Fr::rand applies), vectorised so that a 4096-proof batch does not spend
+        longer drawing randomness on the host than proving on the device."""
+        out = np.zeros((0, 4), np.uint64)
+        r_words = np.array([(R_MOD >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], np.uint64)
+        while out.shape[0] < n:
+            m = max(64, int((n - out.shape[0]) * 1.5))
+            w = np.frombuffer(os.urandom(32 * m), dtype="<u8").reshape(m, 4).copy()
+            w[:, 3] &= np.uint64((1 << 62) - 1)
+            lt = np.zeros(m, bool)
+            eq = np.ones(m, bool)
+            for i in (3, 2, 1, 0):                      # lexicographic compare, most significant word first
+                lt |= eq & (w[:, i] < r_words[i])
+                eq &= w[:, i] == r_words[i]
+            out = np.concatenate([out, w[lt]])
+        return out[:n].view(np.uint8).reshape(n, 32).copy()
+
 
 class Setup:
     def __init__(self, pk: engine.ProvingKey, vk_bytes: bytes):
@@ -165,6 +183,8 @@ def _fr_from_commitment(b: bytes) -> Optional[int]:   # snark.rs:224-229: canoni
 
 
 def _scalars(rng, n: int) -> np.ndarray:
+    if hasattr(rng, "scalars"):
+        return rng.scalars(n)
     return np.frombuffer(b"".join(rng.next_fr().to_bytes(32, "little") for _ in range(n)), np.uint8).reshape(n, 32)
 
 
@@ -192,43 +212,55 @@ class SnarkBackend:
 
     # ---- batched: one device call for many independent proofs of one circuit
     @staticmethod
-    def prove_equality_zk_batch(a: Sequence[int], b: Sequence[int], hash_inputs: Sequence[bytes], rng=None
-                                ) -> List[bytes]:
+    def prove_equality_zk_batch(a: Sequence[int], b: Sequence[int], hash_inputs: Optional[Sequence[bytes]] = None,
+                                rng=None, return_commitments: bool = False):
+        """n x prove_equality_zk in one device call.  hash_inputs=None lets the device compute the MiMC
+        commitments (commit_value_snark) itself; with return_commitments the pair (proofs, commitments) is returned."""
         n = len(a)
         out: List[bytes] = [b""] * n
-        live = [i for i in range(n) if a[i] == b[i] and _fr_from_commitment(bytes(hash_inputs[i])) is not None]
+        cms_out: List[bytes] = [b""] * n
+        done = lambda: (out, cms_out) if return_commitments else out
+        live = [i for i in range(n) if a[i] == b[i]
+                and (hash_inputs is None or _fr_from_commitment(bytes(hash_inputs[i])) is not None)]
         if not live:
-            return out
+            return done()
         setup = SnarkBackend.get_universal_setup()
         if not isinstance(setup, Setup):
-            return out
+            return done()
         rng = rng or OsRng()
         rs = _scalars(rng, 2 * len(live))           # r then s per proof, the order prove() draws them
+        cm_in = None
+        if hash_inputs is not None:
+            cm_in = np.frombuffer(b"".join(bytes(hash_inputs[i]) for i in live), np.uint8).reshape(-1, 32)
         try:
-            proofs, _, status = setup.pk.prove_equality_batch(
-                np.array([a[i] for i in live], np.uint64), np.array([b[i] for i in live], np.uint64),
-                rs[0::2], rs[1::2],
-                np.frombuffer(b"".join(bytes(hash_inputs[i]) for i in live), np.uint8).reshape(-1, 32))
+            av = np.array([a[i] for i in live], np.uint64)
+            proofs, cms, status = setup.pk.prove_equality_batch(av, av, rs[0::2], rs[1::2], cm_in)
         except Exception:                           # noqa: BLE001 - any backend error -> empty Vec
-            return out
+            return done()
+        pb, cb = proofs.tobytes(), cms.tobytes()
         for k, i in enumerate(live):
             if status[k] == 0:
-                out[i] = proofs[k].tobytes()
-        return out
+                out[i] = pb[256 * k:256 * k + 256]
+                cms_out[i] = cb[32 * k:32 * k + 32]
+        return done()
 
     @staticmethod
     def prove_membership_zk_batch(values: Sequence[int], sets: Sequence[Sequence[int]],
-                                  commitments: Sequence[bytes], rng=None) -> List[bytes]:
+                                  commitments: Optional[Sequence[bytes]] = None, rng=None,
+                                  return_commitments: bool = False):
         n = len(values)
         out: List[bytes] = [b""] * n
+        cms_out: List[bytes] = [b""] * n
+        done = lambda: (out, cms_out) if return_commitments else out
         live = [i for i in range(n)
-                if 1 <= len(sets[i]) <= MAX_SET_SIZE and _fr_from_commitment(bytes(commitments[i])) is not None
+                if 1 <= len(sets[i]) <= MAX_SET_SIZE
+                and (commitments is None or _fr_from_commitment(bytes(commitments[i])) is not None)
                 and values[i] in sets[i]]
         if not live:
-            return out
+            return done()
         setup = SnarkBackend.get_membership_setup()
         if not isinstance(setup, Setup):
-            return out
+            return done()
         rng = rng or OsRng()
         rs = _scalars(rng, 2 * len(live))
         sets_arr = np.zeros((len(live), MAX_SET_SIZE), np.uint64)
@@ -236,16 +268,20 @@ class SnarkBackend:
         for k, i in enumerate(live):
             lens[k] = len(sets[i])
             sets_arr[k, :lens[k]] = np.array(sets[i], np.uint64)
+        cm_in = None
+        if commitments is not None:
+            cm_in = np.frombuffer(b"".join(bytes(commitments[i]) for i in live), np.uint8).reshape(-1, 32)
         try:
-            proofs, _, status = setup.pk.prove_membership_batch(
-                np.array([values[i] for i in live], np.uint64), sets_arr, lens, rs[0::2], rs[1::2],
-                np.frombuffer(b"".join(bytes(commitments[i]) for i in live), np.uint8).reshape(-1, 32))
+            proofs, cms, status = setup.pk.prove_membership_batch(
+                np.array([values[i] for i in live], np.uint64), sets_arr, lens, rs[0::2], rs[1::2], cm_in)
         except Exception:                           # noqa: BLE001
-            return out
+            return done()
+        pb, cb = proofs.tobytes(), cms.tobytes()
         for k, i in enumerate(live):
             if status[k] == 0:
-                out[i] = proofs[k].tobytes()
-        return out
+                out[i] = pb[256 * k:256 * k + 256]
+                cms_out[i] = cb[32 * k:32 * k + 32]
+        return done()
 
     # ---- ZkpBackend trait (src/backend/mod.rs:5-8; impl snark.rs:587-611)
     @staticmethod

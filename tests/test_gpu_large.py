@@ -142,3 +142,30 @@ def test_sharded_prover_world_1(co, trapdoor, frs):
     got = sp.prove(z, r[0].tobytes(), s[0].tobytes())
     assert got == co.prove(circ, co.ProvingKey(pk_bytes), z, co.fr_list(r)[0], co.fr_list(s)[0])
     sp.close()
+
+
+def test_membership_1024_slots_matches_oracle(co, trapdoor, frs, po):
+    # BASELINE.json configs[2]: membership with a 1024-element public set (m = 5453, n = 8192).  The reference
+    # itself caps sets at 64 (snark.rs:503); the same circuit re-parameterised runs on the large-domain path.
+    S = 1024
+    circ = co.Circuit("membership", S)
+    assert (circ.m, circ.n_inst, circ.n_wit, circ.n) == (5453, 2050, 3403, 8192)
+    pk_bytes, vk_bytes = engine.setup_builtin(engine.MEMBERSHIP, S, trapdoor)
+    opk_bytes, ovk_bytes = circ.setup(trapdoor)
+    assert pk_bytes == opk_bytes and vk_bytes == ovk_bytes
+    pk = engine.ProvingKey(pk_bytes)
+    pk.circuit_builtin(engine.MEMBERSHIP, S)
+    rng = po.SplitMix64(5)
+    n = 3
+    sets = np.array([[rng.next_u64() for _ in range(S)] for _ in range(n)], np.uint64)
+    lens = np.array([S, 700, 1], np.uint32)
+    vals = np.array([sets[0, 1023], sets[1, 350], sets[2, 0]], np.uint64)
+    r, s = frs(7, n), frs(8, n)
+    proofs, cms, status = pk.prove_membership_batch(vals, sets, lens, r, s)
+    assert not status.any()
+    opk = co.ProvingKey(opk_bytes)
+    for i in range(n):
+        z = circ.assign(int(vals[i]), set_=[int(v) for v in sets[i, :lens[i]]])
+        assert proofs[i].tobytes() == co.prove(circ, opk, z, co.fr_list(r[i])[0], co.fr_list(s[i])[0]), i
+        assert cms[i].tobytes() == co.mimc_hash(int(vals[i]))
+    pk.close()
