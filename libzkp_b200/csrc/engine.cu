@@ -114,7 +114,7 @@ struct HBuf {
 // run under the MSM kernels of the other.
 struct Workspace {
     uint32_t chunk = 0;            // proofs the buffers are sized for
-    DBuf z, abc, h, dig, r, s, rs, part1, part2, res1, res2, proofs, status, a, b, commit, sets, setlen;
+    DBuf z, abc, tmp, h, dig, r, s, rs, part1, part2, res1, res2, proofs, status, a, b, commit, sets, setlen;
     HBuf h_proofs, h_status, h_commit;
 };
 
@@ -142,8 +142,9 @@ struct lzkp_pk {
     Workspace ws[2];
     // large mode (domain above 2^12): Pippenger MSMs over resident window-shifted bases, tiled NTTs
     bool large = false;
+    bool tiled_wm = false;     // witness map on the tiled multi-pass NTT (domain above 2^12)
     MsmBases *L_a = nullptr, *L_b1 = nullptr, *L_b2 = nullptr, *L_l = nullptr, *L_h = nullptr;
-    DBuf L_tmp, L_sa, L_sb, L_sl;
+    DBuf L_sa, L_sb, L_sl;
     // single-proof sharding across GPUs: this rank's point range [lo, lo + cnt) of each query,
     // in the order a, b1, l, h, b2 (extras +-delta included); unsharded = the full ranges
     uint32_t shard_index = 0, shard_count = 1;
@@ -269,7 +270,16 @@ static int pk_load_impl(const uint8_t *bytes, size_t len, int validate, const lz
     pk->n_dig_rows = pk->nz + 3 + (n - 1);
     const uint32_t ROW_R = pk->nz, ROW_S = pk->nz + 1, ROW_RS = pk->nz + 2, ROW_H = pk->nz + 3;
 
-    pk->large = pk->log_n > 12 || getenv("LZKP_FORCE_LARGE") != nullptr;
+    // Resident window tables (batched proving) while the domain is at most 2^16 and the tables fit the memory
+    // budget at some c >= 8; beyond that, one proof per pass over Pippenger MSMs ("large" mode).
+    {
+        size_t free_b0 = 0, total_b0 = 0;
+        CUDA_TRY(cudaMemGetInfo(&free_b0, &total_b0));
+        const uint64_t budget0 = opt && opt->table_budget_bytes ? opt->table_budget_bytes : (uint64_t)(free_b0 * 0.6);
+        const uint64_t rows1_max = 2ull * nv + pk->n_wit + n + 2, rows2_max = (uint64_t)nv + 1;
+        const uint64_t min_table = (rows1_max * 64 + rows2_max * 128) * 32 * 128;      // c = 8: W = 32, N = 128
+        pk->large = pk->log_n > 16 || min_table > budget0 || getenv("LZKP_FORCE_LARGE") != nullptr;
+    }
     if (pk->large) {
         // A = alpha + a_q[0] + sum_{j>=1} z_j a_q[j] + r delta: delta rides along as one more base (scalar r / s / rs)
         CUDA_TRY(cudaStreamCreate(&pk->stream));
@@ -443,6 +453,17 @@ static int pk_load_impl(const uint8_t *bytes, size_t len, int validate, const lz
         TRY(build_table_g2(d_rows2.p, (uint32_t)rows2.size(), c, pk->W, pk->N, pk->g2.table.p, st));
     TRY(finish_plan(pk->g1, msm1, pk->W));
     TRY(finish_plan(pk->g2, msm2, pk->W));
+    // proofs per device pass: two workspaces must fit beside the tables
+    {
+        const uint64_t per_proof = (uint64_t)nv * 32 + 7ull * n * 32 + (uint64_t)pk->n_dig_rows * pk->W * 2 +
+                                   (uint64_t)pk->g1.n_items[1] * sizeof(G1XYZZ) + (uint64_t)pk->g2.n_items[0] * sizeof(G2XYZZ) +
+                                   4 * sizeof(G1XYZZ) + sizeof(G2XYZZ) + 1024;
+        size_t free_now = 0, total_now = 0;
+        CUDA_TRY(cudaMemGetInfo(&free_now, &total_now));
+        uint64_t fit = (uint64_t)(free_now * 0.4) / (2 * per_proof);
+        fit = std::max<uint64_t>(32, fit / 32 * 32);
+        if (pk->max_chunk > fit) pk->max_chunk = (uint32_t)fit;
+    }
     CUDA_TRY(cudaGetLastError());
     return LZKP_OK;
 }
@@ -455,7 +476,7 @@ static int circuit_install(lzkp_pk *pk, uint32_t m, uint32_t n_inst, uint32_t n_
     uint32_t n = 1;
     while (n < need) n <<= 1;
     if (n != pk->n) return fail(LZKP_E_INVALID, "circuit domain size does not match the proving key's h_query");
-    if (pk->log_n > 12 && !pk->large) return fail(LZKP_E_UNSUPPORTED, "batched witness map supports domains up to 2^12");
+    pk->tiled_wm = pk->large || pk->log_n > 12;      // above 2^12 a polynomial no longer fits one CTA's shared memory
     cudaStream_t st = pk->stream;
     for (int k = 0; k < 3; k++) {
         uint32_t nnz = rowptr[k][m];
@@ -480,7 +501,7 @@ static int circuit_install(lzkp_pk *pk, uint32_t m, uint32_t n_inst, uint32_t n_
     Fr gn = g;
     for (uint32_t i = 0; i < pk->log_n; i++) gn = gn.sqr();
     Fr zinv = (gn - Fr::one()).inverse();
-    if (pk->large) {          // transforms come from ntt_large.cu's cached plans; only Z(g)^-1 is needed here
+    if (pk->tiled_wm) {       // transforms come from ntt_large.cu's cached plans; only Z(g)^-1 is needed here
         pk->ntt = NttTables{nullptr, nullptr, nullptr, nullptr, nullptr, ninv, zinv};
         CUDA_TRY(cudaStreamSynchronize(st));
         CUDA_TRY(cudaGetLastError());
@@ -524,8 +545,8 @@ static int ensure_workspace(lzkp_pk *pk, Workspace &ws, uint32_t P) {
     TRY(ws.z.ensure(P * nv * 32));
     TRY(ws.abc.ensure(3 * P * n * 32));
     TRY(ws.h.ensure(P * n * 32));
+    if (pk->tiled_wm) TRY(ws.tmp.ensure(3 * P * n * 32));
     if (pk->large) {
-        TRY(pk->L_tmp.ensure(n * 32));
         TRY(pk->L_sa.ensure(nv * 32)); TRY(pk->L_sb.ensure(nv * 32)); TRY(pk->L_sl.ensure(((size_t)pk->n_wit + 1) * 32));
     } else {
         TRY(ws.dig.ensure((size_t)pk->n_dig_rows * pk->W * P * sizeof(int16_t)));
@@ -561,19 +582,19 @@ static int run_witness_map(lzkp_pk *pk, Workspace &ws, uint32_t P, cudaStream_t 
     const uint32_t n = pk->n, threads = std::max(32u, std::min(n / 2, 512u));
     const size_t smem = (size_t)32 * n;
     Region reg(pk, LZKP_REGION_WITNESS_MAP, st);
-    if (pk->large) {
-        // a3-a7 for one proof on a large domain: SpMV, then per vector iNTT -> coset NTT (tiled passes),
-        // pointwise (ab - c) / Z(g), coset iNTT, and one conversion of h to canonical form
-        Fr *abc = ws.abc.as<Fr>(), *tmp = pk->L_tmp.as<Fr>(), *h = ws.h.as<Fr>();
-        LAUNCH(k_spmv_abc, dim3((n + 127) / 128, 1), 128, 0, st, pk->csr[0], pk->csr[1], pk->csr[2], ws.z.as<Fr>(), abc, 1u,
+    if (pk->tiled_wm) {
+        // a3-a7 on a domain above 2^12: SpMV, then all 3P polynomials through iNTT -> coset NTT as ONE batch of
+        // tiled passes, pointwise (ab - c) / Z(g), coset iNTT of the P quotients, conversion of h to canonical form
+        Fr *abc = ws.abc.as<Fr>(), *tmp = ws.tmp.as<Fr>(), *h = ws.h.as<Fr>();
+        const size_t plane = (size_t)P * n;
+        LAUNCH(k_spmv_abc, dim3((n + 127) / 128, P), 128, 0, st, pk->csr[0], pk->csr[1], pk->csr[2], ws.z.as<Fr>(), abc, P,
                pk->n_vars, pk->m, pk->n_inst, n);
-        for (int k = 0; k < 3; k++) {
-            TRY(large_ntt_device(abc + (size_t)k * n, tmp, pk->log_n, 1, 0, st));
-            TRY(large_ntt_device(tmp, abc + (size_t)k * n, pk->log_n, 0, 1, st));
-        }
-        LAUNCH(k_pointwise_h, (n + 127) / 128, 128, 0, st, abc, abc + n, abc + 2 * (size_t)n, tmp, pk->ntt.zinv, n);
-        TRY(large_ntt_device(tmp, h, pk->log_n, 1, 1, st));
-        LAUNCH(k_fr_to_canonical, (n + 127) / 128, 128, 0, st, h, n);
+        TRY(large_ntt_device(abc, tmp, pk->log_n, 1, 0, st, 3 * P, n));
+        TRY(large_ntt_device(tmp, abc, pk->log_n, 0, 1, st, 3 * P, n));
+        LAUNCH(k_pointwise_h, (unsigned)((plane + 127) / 128), 128, 0, st, abc, abc + plane, abc + 2 * plane, tmp, pk->ntt.zinv,
+               plane);
+        TRY(large_ntt_device(tmp, h, pk->log_n, 1, 1, st, P, n));
+        LAUNCH(k_fr_to_canonical, (unsigned)((plane + 127) / 128), 128, 0, st, h, plane);
         return LZKP_OK;
     }
     LAUNCH(k_spmv_abc, dim3((n + 127) / 128, P), 128, 0, st, pk->csr[0], pk->csr[1], pk->csr[2], ws.z.as<Fr>(),

@@ -283,13 +283,13 @@ __global__ void k_ntt_small(Fr *data, NttTables T, uint32_t log_n, int inverse, 
 
 // Large-domain witness map helpers (the transforms themselves are ntt_large.cu's tiled passes).
 // hq[i] = (a[i] * b[i] - c[i]) * zinv on the coset (Montgomery in / out)
-__global__ void k_pointwise_h(const Fr *a, const Fr *b, const Fr *c, Fr *hq, Fr zinv, uint32_t n) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void k_pointwise_h(const Fr *a, const Fr *b, const Fr *c, Fr *hq, Fr zinv, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     st_vec(hq + i, (ld_vec(a + i) * ld_vec(b + i) - ld_vec(c + i)) * zinv);
 }
-__global__ void k_fr_to_canonical(Fr *v, uint32_t n) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void k_fr_to_canonical(Fr *v, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     st_vec(v + i, ld_vec(v + i).to_canonical());
 }

@@ -8,7 +8,9 @@ namespace eng {
 // In-place radix-2 (i)NTT over Fr on 2^log_n canonical elements in HOST memory (ntt_large.cu).
 int large_ntt_host(uint8_t *data, uint32_t log_n, int inverse, int coset);
 // Device buffers: d_in is clobbered for multi-pass sizes (log_n > 11), the result lands in d_out.
-int large_ntt_device(void *d_in, void *d_out, uint32_t log_n, int inverse, int coset, cudaStream_t st);
+// `batch` polynomials, `batch_stride` elements apart, are transformed by the same launches.
+int large_ntt_device(void *d_in, void *d_out, uint32_t log_n, int inverse, int coset, cudaStream_t st, uint32_t batch = 1,
+                     size_t batch_stride = 0);
 // Pippenger MSM over host buffers in ark-serialize layout (msm_large.cu).
 int large_msm_g1_host(const uint8_t *bases_affine, const uint8_t *scalars, size_t n, uint8_t *out_affine);
 int large_msm_g2_host(const uint8_t *bases_affine, const uint8_t *scalars, size_t n, uint8_t *out_affine);

@@ -62,6 +62,7 @@ struct PassArgs {
     uint32_t log_cols;      // columns per tile (1 << log_cols <= M_q)
     uint32_t tw_shift;      // tile twiddle table is for 2^tile_max points: index shift for smaller tiles
     const Fr *tile_tw;      // rho^k, k < 2^(tile_max-1)
+    size_t batch_stride;    // elements between consecutive polynomials of a batch (blockIdx.y)
     const Fr *cross;        // cross twiddle of this pass by output position (n entries), or null: two-level powers
     PowTable w;             // powers of the n-th root (forward or inverse)
     PowTable g;             // powers of the coset generator (forward) or its inverse times n^-1 (inverse)
@@ -94,6 +95,8 @@ __global__ void k_ntt_cross_table(Fr *cross, PowTable w, uint32_t log_n, uint32_
 
 __global__ void __launch_bounds__(1024) k_ntt_pass(const Fr *__restrict__ in, Fr *__restrict__ out, PassArgs A) {
     extern __shared__ uint4 smem[];
+    in += (size_t)blockIdx.y * A.batch_stride;
+    out += (size_t)blockIdx.y * A.batch_stride;
     const uint32_t b = A.bits[A.q], nq = 1u << b, cols = 1u << A.log_cols, E = nq << A.log_cols;
     SmemVec s{smem, smem + E};
     const uint32_t tiles_per_hi = 1u << (A.log_stride - A.log_cols);
@@ -256,7 +259,8 @@ static int get_plan(uint32_t log_n, int inverse, cudaStream_t st, NttPlan **out)
 
 // d_in is clobbered when the transform needs more than one pass; the result is written to d_out
 // (d_out may equal d_in only for single-pass sizes, log_n <= 11).
-int large_ntt_device(void *d_in, void *d_out, uint32_t log_n, int inverse, int coset, cudaStream_t st) {
+int large_ntt_device(void *d_in, void *d_out, uint32_t log_n, int inverse, int coset, cudaStream_t st, uint32_t batch,
+                     size_t batch_stride) {
     if (log_n > 28) return fail(LZKP_E_INVALID, "NTT size above 2^28 (the two-adicity of Fr)");
     NttPlan *P;
     TRY(get_plan(log_n, inverse, st, &P));
@@ -270,6 +274,9 @@ int large_ntt_device(void *d_in, void *d_out, uint32_t log_n, int inverse, int c
     A.ninv = P->ninv;
     A.inverse = inverse;
     A.coset = coset;
+    A.batch_stride = batch_stride;
+    if (batch == 0) return LZKP_OK;
+    if (batch > 65535) return fail(LZKP_E_INVALID, "NTT batch above 65535");
     uint32_t log_stride = log_n;
     for (uint32_t q = 0; q < P->n_pass; q++) {
         const uint32_t b = P->bits[q];
@@ -286,7 +293,8 @@ int large_ntt_device(void *d_in, void *d_out, uint32_t log_n, int inverse, int c
         const uint32_t threads = std::max(32u, std::min(1024u, E / 4));
         const size_t tiles = ((size_t)1 << log_n) >> (b + A.log_cols);
         const bool last = q + 1 == P->n_pass;
-        LAUNCH(k_ntt_pass, (unsigned)tiles, threads, (size_t)32 * E, st, (const Fr *)d_in, (Fr *)(last ? d_out : d_in), A);
+        LAUNCH(k_ntt_pass, dim3((unsigned)tiles, batch), threads, (size_t)32 * E, st, (const Fr *)d_in,
+               (Fr *)(last ? d_out : d_in), A);
     }
     CUDA_TRY(cudaGetLastError());
     return LZKP_OK;

@@ -123,17 +123,18 @@ def bench_large_proof(torch, dev, rounds=349524, iters=5):
     return out
 
 
-def bench_membership(torch, dev, n=1024, iters=5):
-    """BASELINE.json configs[2] at the reference's MAX_SET_SIZE = 64 (the 1024-slot variant is not runnable on the
-    reference, SURVEY.md headline fact 6): batch of 1024 membership proofs through the host-buffer C ABI."""
+def bench_membership(torch, dev, n=1024, iters=5, slots=64):
+    """BASELINE.json configs[2]: batch of 1024 membership proofs through the host-buffer C ABI, at the reference's
+    MAX_SET_SIZE = 64 and at the 1024-slot size the config names (m = 5453, n = 8192; the reference itself rejects
+    sets above 64, SURVEY.md headline fact 6)."""
     import time
-    pk_bytes, _ = engine.setup_builtin(engine.MEMBERSHIP, 64, _toxic(1))
+    pk_bytes, _ = engine.setup_builtin(engine.MEMBERSHIP, slots, _toxic(1))
     pk = engine.ProvingKey(pk_bytes)
-    pk.circuit_builtin(engine.MEMBERSHIP, 64)
+    pk.circuit_builtin(engine.MEMBERSHIP, slots)
     rng = np.random.default_rng(5)
-    sets = rng.integers(0, 2**63, size=(n, 64), dtype=np.uint64)
-    lens = np.full(n, 64, np.uint32)
-    vals = sets[np.arange(n), np.arange(n) % 64].copy()
+    sets = rng.integers(0, 2**63, size=(n, slots), dtype=np.uint64)
+    lens = np.full(n, slots, np.uint32)
+    vals = sets[np.arange(n), np.arange(n) % slots].copy()
     r = _uniform_fr(torch, dev, n, 7).cpu().numpy().view(np.uint8).reshape(n, 32)
     s = _uniform_fr(torch, dev, n, 8).cpu().numpy().view(np.uint8).reshape(n, 32)
     for _ in range(2):
@@ -142,7 +143,7 @@ def bench_membership(torch, dev, n=1024, iters=5):
     for _ in range(iters):
         proofs, _, status = pk.prove_membership_batch(vals, sets, lens, r, s)
     dt = (time.perf_counter() - t0) / iters
-    out = {"batch": n, "set_slots": 64, "ms_per_batch": 1e3 * dt, "proofs_per_s_e2e": n / dt, "failed": int((status != 0).sum()),
+    out = {"batch": n, "set_slots": slots, "domain": pk.n, "max_chunk": pk.max_chunk, "ms_per_batch": 1e3 * dt, "proofs_per_s_e2e": n / dt, "failed": int((status != 0).sum()),
            "table_gb": pk.table_bytes / 1e9, "window_bits": pk.window_bits}
     pk.close()
     return out
@@ -155,4 +156,5 @@ def bench(torch, dev, imad_peak, hbm_gbs):
             "ntt_2^22_coset_inverse": bench_ntt(torch, dev, imad_peak, hbm_gbs, 22, inverse=True, coset=True),
             "ntt_2^20": bench_ntt(torch, dev, imad_peak, hbm_gbs, 20),
             "membership_batch_1024": bench_membership(torch, dev),
+            "membership_1024_slots_batch_1024": bench_membership(torch, dev, iters=2, slots=1024),
             "proof_2^20_constraints": bench_large_proof(torch, dev)}

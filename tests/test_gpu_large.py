@@ -52,7 +52,8 @@ def test_mimc_chain_circuit_matches_oracle(co, po, trapdoor, frs, rounds):
     assert pk_bytes == opk_bytes and vk_bytes == ovk_bytes
     pk = engine.ProvingKey(pk_bytes)
     pk.circuit_builtin(engine.EQUALITY, rounds)
-    assert pk.n == circ.n and pk.max_chunk == 1
+    # 2^14: window tables still fit -> batched path with the tiled witness map; 2^17: one proof per pass
+    assert pk.n == circ.n and (pk.max_chunk == 1) == (circ.n > 1 << 16)
     z = np.stack([engine.builtin_witness(engine.EQUALITY, rounds, a, a) for a in (5, 2**64 - 1)])
     assert np.array_equal(z[0], circ.assign(5, 5, commitment=z[0, 1].tobytes()))
     assert np.array_equal(pk.witness_map(z)[1], circ.witness_map(z[1]))
@@ -97,7 +98,7 @@ def test_config4_2_20_constraints_proof_verifies(po, trapdoor, frs, co):
 
 
 @pytest.mark.parametrize("shards", [2, 3, 8])
-def test_sharded_single_proof_partials_combine(co, trapdoor, frs, shards):
+def test_sharded_single_proof_partials_combine(force_large, co, trapdoor, frs, shards):
     # §8e single-proof split, emulated on one GPU: every "rank" is a pk holding only its point ranges;
     # partial sums of all shards are combined by shard 0.  Bit-exact against the oracle's proof.
     import torch
@@ -130,7 +131,7 @@ def test_sharded_single_proof_partials_combine(co, trapdoor, frs, shards):
         pk.close()
 
 
-def test_sharded_prover_world_1(co, trapdoor, frs):
+def test_sharded_prover_world_1(force_large, co, trapdoor, frs):
     import torch
     from libzkp_b200.multi import ShardedProver
     rounds = 2730
@@ -144,6 +145,22 @@ def test_sharded_prover_world_1(co, trapdoor, frs):
     sp.close()
 
 
+def test_mid_size_circuit_forced_large_path(force_large, co, trapdoor, frs):
+    # the 2^14 chain circuit again, pushed onto the one-proof-per-pass path (two-pass NTT, Pippenger at n = 8k)
+    rounds = 2730
+    circ = co.Circuit("equality", rounds)
+    pk_bytes, _ = circ.setup(trapdoor)
+    pk = engine.ProvingKey(pk_bytes)
+    pk.circuit_builtin(engine.EQUALITY, rounds)
+    assert pk.max_chunk == 1
+    z = engine.builtin_witness(engine.EQUALITY, rounds, 12, 12)[None]
+    r, s = frs(4, 1), frs(40, 1)
+    proofs, status = pk.prove_batch(z, r, s)
+    assert not status.any()
+    assert proofs[0].tobytes() == co.prove(circ, co.ProvingKey(pk_bytes), z[0], co.fr_list(r)[0], co.fr_list(s)[0])
+    pk.close()
+
+
 def test_membership_1024_slots_matches_oracle(co, trapdoor, frs, po):
     # BASELINE.json configs[2]: membership with a 1024-element public set (m = 5453, n = 8192).  The reference
     # itself caps sets at 64 (snark.rs:503); the same circuit re-parameterised runs on the large-domain path.
@@ -155,6 +172,7 @@ def test_membership_1024_slots_matches_oracle(co, trapdoor, frs, po):
     assert pk_bytes == opk_bytes and vk_bytes == ovk_bytes
     pk = engine.ProvingKey(pk_bytes)
     pk.circuit_builtin(engine.MEMBERSHIP, S)
+    assert pk.max_chunk > 1 and pk.window_bits >= 8           # batched path: window tables + tiled witness map
     rng = po.SplitMix64(5)
     n = 3
     sets = np.array([[rng.next_u64() for _ in range(S)] for _ in range(n)], np.uint64)
