@@ -99,11 +99,24 @@ __global__ void __launch_bounds__(BLOCK) k_bucket_accum(const uint32_t *__restri
     uint32_t cur = kp[0];
     int run = 0;
     XYZZ<F> acc = XYZZ<F>::inf();
-    Affine<F> pt = fetch_point(points, vp[0]);
+    // G1: the next point is loaded into registers under the current add.  G2 is register-starved (a 256-byte
+    // accumulator, 128-byte points, 255 registers): it only issues an L2 prefetch for the next point instead.
+    constexpr bool kRegPrefetch = sizeof(F) == sizeof(Fq);
+    Affine<F> pt = Affine<F>::inf();
+    if constexpr (kRegPrefetch) pt = fetch_point(points, vp[0]);
     for (uint32_t j = 0; j < len; j++) {
         uint32_t k = kp[j];
         Affine<F> nxt = Affine<F>::inf();
-        if (j + 1 < len) nxt = fetch_point(points, vp[j + 1]);       // prefetch under the current add
+        if constexpr (kRegPrefetch) {
+            if (j + 1 < len) nxt = fetch_point(points, vp[j + 1]);       // prefetch under the current add
+        } else {
+            if (j + 1 < len) {
+                const char *np_ = reinterpret_cast<const char *>(points + (vp[j + 1] & 0x7FFFFFFFu));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(np_));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(np_ + 64));
+            }
+            pt = fetch_point(points, vp[j]);
+        }
         if (k != cur) {
             if (run == 0) { pkey[2 * t] = cur; st_vec(ppt + 2 * t, acc); }
             else st_vec(buckets + cur, acc);                          // a run strictly inside the chunk: complete
@@ -112,7 +125,7 @@ __global__ void __launch_bounds__(BLOCK) k_bucket_accum(const uint32_t *__restri
             cur = k;
         }
         acc.madd(pt);
-        pt = nxt;
+        if constexpr (kRegPrefetch) pt = nxt;
     }
     if (run == 0) {
         pkey[2 * t] = cur; st_vec(ppt + 2 * t, acc);
@@ -523,7 +536,8 @@ static int msm_run(MsmBases *B, const Fr *d_scalars, uint32_t n_used, uint8_t *d
     const uint32_t *keys = dk.Current(), *vals = dv.Current();
     uint32_t *count = B->count.as<uint32_t>();
     LAUNCH(k_find_count, 1, 1, 0, st, keys, (uint32_t)total, count);
-    LAUNCH((k_bucket_accum<F, kChunk, 128>), (B->T + 127) / 128, 128, 0, st, keys, vals, count, B->points.as<Affine<F>>(),
+    constexpr int AB = sizeof(F) == sizeof(Fq) ? 128 : 64;     // G2 runs at 255 registers: smaller CTAs fill the SMs better
+    LAUNCH((k_bucket_accum<F, kChunk, AB>), (B->T + AB - 1) / AB, AB, 0, st, keys, vals, count, B->points.as<Affine<F>>(),
            B->buckets.as<X>(), B->pkey.as<uint32_t>(), B->ppt.as<X>());
     uint32_t *pk = B->pkey.as<uint32_t>();
     X *pp = B->ppt.as<X>();
