@@ -4,6 +4,11 @@
 #include "tables.h"
 #include "dev_util.cuh"
 
+#ifndef LZKP_G2_MINB
+#define LZKP_G2_MINB 4
+#endif
+// minimum resident CTAs per SM: G1 kernels leave it to ptxas, G2 kernels (64-thread CTAs) trade registers for warps
+#define LZKP_G2_MINB_SEL(F) (sizeof(F) == sizeof(::lzkp::Fq) ? 1 : LZKP_G2_MINB)
 namespace lzkp {
 
 // ---------------------------------------------------------------- batched table MSM
@@ -12,7 +17,7 @@ namespace lzkp {
 // digit d of every unit in the item and accumulates in XYZZ.  Lanes of a warp are 32 different proofs
 // walking the same units, so a warp-step touches one N*sizeof(point) slab (2 MiB for G1 at c=16).
 template <class F, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_msm_batch(const Affine<F> *__restrict__ table, uint32_t N,
+__global__ void __launch_bounds__(BLOCK, LZKP_G2_MINB_SEL(F)) k_msm_batch(const Affine<F> *__restrict__ table, uint32_t N,
                                                      const uint32_t *__restrict__ unit_dig,
                                                      const uint32_t *__restrict__ unit_tbl,
                                                      const uint2 *__restrict__ items, const int16_t *__restrict__ dig,

@@ -27,6 +27,11 @@
 #include "host_util.h"
 #include "large.h"
 
+#ifndef LZKP_G2_MINB
+#define LZKP_G2_MINB 4
+#endif
+// minimum resident CTAs per SM: G1 kernels leave it to ptxas, G2 kernels (64-thread CTAs) trade registers for warps
+#define LZKP_G2_MINB_SEL(F) (sizeof(F) == sizeof(::lzkp::Fq) ? 1 : LZKP_G2_MINB)
 namespace lzkp {
 
 namespace {
@@ -87,7 +92,7 @@ __device__ __forceinline__ Affine<F> fetch_point(const Affine<F> *__restrict__ p
 }
 
 template <class F, int L, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_bucket_accum(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+__global__ void __launch_bounds__(BLOCK, LZKP_G2_MINB_SEL(F)) k_bucket_accum(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals,
                                                         const uint32_t *__restrict__ count,
                                                         const Affine<F> *__restrict__ points, XYZZ<F> *__restrict__ buckets,
                                                         uint32_t *__restrict__ pkey, XYZZ<F> *__restrict__ ppt) {

@@ -34,12 +34,16 @@ def _time(torch, fn, iters, warmup=3):
     return e0.elapsed_time(e1) / iters
 
 
-def bench_msm(torch, dev, imad_peak, log_n=20, group=1, c=16, iters=10, resident=True):
+def bench_msm(torch, dev, imad_peak, log_n=20, group=1, c=16, iters=10, resident=True, witness_like=False):
     n = 1 << log_n
     ks = _uniform_fr(torch, dev, n, 9).cpu().numpy().view(np.uint8).reshape(n, 32)
     bases = engine.generator_mul(group, ks)                      # n distinct points k_i * G
     B = engine.MsmBases(group, bases, window_bits=c, resident_windows=resident)
     sc = _uniform_fr(torch, dev, n, 10)
+    if witness_like:                    # half of the scalars are 0 or 1 (booleans, unused wires)
+        sc[0::4] = 0
+        sc[1::4] = 0
+        sc[1::4, 0] = 1
     out = torch.zeros(64 if group == 1 else 128, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
     ms = _time(torch, lambda: B.msm_device(sc.data_ptr(), n, out.data_ptr(), stream), iters)
@@ -55,6 +59,7 @@ def bench_msm(torch, dev, imad_peak, log_n=20, group=1, c=16, iters=10, resident
             "imad_achieved_T": muls * IMAD_PER_MUL / (ms * 1e-3) / 1e12,
             "imad_frac_of_measured_peak": muls * IMAD_PER_MUL / (ms * 1e-3) / imad_peak,
             "mode": "bases resident in HBM with all window multiples" if resident else "one bucket set per window",
+            "scalars": "50% zero/one, 50% uniform" if witness_like else "uniform in [0, r)",
             "result_hex": bytes(out.cpu().numpy()).hex()[:32], "_check": kl is not None}
 
 
@@ -151,6 +156,8 @@ def bench_membership(torch, dev, n=1024, iters=5, slots=64):
 
 def bench(torch, dev, imad_peak, hbm_gbs):
     return {"msm_g1_2^20": bench_msm(torch, dev, imad_peak, 20, 1),
+            "msm_g1_2^20_witness_like": bench_msm(torch, dev, imad_peak, 20, 1, witness_like=True),
+            "msm_g1_2^20_one_shot_bases": bench_msm(torch, dev, imad_peak, 20, 1, resident=False),
             "msm_g2_2^18": bench_msm(torch, dev, imad_peak, 18, 2, iters=5),
             "ntt_2^22": bench_ntt(torch, dev, imad_peak, hbm_gbs, 22),
             "ntt_2^22_coset_inverse": bench_ntt(torch, dev, imad_peak, hbm_gbs, 22, inverse=True, coset=True),
