@@ -122,6 +122,87 @@ LZ_COLD XYZZ<F> scalar_mul(const XYZZ<F> &p, const Fr &k_canonical) {
     return acc;
 }
 
+// ---- GLV split of a BN254 scalar: k = +-k1 +- k2 * lambda (mod r) with k1, k2 < 2^128, where lambda is the
+// eigenvalue of the G1 endomorphism phi(x, y) = (beta * x, y).  Halves the serial doubling chain of a
+// variable-base scalar multiplication (proof assembly: s * A and r * B1).  Lattice basis (a1, b1), (a2, b2)
+// from the extended Euclidean algorithm on (r, lambda); c_i = floor(k * g_i / 2^256) with g_i = floor(2^256 *
+// {b2, -b1} / r) (checked against exact rounding over 2 * 10^5 scalars: |k1|, |k2| <= 2^127).
+struct GlvSplit {
+    uint32_t k1[4], k2[4];
+    bool neg1, neg2, ok;      // ok == false: magnitudes did not fit 128 bits (never observed) -> caller uses the plain ladder
+};
+// out (no limbs) = low limbs of a (na limbs) * b (nb limbs)
+template <int NO, int NA, int NB>
+LZ_HD void mul_limbs(uint32_t (&out)[NO], const uint32_t (&a)[NA], const uint32_t (&b)[NB]) {
+    uint64_t acc = 0, hi = 0;
+#pragma unroll
+    for (int k = 0; k < NO; k++) {
+#pragma unroll
+        for (int i = 0; i < NA; i++) {
+            int j = k - i;
+            if (j < 0 || j >= NB) continue;
+            uint64_t p = (uint64_t)a[i] * b[j];
+            acc += (uint32_t)p;
+            hi += p >> 32;
+        }
+        out[k] = (uint32_t)acc;
+        acc = (acc >> 32) + hi;
+        hi = 0;
+    }
+}
+LZ_HD GlvSplit glv_split(const Fr &k) {
+    const uint32_t G1C[5] = {0x00ff6565u, 0x5398fd03u, 0xa773d2d2u, 0x4ccef014u, 0x00000002u};
+    const uint32_t G2C[3] = {0xc7e0b3d7u, 0xd91d232eu, 0x00000002u};
+    const uint32_t A1[4] = {0x7d4f1128u, 0x8211bbebu, 0xeeb859fcu, 0x6f4d8248u};
+    const uint32_t A2[2] = {0x94d213e3u, 0x89d32568u};          // a2 = -b1
+    const uint32_t B2[4] = {0x1221250bu, 0x0be4e154u, 0xeeb859fdu, 0x6f4d8248u};
+    uint32_t t13[13], t11[11], c1[5], c2[3];
+    mul_limbs<13, 8, 5>(t13, k.l, G1C);
+#pragma unroll
+    for (int i = 0; i < 5; i++) c1[i] = t13[8 + i];
+    mul_limbs<11, 8, 3>(t11, k.l, G2C);
+#pragma unroll
+    for (int i = 0; i < 3; i++) c2[i] = t11[8 + i];
+    // k1 = k - c1 a1 - c2 a2,  k2 = c1 |b1| - c2 b2   (mod 2^256, two's complement)
+    uint32_t p1[8], p2[8], p3[8], p4[8], k1[8], k2[8], t[8];
+    mul_limbs<8, 5, 4>(p1, c1, A1);
+    mul_limbs<8, 3, 2>(p2, c2, A2);
+    mul_limbs<8, 5, 2>(p3, c1, A2);       // |b1| == a2
+    mul_limbs<8, 3, 4>(p4, c2, B2);
+    sub8(t, k.l, p1);
+    sub8(k1, t, p2);
+    sub8(k2, p3, p4);
+    GlvSplit o;
+    o.neg1 = (k1[7] >> 31) != 0;
+    o.neg2 = (k2[7] >> 31) != 0;
+    uint32_t zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (o.neg1) { sub8(t, zero, k1);
+#pragma unroll
+        for (int i = 0; i < 8; i++) k1[i] = t[i]; }
+    if (o.neg2) { sub8(t, zero, k2);
+#pragma unroll
+        for (int i = 0; i < 8; i++) k2[i] = t[i]; }
+    o.ok = (k1[4] | k1[5] | k1[6] | k1[7] | k2[4] | k2[5] | k2[6] | k2[7]) == 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { o.k1[i] = k1[i]; o.k2[i] = k2[i]; }
+    return o;
+}
+// k * p for a 128-bit magnitude, MSB-first double-and-add
+template <class F>
+LZ_COLD XYZZ<F> scalar_mul_u128(const XYZZ<F> &p, const uint32_t (&k)[4]) {
+    XYZZ<F> acc = XYZZ<F>::inf();
+    bool started = false;
+#pragma unroll 1
+    for (int i = 127; i >= 0; i--) {
+        if (started) acc.dbl_cold();
+        if ((k[i >> 5] >> (i & 31)) & 1u) {
+            acc.add_cold(p);
+            started = true;
+        }
+    }
+    return acc;
+}
+
 using G1Affine = Affine<Fq>;
 using G2Affine = Affine<Fq2>;
 using G1XYZZ = XYZZ<Fq>;

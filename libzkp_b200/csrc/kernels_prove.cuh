@@ -332,32 +332,44 @@ struct ProofConsts {
     G2Affine b2;        // beta_g2 + b_g2_query[0]
 };
 // g1[q * P + p]: q = 0 A-sum (incl. r*delta), 1 B1-sum (incl. s*delta), 2 L-sum (incl. -rs*delta), 3 H-sum.
-// The stage is a chain of ~4000 dependent field products per proof (two 254-bit scalar multiplications,
-// three inversions), so it is latency-bound: the four independent strands of a proof run on four warps of
-// the CTA (warp-uniform roles, lane = proof) and meet once in shared memory.
-//   warp 0: s * A, then C = s*A + r*B1 + L + H -> affine -> bytes      warp 2: A -> affine -> bytes
-//   warp 1: r * B1                                                     warp 3: B (G2) -> affine -> bytes
-// Launch with 128 threads and role0 = 0 for all four strands, or as two launches - 96 threads / role0 = 0 (the G1
-// strands, which only need the G1 sums) and 32 threads / role0 = 3 (the G2 strand) - so that the G1 part can run
-// on a side stream underneath the G2 MSM.
-__global__ void __launch_bounds__(128) k_assemble(const G1XYZZ *g1, const G2XYZZ *g2, ProofConsts K, const Fr *r,
-                                                  const Fr *s, uint32_t P, uint8_t *proofs, uint32_t role0) {
-    __shared__ uint4 sm_raw[32 * sizeof(G1XYZZ) / 16];
+// The stage is a chain of dependent field products per proof (two variable-base scalar multiplications,
+// three inversions), so it is latency-bound.  Its independent strands run on six warps of the CTA
+// (warp-uniform roles, lane = proof) and meet once in shared memory; each scalar multiplication is split by
+// the GLV endomorphism into two 128-bit ladders (k = +-k1 +- k2 lambda, phi(P) = (beta x, y)):
+//   warp 0: k1(s) * A, then C = s*A + r*B1 + L + H -> affine -> bytes      warp 4: A -> affine -> bytes
+//   warp 1: k2(s) * phi(A)     warp 2: k1(r) * B1     warp 3: k2(r) * phi(B1)     warp 5: B (G2) -> affine -> bytes
+__device__ __forceinline__ G1XYZZ glv_half(const G1XYZZ &P, const Fr &k, int half) {
+    GlvSplit sp = glv_split(k);
+    if (!sp.ok) return half == 0 ? scalar_mul(P, k) : G1XYZZ::inf();
+    G1XYZZ Q = P;
+    if (half == 1) {
+        Fq beta;
+#pragma unroll
+        for (int i = 0; i < 8; i++) beta.l[i] = FqParams::BETA(i);
+        Q.x = Q.x * beta;
+    }
+    if (half == 0 ? sp.neg1 : sp.neg2) Q.y = Q.y.neg();
+    return half == 0 ? scalar_mul_u128(Q, sp.k1) : scalar_mul_u128(Q, sp.k2);
+}
+__global__ void __launch_bounds__(192) k_assemble(const G1XYZZ *g1, const G2XYZZ *g2, ProofConsts K, const Fr *r,
+                                                  const Fr *s, uint32_t P, uint8_t *proofs) {
+    __shared__ uint4 sm_raw[3 * 32 * sizeof(G1XYZZ) / 16];
     G1XYZZ *sm = reinterpret_cast<G1XYZZ *>(sm_raw);
-    const uint32_t role = role0 + (threadIdx.x >> 5), lane = threadIdx.x & 31, p = blockIdx.x * 32 + lane;
+    const uint32_t role = threadIdx.x >> 5, lane = threadIdx.x & 31, p = blockIdx.x * 32 + lane;
     const bool live = p < P;
     uint8_t *out = proofs + (size_t)p * 256;
     G1XYZZ acc = G1XYZZ::inf();
     if (live) {
-        if (role == 0 || role == 2) {
+        if (role <= 1 || role == 4) {
             G1XYZZ A = ld_vec(g1 + p);
             A.madd_cold(K.a0);
-            if (role == 2) write_g1(out, A.to_affine());
-            else acc = scalar_mul(A, ld_vec(s + p));
-        } else if (role == 1) {
+            if (role == 4) write_g1(out, A.to_affine());
+            else if (role == 0) acc = glv_half(A, ld_vec(s + p), 0);
+            else st_vec(sm + lane, glv_half(A, ld_vec(s + p), 1));
+        } else if (role <= 3) {
             G1XYZZ B1 = ld_vec(g1 + (size_t)P + p);
             B1.madd_cold(K.b0);
-            st_vec(sm + lane, scalar_mul(B1, ld_vec(r + p)));
+            st_vec(sm + (role - 1) * 32 + lane, glv_half(B1, ld_vec(r + p), role - 2));
         } else {
             G2XYZZ B2 = ld_vec(g2 + p);
             B2.madd_cold(K.b2);
@@ -367,6 +379,8 @@ __global__ void __launch_bounds__(128) k_assemble(const G1XYZZ *g1, const G2XYZZ
     __syncthreads();
     if (role == 0 && live) {
         acc.add_cold(ld_vec(sm + lane));
+        acc.add_cold(ld_vec(sm + 32 + lane));
+        acc.add_cold(ld_vec(sm + 64 + lane));
         acc.add_cold(ld_vec(g1 + 2 * (size_t)P + p));
         acc.add_cold(ld_vec(g1 + 3 * (size_t)P + p));
         write_g1(out + 192, acc.to_affine());

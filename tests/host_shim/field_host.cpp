@@ -1,6 +1,6 @@
 // Host build of libzkp_b200/csrc/field.cuh (row primitives take their portable C++
 // bodies) so the Montgomery composition logic can be checked without a GPU.
-#include "../../libzkp_b200/csrc/field.cuh"
+#include "../../libzkp_b200/csrc/ec.cuh"
 #include <cstring>
 using namespace lzkp;
 template <class F> static void ld(F &f, const uint8_t *p) { std::memcpy(f.l, p, 32); }
@@ -20,4 +20,12 @@ void fq_op(int op, const uint8_t *a, const uint8_t *b, uint8_t *o) {
     st(o, r);
 }
 int fq_gt(const uint8_t *a, const uint8_t *b) { Fq x, y; ld(x, a); ld(y, b); return Fq::gt_canonical(x, y); }
+// GLV split (ec.cuh): out = k1 (16 B) || k2 (16 B); returns neg1 | neg2 << 1 | ok << 2
+int glv_split_host(const uint8_t *k, uint8_t *out) {
+    Fr x; ld(x, k);
+    GlvSplit sp = glv_split(x);
+    std::memcpy(out, sp.k1, 16);
+    std::memcpy(out + 16, sp.k2, 16);
+    return (sp.neg1 ? 1 : 0) | (sp.neg2 ? 2 : 0) | (sp.ok ? 4 : 0);
+}
 }

@@ -111,6 +111,24 @@ def test_device_field_composition_on_host(field_shim, po):
     assert field_shim.fq_gt((C.c_uint8 * 32)(*(4).to_bytes(32, "little")), (C.c_uint8 * 32)(*(4).to_bytes(32, "little"))) == 0
 
 
+def test_glv_split_on_host(field_shim, po):
+    """ec.cuh's GLV split: k == +-k1 +- k2 * lambda (mod r) with both halves below 2^128."""
+    lam = 0x30644e72e131a029048b6e193fd84104cc37a73fec2bc5e9b8ca0b2d36636f23
+    beta = 0x30644e72e131a0295e6dd9e7e0acccb0c28f069fbb966e3de4bd44e5607cfd48
+    assert (lam * lam + lam + 1) % po.R_MOD == 0 and pow(beta, 3, po.Q_MOD) == 1 and beta != 1
+    G = po.G1_GEN
+    assert po.G1.mul(G, lam) == (beta * G[0] % po.Q_MOD, G[1])         # phi(P) = lambda * P
+    rng = po.SplitMix64(123)
+    ks = [0, 1, 2, po.R_MOD - 1, po.R_MOD - 2, lam, lam + 1, po.R_MOD // 2, 1 << 253] + [rng.next_fr() for _ in range(3000)]
+    for k in ks:
+        out = (C.c_uint8 * 32)()
+        fl = field_shim.glv_split_host((C.c_uint8 * 32)(*k.to_bytes(32, "little")), out)
+        assert fl & 4, "split must fit 128 bits"
+        k1 = int.from_bytes(bytes(out[:16]), "little") * (-1 if fl & 1 else 1)
+        k2 = int.from_bytes(bytes(out[16:]), "little") * (-1 if fl & 2 else 1)
+        assert (k1 + k2 * lam - k) % po.R_MOD == 0
+
+
 # ---------------------------------------------------------------- host mirror behaviour
 def test_envelope_layout_and_limits():
     p = proof.Proof(2, b"\x01" * 256, b"\x02" * 32)
