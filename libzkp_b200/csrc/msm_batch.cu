@@ -42,19 +42,34 @@ __global__ void __launch_bounds__(BLOCK, LZKP_G2_MINB_SEL(F)) k_msm_batch(const 
     }
     st_vec(partial + (size_t)item * P + p, acc);
 }
-// out[q * P + p] = sum of partial[item][p] over the items of MSM q.  grid (ceil(P/128), n_msm)
+// Reduction of the per-item partial sums, in two launches so that the serial chain per thread stays short:
+// stage 1: thread (p, q, g) folds items first+g, first+g+G, ... of MSM q into slot first+g (in place);
+// stage 2: out[q * P + p] = sum of the first min(G, count) slots.
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_reduce1(XYZZ<F> *partial, const uint2 *msm_items, uint32_t P, uint32_t G) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x, q = blockIdx.y, g = blockIdx.z;
+    if (p >= P) return;
+    uint2 r = msm_items[q];
+    if (r.x + g >= r.y) return;
+    XYZZ<F> acc = ld_vec(partial + (size_t)(r.x + g) * P + p);
+    for (uint32_t it = r.x + g + G; it < r.y; it += G) acc.add_cold(ld_vec(partial + (size_t)it * P + p));
+    st_vec(partial + (size_t)(r.x + g) * P + p, acc);
+}
 template <class F>
 __global__ void __launch_bounds__(128) k_msm_reduce(const XYZZ<F> *partial, const uint2 *msm_items, uint32_t P,
-                                                    XYZZ<F> *out) {
+                                                    uint32_t G, XYZZ<F> *out) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x, q = blockIdx.y;
     if (p >= P) return;
     uint2 r = msm_items[q];
+    uint32_t end = min(r.y, r.x + G);
     XYZZ<F> acc = XYZZ<F>::inf();
-    for (uint32_t it = r.x; it < r.y; it++) acc.add_cold(ld_vec(partial + (size_t)it * P + p));
+    for (uint32_t it = r.x; it < end; it++) acc.add_cold(ld_vec(partial + (size_t)it * P + p));
     st_vec(out + (size_t)q * P + p, acc);
 }
 
+}  // namespace lzkp
 
+namespace lzkp {
 namespace eng {
 
 // gather + accumulate the items [item0, item0 + count) (partial sums land at their global item index)
@@ -63,9 +78,12 @@ void batch_msm_g1_items(const BatchMsmArgs &a, uint32_t item0, uint32_t count, c
     LAUNCH((k_msm_batch<Fq, 128>), dim3((a.P + 127) / 128, count), 128, 0, st, (const G1Affine *)a.table, a.N, a.unit_dig,
            a.unit_tbl, (const uint2 *)a.items + item0, a.dig, a.P, (G1XYZZ *)a.partial + (size_t)item0 * a.P);
 }
+constexpr uint32_t kReduceFan = 8;
 void batch_msm_g1_reduce(const BatchMsmArgs &a, cudaStream_t st) {
+    LAUNCH((k_msm_reduce1<Fq>), dim3((a.P + 127) / 128, a.n_msm, kReduceFan), 128, 0, st, (G1XYZZ *)a.partial,
+           (const uint2 *)a.msm_items, a.P, kReduceFan);
     LAUNCH((k_msm_reduce<Fq>), dim3((a.P + 127) / 128, a.n_msm), 128, 0, st, (const G1XYZZ *)a.partial,
-           (const uint2 *)a.msm_items, a.P, (G1XYZZ *)a.out);
+           (const uint2 *)a.msm_items, a.P, kReduceFan, (G1XYZZ *)a.out);
 }
 void batch_msm_g1(const BatchMsmArgs &a, cudaStream_t st) {
     batch_msm_g1_items(a, 0, a.n_items, st);
@@ -74,8 +92,10 @@ void batch_msm_g1(const BatchMsmArgs &a, cudaStream_t st) {
 void batch_msm_g2(const BatchMsmArgs &a, cudaStream_t st) {
     LAUNCH((k_msm_batch<Fq2, 64>), dim3((a.P + 63) / 64, a.n_items), 64, 0, st, (const G2Affine *)a.table, a.N,
            a.unit_dig, a.unit_tbl, (const uint2 *)a.items, a.dig, a.P, (G2XYZZ *)a.partial);
+    LAUNCH((k_msm_reduce1<Fq2>), dim3((a.P + 127) / 128, a.n_msm, 2 * kReduceFan), 128, 0, st, (G2XYZZ *)a.partial,
+           (const uint2 *)a.msm_items, a.P, 2 * kReduceFan);
     LAUNCH((k_msm_reduce<Fq2>), dim3((a.P + 127) / 128, a.n_msm), 128, 0, st, (const G2XYZZ *)a.partial,
-           (const uint2 *)a.msm_items, a.P, (G2XYZZ *)a.out);
+           (const uint2 *)a.msm_items, a.P, 2 * kReduceFan, (G2XYZZ *)a.out);
 }
 
 }  // namespace eng
