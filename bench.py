@@ -83,6 +83,25 @@ def imad_peak():
         else (IMAD_PEAK_FALLBACK, "fallback")
 
 
+def ncu_traffic(kernel_substr):
+    """dram__bytes_read + dram__bytes_write per launch of a kernel, from the committed ncu --set full summary."""
+    path = os.path.join(ROOT, "profiles", "r1_ncu_msm_batch.txt")
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    try:
+        lines = open(path).read().splitlines()
+    except OSError:
+        return None
+    for i, line in enumerate(lines):
+        if line.startswith("==") and kernel_substr in line:
+            tot = 0.0
+            for l2 in lines[i + 1:i + 8]:
+                parts = l2.split()
+                if len(parts) >= 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    tot += float(parts[1]) * unit.get(parts[2], 1.0)
+            return tot or None
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -277,7 +296,9 @@ def run_ours(args, rank, world, local_rank):
     roofline = {
         "bound": "imad", "kernel": "k_msm_batch<Fq> + k_msm_reduce<Fq> (G1 fixed-base table MSM)",
         "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "T IMAD/s", "frac": achieved / peak,
-        "peak_source": peak_src, "traffic": None,
+        "peak_source": peak_src, "traffic": ncu_traffic("k_msm_batch<Fp<FqParams>"),
+        "traffic_note": "DRAM bytes per launch from profiles/r1_ncu_msm_batch.txt (ncu --set full); algorithmic bytes "
+                        "are in hbm.algorithmic_bytes_per_launch - 64 B table entries are fetched as 128 B lines",
         "algorithmic_imad_per_launch": imad_per_launch, "avg_launch_ms": ms_g1 / max(n_g1, 1),
         "share_of_step": ms_g1 / ms,
         "hbm": {"algorithmic_bytes_per_launch": bytes_per_launch,
