@@ -145,6 +145,10 @@ struct lzkp_pk {
     bool tiled_wm = false;     // witness map on the tiled multi-pass NTT (domain above 2^12)
     MsmBases *L_a = nullptr, *L_b1 = nullptr, *L_b2 = nullptr, *L_l = nullptr, *L_h = nullptr;
     DBuf L_sa, L_sb, L_sl;
+    // the five MSMs of one large proof run on side streams (each MsmBases has its own workspace), so the
+    // latency-bound tail of one (bucket reduction, a few CTAs) runs under the accumulation of another
+    cudaStream_t L_st[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t L_ev_in = nullptr, L_ev_done[3] = {nullptr, nullptr, nullptr};
     // single-proof sharding across GPUs: this rank's point range [lo, lo + cnt) of each query,
     // in the order a, b1, l, h, b2 (extras +-delta included); unsharded = the full ranges
     uint32_t shard_index = 0, shard_count = 1;
@@ -160,6 +164,9 @@ struct lzkp_pk {
     ~lzkp_pk() {
         for (auto &m : marks) { cudaEventDestroy(m.a); cudaEventDestroy(m.b); }
         for (MsmBases *b : {L_a, L_b1, L_b2, L_l, L_h}) if (b) msm_bases_free(b);
+        for (auto s_ : L_st) if (s_) cudaStreamDestroy(s_);
+        if (L_ev_in) cudaEventDestroy(L_ev_in);
+        for (auto ev : L_ev_done) if (ev) cudaEventDestroy(ev);
         if (ev_fork) cudaEventDestroy(ev_fork);
         for (auto ev : ev_join) if (ev) cudaEventDestroy(ev);
         if (stream2) cudaStreamDestroy(stream2);
@@ -324,6 +331,9 @@ static int pk_load_impl(const uint8_t *bytes, size_t len, int validate, const lz
             v.push_back(delta_g2);
             TRY(msm_bases_load(2, reinterpret_cast<const uint8_t *>(v.data() + pk->L_lo[4]), pk->L_cnt[4], wb, 1, validate, &pk->L_b2, 1));
         }
+        for (auto &s_ : pk->L_st) CUDA_TRY(cudaStreamCreateWithFlags(&s_, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&pk->L_ev_in, cudaEventDisableTiming));
+        for (auto &ev : pk->L_ev_done) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         pk->c = wb ? wb : 16;
         pk->W = (255 + pk->c - 1) / pk->c;
         pk->max_chunk = 1;
@@ -608,7 +618,6 @@ static int run_witness_map(lzkp_pk *pk, Workspace &ws, uint32_t P, cudaStream_t 
 static int run_prove(lzkp_pk *pk, Workspace &ws, uint32_t P, const Fr *d_r, const Fr *d_s, uint8_t *d_proofs,
                      int32_t *d_status, cudaStream_t st, bool have_h = false) {
     if (pk->large) {
-        if (!have_h) TRY(run_witness_map(pk, ws, P, st));
         if (P != 1) return fail(LZKP_E_STATE, "large-domain proving runs one proof per pass");
         const uint32_t nv = pk->n_vars, ni = pk->n_inst, nw = pk->n_wit;
         const uint8_t *z = ws.z.as<uint8_t>();
@@ -627,16 +636,24 @@ static int run_prove(lzkp_pk *pk, Workspace &ws, uint32_t P, const Fr *d_r, cons
         CUDA_TRY(cudaMemcpyAsync(sl + (size_t)nw * 32, ws.rs.p, 32, dd, st));
         G1XYZZ *res1 = ws.res1.as<G1XYZZ>();
         const uint32_t *lo = pk->L_lo, *cnt = pk->L_cnt;
+        // fork: the z-only MSMs (a, l | b1 | b2) on three side streams; this stream runs the witness map, then h
+        CUDA_TRY(cudaEventRecord(pk->L_ev_in, st));
+        for (auto s_ : pk->L_st) CUDA_TRY(cudaStreamWaitEvent(s_, pk->L_ev_in, 0));
         {
-            Region reg(pk, LZKP_REGION_MSM_G1, st);
-            TRY(msm_device_raw(pk->L_a, sa + (size_t)lo[0] * 32, cnt[0], res1 + 0, st));
-            TRY(msm_device_raw(pk->L_b1, sb + (size_t)lo[1] * 32, cnt[1], res1 + 1, st));
-            TRY(msm_device_raw(pk->L_l, sl + (size_t)lo[2] * 32, cnt[2], res1 + 2, st));
-            TRY(msm_device_raw(pk->L_h, ws.h.as<uint8_t>() + (size_t)lo[3] * 32, cnt[3], res1 + 3, st));
+            Region reg(pk, LZKP_REGION_MSM_G1, pk->L_st[0]);
+            TRY(msm_device_raw(pk->L_a, sa + (size_t)lo[0] * 32, cnt[0], res1 + 0, pk->L_st[0]));
+            TRY(msm_device_raw(pk->L_l, sl + (size_t)lo[2] * 32, cnt[2], res1 + 2, pk->L_st[0]));
         }
+        TRY(msm_device_raw(pk->L_b1, sb + (size_t)lo[1] * 32, cnt[1], res1 + 1, pk->L_st[1]));
         {
-            Region reg(pk, LZKP_REGION_MSM_G2, st);
-            TRY(msm_device_raw(pk->L_b2, sb + (size_t)lo[4] * 32, cnt[4], ws.res2.p, st));
+            Region reg(pk, LZKP_REGION_MSM_G2, pk->L_st[2]);
+            TRY(msm_device_raw(pk->L_b2, sb + (size_t)lo[4] * 32, cnt[4], ws.res2.p, pk->L_st[2]));
+        }
+        if (!have_h) TRY(run_witness_map(pk, ws, P, st));
+        TRY(msm_device_raw(pk->L_h, ws.h.as<uint8_t>() + (size_t)lo[3] * 32, cnt[3], res1 + 3, st));
+        for (int i = 0; i < 3; i++) {
+            CUDA_TRY(cudaEventRecord(pk->L_ev_done[i], pk->L_st[i]));
+            CUDA_TRY(cudaStreamWaitEvent(st, pk->L_ev_done[i], 0));
         }
         if (!d_proofs) return LZKP_OK;           // partial sums only (sharded proving): the caller combines
         Region reg(pk, LZKP_REGION_ASSEMBLE, st);
