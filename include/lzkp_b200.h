@@ -161,12 +161,14 @@ int lzkp_witness_map(lzkp_pk *pk, size_t n_proofs, const uint8_t *z, uint8_t *h_
 
 /* Device-resident pieces of ONE large-domain proof, for splitting it across GPUs (one process per GPU):
  *   lzkp_witness_map_device    z -> h on the rank that holds the circuit (then broadcast h, e.g. ncclBroadcast)
- *   lzkp_prove_partial_device  every rank: the five MSMs over ITS point ranges -> LZKP_PARTIAL_BYTES
+ *   lzkp_prove_partial_device  every rank: the five MSMs over ITS point ranges -> LZKP_PARTIAL_BYTES.  phase 1 starts
+ *                              the MSMs that only need z (so they run while rank 0 computes h), phase 2 adds the
+ *                              H MSM and writes the partial sums; phase 0 or 3 = both in one call
  *   lzkp_prove_combine_device  one rank: add the gathered partial sums, assemble and serialize the proof
  * All pointers are device pointers; calls are asynchronous on `stream`. */
 int lzkp_witness_map_device(lzkp_pk *pk, const void *d_z, void *d_h, void *stream);
 int lzkp_prove_partial_device(lzkp_pk *pk, const void *d_z, const void *d_r, const void *d_s, const void *d_h,
-                              void *d_partial, void *d_status, void *stream);
+                              void *d_partial, void *d_status, void *stream, int phase);
 int lzkp_prove_combine_device(lzkp_pk *pk, const void *d_partials, int n_partials, const void *d_r, const void *d_s,
                               void *d_proof, void *stream);
 

@@ -58,7 +58,7 @@ SIGNATURES = {
     "lzkp_prove_equality_batch_device": (_int, [_vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lzkp_witness_map": (_int, [_vp, _sz, _vp, _vp]),
     "lzkp_witness_map_device": (_int, [_vp, _vp, _vp, _vp]),
-    "lzkp_prove_partial_device": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lzkp_prove_partial_device": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int]),
     "lzkp_prove_combine_device": (_int, [_vp, _vp, _int, _vp, _vp, _vp, _vp]),
     "lzkp_msm_g1": (_int, [_vp, _vp, _sz, _vp]),
     "lzkp_msm_g2": (_int, [_vp, _vp, _sz, _vp]),

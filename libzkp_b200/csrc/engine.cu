@@ -301,7 +301,16 @@ static int pk_load_impl(const uint8_t *bytes, size_t len, int validate, const lz
         const uint64_t sizes[5] = {nv, nv, (uint64_t)pk->n_wit + 1, (uint64_t)n - 1, nv}, wts[5] = {10, 10, 10, 10, 28};
         uint64_t wtot = 0;
         for (int q = 0; q < 5; q++) wtot += sizes[q] * wts[q];
-        const uint64_t w_lo = wtot * pk->shard_index / pk->shard_count, w_hi = wtot * (pk->shard_index + 1) / pk->shard_count;
+        // rank 0 also runs the witness map (and the final assembly), so it takes a smaller slice: measured at 2^20,
+        // the map costs ~8.5 % of one GPU's MSM time, i.e. a share of (1 - 0.085 G) relative to the other ranks
+        const uint32_t G_ = pk->shard_count;
+        const double rho = G_ > 1 ? std::max(0.1, 1.0 - 0.085 * G_) : 1.0, denom = rho + (G_ - 1);
+        auto cut = [&](uint32_t i) -> uint64_t {      // weighted start of shard i
+            if (i == 0) return 0;
+            if (i >= G_) return wtot;
+            return (uint64_t)((rho + (i - 1)) / denom * (double)wtot);
+        };
+        const uint64_t w_lo = cut(pk->shard_index), w_hi = cut(pk->shard_index + 1);
         uint64_t acc_w = 0;
         for (int q = 0; q < 5; q++) {
             // points of query q whose weighted start lies in [w_lo, w_hi)
@@ -615,13 +624,18 @@ static int run_witness_map(lzkp_pk *pk, Workspace &ws, uint32_t P, cudaStream_t 
 }
 
 // From ws_z, r, s (device, canonical) to proofs (device).  status must be initialised by the caller.
+// phase (large mode, sharded proving): 1 = inputs + the z-only MSMs on the side streams, 2 = the H MSM + join,
+// 3 = both (default).
 static int run_prove(lzkp_pk *pk, Workspace &ws, uint32_t P, const Fr *d_r, const Fr *d_s, uint8_t *d_proofs,
-                     int32_t *d_status, cudaStream_t st, bool have_h = false) {
+                     int32_t *d_status, cudaStream_t st, bool have_h = false, int phase = 3) {
     if (pk->large) {
         if (P != 1) return fail(LZKP_E_STATE, "large-domain proving runs one proof per pass");
         const uint32_t nv = pk->n_vars, ni = pk->n_inst, nw = pk->n_wit;
         const uint8_t *z = ws.z.as<uint8_t>();
         uint8_t *sa = pk->L_sa.as<uint8_t>(), *sb = pk->L_sb.as<uint8_t>(), *sl = pk->L_sl.as<uint8_t>();
+        G1XYZZ *res1 = ws.res1.as<G1XYZZ>();
+        const uint32_t *lo = pk->L_lo, *cnt = pk->L_cnt;
+        if (phase & 1) {
         LAUNCH(k_fr_mul_canonical, 1, 128, 0, st, d_r, d_s, ws.rs.as<Fr>(), 1u);
         LAUNCH(k_check_canonical, (nv + 127) / 128, 128, 0, st, ws.z.as<Fr>(), nv, d_status);
         LAUNCH(k_check_canonical, 1, 32, 0, st, d_r, 1u, d_status);
@@ -634,8 +648,6 @@ static int run_prove(lzkp_pk *pk, Workspace &ws, uint32_t P, const Fr *d_r, cons
         CUDA_TRY(cudaMemcpyAsync(sb + (size_t)(nv - 1) * 32, d_s, 32, dd, st));
         CUDA_TRY(cudaMemcpyAsync(sl, z + (size_t)ni * 32, (size_t)nw * 32, dd, st));
         CUDA_TRY(cudaMemcpyAsync(sl + (size_t)nw * 32, ws.rs.p, 32, dd, st));
-        G1XYZZ *res1 = ws.res1.as<G1XYZZ>();
-        const uint32_t *lo = pk->L_lo, *cnt = pk->L_cnt;
         // fork: the z-only MSMs (a, l | b1 | b2) on three side streams; this stream runs the witness map, then h
         CUDA_TRY(cudaEventRecord(pk->L_ev_in, st));
         for (auto s_ : pk->L_st) CUDA_TRY(cudaStreamWaitEvent(s_, pk->L_ev_in, 0));
@@ -649,6 +661,8 @@ static int run_prove(lzkp_pk *pk, Workspace &ws, uint32_t P, const Fr *d_r, cons
             Region reg(pk, LZKP_REGION_MSM_G2, pk->L_st[2]);
             TRY(msm_device_raw(pk->L_b2, sb + (size_t)lo[4] * 32, cnt[4], ws.res2.p, pk->L_st[2]));
         }
+        }
+        if (!(phase & 2)) return LZKP_OK;
         if (!have_h) TRY(run_witness_map(pk, ws, P, st));
         TRY(msm_device_raw(pk->L_h, ws.h.as<uint8_t>() + (size_t)lo[3] * 32, cnt[3], res1 + 3, st));
         for (int i = 0; i < 3; i++) {
@@ -1124,18 +1138,23 @@ int lzkp_witness_map_device(lzkp_pk *pk, const void *d_z, void *d_h, void *strea
 }
 
 int lzkp_prove_partial_device(lzkp_pk *pk, const void *d_z, const void *d_r, const void *d_s, const void *d_h,
-                              void *d_partial, void *d_status, void *stream) {
-    if (!pk || !d_z || !d_r || !d_s || !d_h || !d_partial || !d_status) return fail(LZKP_E_INVALID, "null argument");
+                              void *d_partial, void *d_status, void *stream, int phase) {
+    if (phase == 0) phase = 3;
+    if (!pk || !d_r || !d_s || !d_status || ((phase & 1) && !d_z) || ((phase & 2) && (!d_h || !d_partial)))
+        return fail(LZKP_E_INVALID, "null argument");
     TRY(ensure_device());
     std::lock_guard<std::mutex> lk(pk->mu);
     if (!pk->large) return fail(LZKP_E_STATE, "sharded proving needs a large-domain proving key");
     cudaStream_t st = (cudaStream_t)stream;
     Workspace &ws = pk->ws[0];
     TRY(ensure_workspace(pk, ws, 1));
-    CUDA_TRY(cudaMemsetAsync(d_status, 0, 4, st));
-    CUDA_TRY(cudaMemcpyAsync(ws.z.p, d_z, (size_t)pk->n_vars * 32, cudaMemcpyDeviceToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(ws.h.p, d_h, (size_t)pk->n * 32, cudaMemcpyDeviceToDevice, st));
-    TRY(run_prove(pk, ws, 1, (const Fr *)d_r, (const Fr *)d_s, nullptr, (int32_t *)d_status, st, true));
+    if (phase & 1) {
+        CUDA_TRY(cudaMemsetAsync(d_status, 0, 4, st));
+        CUDA_TRY(cudaMemcpyAsync(ws.z.p, d_z, (size_t)pk->n_vars * 32, cudaMemcpyDeviceToDevice, st));
+    }
+    if (phase & 2) CUDA_TRY(cudaMemcpyAsync(ws.h.p, d_h, (size_t)pk->n * 32, cudaMemcpyDeviceToDevice, st));
+    TRY(run_prove(pk, ws, 1, (const Fr *)d_r, (const Fr *)d_s, nullptr, (int32_t *)d_status, st, true, phase));
+    if (!(phase & 2)) return LZKP_OK;
     uint8_t *out = (uint8_t *)d_partial;
     CUDA_TRY(cudaMemcpyAsync(out, ws.res1.p, 4 * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(out + 4 * sizeof(G1XYZZ), ws.res2.p, sizeof(G2XYZZ), cudaMemcpyDeviceToDevice, st));

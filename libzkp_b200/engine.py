@@ -191,8 +191,8 @@ class ProvingKey:
         check(lib().lzkp_witness_map_device(self._h, d_z, d_h, stream))
 
     def prove_partial_device(self, d_z: int, d_r: int, d_s: int, d_h: int, d_partial: int, d_status: int,
-                             stream: int = 0) -> None:
-        check(lib().lzkp_prove_partial_device(self._h, d_z, d_r, d_s, d_h, d_partial, d_status, stream))
+                             stream: int = 0, phase: int = 3) -> None:
+        check(lib().lzkp_prove_partial_device(self._h, d_z, d_r, d_s, d_h, d_partial, d_status, stream, phase))
 
     def prove_combine_device(self, d_partials: int, n_partials: int, d_r: int, d_s: int, d_proof: int,
                              stream: int = 0) -> None:

@@ -4,8 +4,9 @@ One process per GPU.  Every rank keeps only ITS cost-weighted point ranges of th
 queries (a, b1, l, h in G1; b2 in G2, ~2.8x per point) resident in HBM.  Per proof:
 
   1. rank 0 holds the assignment z and r, s; they are broadcast (NCCL over NVLink, 32 B x n_vars);
-  2. rank 0 runs the witness map (7 tiled NTTs - not worth distributing below ~2^24) and broadcasts h;
-  3. every rank runs its slice of the five MSMs -> 768 B of partial sums;
+  2. every rank starts the MSM slices that only need z, while rank 0 runs the witness map (7 tiled NTTs - not
+     worth distributing below ~2^24; rank 0 holds a smaller slice in exchange) and broadcasts h;
+  3. every rank adds its slice of the H MSM -> 768 B of partial sums;
   4. the partial sums are gathered on rank 0, which adds them, assembles and serializes the proof.
 
 The only data-path collectives are the two broadcasts and one 768-byte-per-rank gather.
@@ -48,14 +49,19 @@ class ShardedProver:
         if self.rank == 0 and not resident:
             self.z.copy_(torch.from_numpy(np.ascontiguousarray(z, np.uint8).reshape(self.n_vars, 32)), non_blocking=True)
             self.rs.copy_(torch.from_numpy(np.frombuffer(bytes(r) + bytes(s), np.uint8).reshape(2, 32).copy()))
-        if self.rank == 0:
-            self.pk.witness_map_device(self.z.data_ptr(), self.h.data_ptr(), st)
         if self.world > 1:
             dist.broadcast(self.z, 0)
             dist.broadcast(self.rs, 0)
+        # phase 1: the MSMs that only need z start on the engine's side streams on every rank ...
+        self.pk.prove_partial_device(self.z.data_ptr(), self.rs[0].data_ptr(), self.rs[1].data_ptr(), 0, 0,
+                                     self.status.data_ptr(), st, phase=1)
+        # ... while rank 0 runs the witness map and h travels to the ranks that hold h_query ranges
+        if self.rank == 0:
+            self.pk.witness_map_device(self.z.data_ptr(), self.h.data_ptr(), st)
+        if self.world > 1:
             dist.broadcast(self.h, 0)
-        self.pk.prove_partial_device(self.z.data_ptr(), self.rs[0].data_ptr(), self.rs[1].data_ptr(), self.h.data_ptr(),
-                                     self.partial.data_ptr(), self.status.data_ptr(), st)
+        self.pk.prove_partial_device(0, self.rs[0].data_ptr(), self.rs[1].data_ptr(), self.h.data_ptr(),
+                                     self.partial.data_ptr(), self.status.data_ptr(), st, phase=2)
         if self.world > 1:
             dist.all_gather_into_tensor(self.partials.view(-1), self.partial)
             dist.all_reduce(self.status, op=dist.ReduceOp.MAX)

@@ -120,8 +120,13 @@ def test_sharded_single_proof_partials_combine(force_large, co, trapdoor, frs, s
     partials = torch.zeros((shards, 768), dtype=torch.uint8, device=dev)
     status = torch.zeros(shards, dtype=torch.int32, device=dev)
     for i, pk in enumerate(pks):
-        pk.prove_partial_device(d_z.data_ptr(), d_r.data_ptr(), d_s.data_ptr(), d_h.data_ptr(), partials[i].data_ptr(),
-                                status[i:].data_ptr())
+        if i % 2:                                            # two-phase form: z-only MSMs first, H MSM once h is there
+            pk.prove_partial_device(d_z.data_ptr(), d_r.data_ptr(), d_s.data_ptr(), 0, 0, status[i:].data_ptr(), phase=1)
+            pk.prove_partial_device(0, d_r.data_ptr(), d_s.data_ptr(), d_h.data_ptr(), partials[i].data_ptr(),
+                                    status[i:].data_ptr(), phase=2)
+        else:
+            pk.prove_partial_device(d_z.data_ptr(), d_r.data_ptr(), d_s.data_ptr(), d_h.data_ptr(),
+                                    partials[i].data_ptr(), status[i:].data_ptr())
     proof = torch.zeros(256, dtype=torch.uint8, device=dev)
     pks[0].prove_combine_device(partials.data_ptr(), shards, d_r.data_ptr(), d_s.data_ptr(), proof.data_ptr())
     torch.cuda.synchronize()
