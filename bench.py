@@ -330,8 +330,17 @@ def run_ours(args, rank, world, local_rank):
 
     extra = {}
     if world == 1 and not args.no_extra:
+        lat = {}
+        for nb in (1, 8, 64, 512):                  # BASELINE.json configs[0]: latency of small calls, host buffers
+            for _ in range(3):
+                pk.prove_equality_batch(a_p[:nb], a_p[:nb], r_p[:nb], s_p[:nb])
+            t0 = time.perf_counter()
+            for _ in range(10):
+                pk.prove_equality_batch(a_p[:nb], a_p[:nb], r_p[:nb], s_p[:nb])
+            lat[str(nb)] = round(1e2 * (time.perf_counter() - t0), 3)
         pk.close()                                  # free the 60 GB of tables before the other workloads load theirs
         extra = bench_transforms(engine, torch, dev, args)
+        extra["latency_ms_by_batch_size"] = lat
         extra["api_process_batch"] = bench_python_api(pk_bytes, P)
 
     out = {
