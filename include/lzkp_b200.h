@@ -150,6 +150,17 @@ int lzkp_prove_membership_batch(lzkp_pk *pk, size_t n_proofs, const uint64_t *va
                                 const uint32_t *set_len, uint32_t set_stride, const uint8_t *commitments,
                                 const uint8_t *r, const uint8_t *s, uint8_t *proofs_out, uint8_t *commitments_out,
                                 int32_t *status);
+/* The same batches with libzkp's proof envelope written on the device, so the host shim does no
+ * per-proof framing: Proof::to_bytes of src/proof/mod.rs:23-36 around the MiMC commitment computed on the device.
+ *   equality   (equality_proof.rs:30-31, scheme 2): 298 B each, envelopes_out is n x 298
+ *   membership (set_membership.rs:29-37, scheme 4): 10 + 4 + 8 * set_len + 256 + 32 B, rows envelope_stride apart
+ * envelope_len[i] = bytes written, 0 for a failed proof (status[i] != 0). */
+int lzkp_prove_equality_enveloped(lzkp_pk *pk, size_t n_proofs, const uint64_t *a, const uint64_t *b, const uint8_t *r,
+                                  const uint8_t *s, uint8_t *envelopes_out, uint32_t *envelope_len, int32_t *status);
+int lzkp_prove_membership_enveloped(lzkp_pk *pk, size_t n_proofs, const uint64_t *value, const uint64_t *sets,
+                                    const uint32_t *set_len, uint32_t set_stride, const uint8_t *r, const uint8_t *s,
+                                    uint8_t *envelopes_out, uint32_t envelope_stride, uint32_t *envelope_len,
+                                    int32_t *status);
 /* Same as lzkp_prove_equality_batch with every buffer already in device memory (a, b: u64[n];
  * r, s: n x 32 B; proofs: n x 256 B; status: int32[n]) on CUDA stream `stream` (cudaStream_t or NULL).
  * Asynchronous: returns after enqueueing. */

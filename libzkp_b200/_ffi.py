@@ -55,6 +55,8 @@ SIGNATURES = {
     "lzkp_builtin_witness": (_int, [_int, _u32, _u64, _u64, _vp, _u32, _vp, _vp, _sz]),
     "lzkp_prove_equality_batch": (_int, [_vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lzkp_prove_membership_batch": (_int, [_vp, _sz, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lzkp_prove_equality_enveloped": (_int, [_vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lzkp_prove_membership_enveloped": (_int, [_vp, _sz, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _u32, _vp, _vp]),
     "lzkp_prove_equality_batch_device": (_int, [_vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lzkp_witness_map": (_int, [_vp, _sz, _vp, _vp]),
     "lzkp_witness_map_device": (_int, [_vp, _vp, _vp, _vp]),

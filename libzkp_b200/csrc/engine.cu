@@ -114,8 +114,8 @@ struct HBuf {
 // run under the MSM kernels of the other.
 struct Workspace {
     uint32_t chunk = 0;            // proofs the buffers are sized for
-    DBuf z, abc, tmp, h, dig, r, s, rs, part1, part2, res1, res2, proofs, status, a, b, commit, sets, setlen;
-    HBuf h_proofs, h_status, h_commit;
+    DBuf z, abc, tmp, h, dig, r, s, rs, part1, part2, res1, res2, proofs, status, a, b, commit, sets, setlen, env, envlen;
+    HBuf h_proofs, h_status, h_commit, h_env, h_envlen;
 };
 
 // pk->stream is a BLOCKING stream on purpose: setup-time uploads use synchronous cudaMemcpy from pageable
@@ -749,7 +749,12 @@ static uint32_t chunk_size(const lzkp_pk *pk, size_t n) {
     }
     return c;
 }
-struct HostOut { uint8_t *proofs; int32_t *status; uint8_t *commit; };
+struct HostOut {
+    uint8_t *proofs; int32_t *status; uint8_t *commit;
+    // libzkp envelopes instead of bare proofs (proofs == nullptr): scheme id, per-proof stride, lengths out
+    uint8_t *env = nullptr; uint32_t *env_len = nullptr; uint32_t env_stride = 0, scheme = 0; bool with_sets = false;
+    uint32_t set_stride = 0;
+};
 // Host-buffer batch: `prep(ws, off, P, st)` enqueues the chunk's input copies and witness generation.
 template <class Prep>
 static int run_batch_host(lzkp_pk *pk, size_t n, const uint8_t *r, const uint8_t *s, HostOut out, Prep prep) {
@@ -761,7 +766,11 @@ static int run_batch_host(lzkp_pk *pk, size_t n, const uint8_t *r, const uint8_t
         for (auto it = pend.begin(); it != pend.end();) {
             if (it->w != w) { ++it; continue; }
             Workspace &ws = pk->ws[w];
-            memcpy(out.proofs + it->off * 256, ws.h_proofs.p, (size_t)it->P * 256);
+            if (out.proofs) memcpy(out.proofs + it->off * 256, ws.h_proofs.p, (size_t)it->P * 256);
+            if (out.env) {
+                memcpy(out.env + it->off * out.env_stride, ws.h_env.p, (size_t)it->P * out.env_stride);
+                memcpy(out.env_len + it->off, ws.h_envlen.p, (size_t)it->P * 4);
+            }
             memcpy(out.status + it->off, ws.h_status.p, (size_t)it->P * 4);
             if (out.commit) memcpy(out.commit + it->off * 32, ws.h_commit.p, (size_t)it->P * 32);
             it = pend.erase(it);
@@ -783,7 +792,16 @@ static int run_batch_host(lzkp_pk *pk, size_t n, const uint8_t *r, const uint8_t
         CUDA_TRY(cudaMemsetAsync(ws.status.p, 0, (size_t)P * 4, st));
         TRY(prep(ws, off, P, st));
         TRY(run_prove(pk, ws, P, ws.r.as<Fr>(), ws.s.as<Fr>(), ws.proofs.as<uint8_t>(), ws.status.as<int32_t>(), st));
-        CUDA_TRY(cudaMemcpyAsync(ws.h_proofs.p, ws.proofs.p, (size_t)P * 256, cudaMemcpyDeviceToHost, st));
+        if (out.proofs) CUDA_TRY(cudaMemcpyAsync(ws.h_proofs.p, ws.proofs.p, (size_t)P * 256, cudaMemcpyDeviceToHost, st));
+        if (out.env) {
+            TRY(ws.env.ensure((size_t)ws.chunk * out.env_stride)); TRY(ws.envlen.ensure((size_t)ws.chunk * 4));
+            TRY(ws.h_env.ensure((size_t)ws.chunk * out.env_stride)); TRY(ws.h_envlen.ensure((size_t)ws.chunk * 4));
+            LAUNCH(k_envelope, (P * 32 + 127) / 128, 128, 0, st, ws.proofs.as<uint8_t>(), ws.commit.as<uint8_t>(),
+                   ws.status.as<int32_t>(), out.with_sets ? ws.sets.as<uint64_t>() : nullptr, ws.setlen.as<uint32_t>(),
+                   out.set_stride, out.scheme, P, ws.env.as<uint8_t>(), out.env_stride, ws.envlen.as<uint32_t>());
+            CUDA_TRY(cudaMemcpyAsync(ws.h_env.p, ws.env.p, (size_t)P * out.env_stride, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(ws.h_envlen.p, ws.envlen.p, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
+        }
         CUDA_TRY(cudaMemcpyAsync(ws.h_status.p, ws.status.p, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
         if (out.commit) CUDA_TRY(cudaMemcpyAsync(ws.h_commit.p, ws.commit.p, (size_t)P * 32, cudaMemcpyDeviceToHost, st));
         pend.push_back({off, P, w});
@@ -791,7 +809,7 @@ static int run_batch_host(lzkp_pk *pk, size_t n, const uint8_t *r, const uint8_t
     TRY(drain(0));
     TRY(drain(1));
     CUDA_TRY(cudaGetLastError());
-    blank_failed(n, out.status, out.proofs);
+    if (out.proofs) blank_failed(n, out.status, out.proofs);
     return LZKP_OK;
 }
 // Device-buffer batch on the caller's stream: fork to the two engine streams, join back.
@@ -1043,14 +1061,13 @@ int lzkp_builtin_witness(int kind, uint32_t param, uint64_t value, uint64_t othe
     return LZKP_OK;
 }
 
-int lzkp_prove_equality_batch(lzkp_pk *pk, size_t n_proofs, const uint64_t *a, const uint64_t *b,
-                              const uint8_t *commitments, const uint8_t *r, const uint8_t *s, uint8_t *proofs_out,
-                              uint8_t *commitments_out, int32_t *status) {
-    if (!pk || (n_proofs && (!a || !b || !r || !s || !proofs_out || !status))) return fail(LZKP_E_INVALID, "null argument");
+static int equality_batch_impl(lzkp_pk *pk, size_t n_proofs, const uint64_t *a, const uint64_t *b,
+                               const uint8_t *commitments, const uint8_t *r, const uint8_t *s, HostOut out) {
+    if (!pk || (n_proofs && (!a || !b || !r || !s || !out.status || (!out.proofs && !out.env)))) return fail(LZKP_E_INVALID, "null argument");
     TRY(ensure_device());
     std::lock_guard<std::mutex> lk(pk->mu);
     if (!pk->has_circuit || pk->kind != LZKP_CIRCUIT_EQUALITY) return fail(LZKP_E_STATE, "pk is not bound to the builtin equality circuit");
-    return run_batch_host(pk, n_proofs, r, s, HostOut{proofs_out, status, commitments_out},
+    return run_batch_host(pk, n_proofs, r, s, out,
                           [&](Workspace &ws, size_t off, uint32_t P, cudaStream_t st) -> int {
         CUDA_TRY(cudaMemcpyAsync(ws.a.p, a + off, (size_t)P * 8, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(ws.b.p, b + off, (size_t)P * 8, cudaMemcpyHostToDevice, st));
@@ -1063,16 +1080,30 @@ int lzkp_prove_equality_batch(lzkp_pk *pk, size_t n_proofs, const uint64_t *a, c
     });
 }
 
-int lzkp_prove_membership_batch(lzkp_pk *pk, size_t n_proofs, const uint64_t *value, const uint64_t *sets,
-                                const uint32_t *set_len, uint32_t set_stride, const uint8_t *commitments,
-                                const uint8_t *r, const uint8_t *s, uint8_t *proofs_out, uint8_t *commitments_out,
-                                int32_t *status) {
-    if (!pk || (n_proofs && (!value || !sets || !set_len || !r || !s || !proofs_out || !status)))
+int lzkp_prove_equality_batch(lzkp_pk *pk, size_t n_proofs, const uint64_t *a, const uint64_t *b,
+                              const uint8_t *commitments, const uint8_t *r, const uint8_t *s, uint8_t *proofs_out,
+                              uint8_t *commitments_out, int32_t *status) {
+    if (n_proofs && !proofs_out) return fail(LZKP_E_INVALID, "null argument");
+    HostOut out{proofs_out, status, commitments_out};
+    return equality_batch_impl(pk, n_proofs, a, b, commitments, r, s, out);
+}
+int lzkp_prove_equality_enveloped(lzkp_pk *pk, size_t n_proofs, const uint64_t *a, const uint64_t *b, const uint8_t *r,
+                                  const uint8_t *s, uint8_t *envelopes_out, uint32_t *envelope_len, int32_t *status) {
+    if (n_proofs && (!envelopes_out || !envelope_len)) return fail(LZKP_E_INVALID, "null argument");
+    HostOut out{nullptr, status, nullptr};
+    out.env = envelopes_out; out.env_len = envelope_len; out.env_stride = 298; out.scheme = 2;
+    return equality_batch_impl(pk, n_proofs, a, b, nullptr, r, s, out);
+}
+
+static int membership_batch_impl(lzkp_pk *pk, size_t n_proofs, const uint64_t *value, const uint64_t *sets,
+                                 const uint32_t *set_len, uint32_t set_stride, const uint8_t *commitments,
+                                 const uint8_t *r, const uint8_t *s, HostOut out) {
+    if (!pk || (n_proofs && (!value || !sets || !set_len || !r || !s || !out.status || (!out.proofs && !out.env))))
         return fail(LZKP_E_INVALID, "null argument");
     TRY(ensure_device());
     std::lock_guard<std::mutex> lk(pk->mu);
     if (!pk->has_circuit || pk->kind != LZKP_CIRCUIT_MEMBERSHIP) return fail(LZKP_E_STATE, "pk is not bound to the builtin membership circuit");
-    return run_batch_host(pk, n_proofs, r, s, HostOut{proofs_out, status, commitments_out},
+    return run_batch_host(pk, n_proofs, r, s, out,
                           [&](Workspace &ws, size_t off, uint32_t P, cudaStream_t st) -> int {
         TRY(ws.sets.ensure((size_t)ws.chunk * set_stride * 8));
         TRY(ws.setlen.ensure((size_t)ws.chunk * 4));
@@ -1086,6 +1117,28 @@ int lzkp_prove_membership_batch(lzkp_pk *pk, size_t n_proofs, const uint64_t *va
                ws.commit.as<Fr>(), ws.status.as<int32_t>(), P, pk->kind_param, pk->n_vars);
         return LZKP_OK;
     });
+}
+
+int lzkp_prove_membership_batch(lzkp_pk *pk, size_t n_proofs, const uint64_t *value, const uint64_t *sets,
+                                const uint32_t *set_len, uint32_t set_stride, const uint8_t *commitments,
+                                const uint8_t *r, const uint8_t *s, uint8_t *proofs_out, uint8_t *commitments_out,
+                                int32_t *status) {
+    if (n_proofs && !proofs_out) return fail(LZKP_E_INVALID, "null argument");
+    HostOut out{proofs_out, status, commitments_out};
+    return membership_batch_impl(pk, n_proofs, value, sets, set_len, set_stride, commitments, r, s, out);
+}
+int lzkp_prove_membership_enveloped(lzkp_pk *pk, size_t n_proofs, const uint64_t *value, const uint64_t *sets,
+                                    const uint32_t *set_len, uint32_t set_stride, const uint8_t *r, const uint8_t *s,
+                                    uint8_t *envelopes_out, uint32_t envelope_stride, uint32_t *envelope_len,
+                                    int32_t *status) {
+    if (n_proofs && (!envelopes_out || !envelope_len)) return fail(LZKP_E_INVALID, "null argument");
+    if (!pk) return fail(LZKP_E_INVALID, "null argument");
+    if (envelope_stride < 10 + 4 + 8 * pk->kind_param + 256 + 32 && pk->kind == LZKP_CIRCUIT_MEMBERSHIP)
+        return fail(LZKP_E_INVALID, "envelope_stride below 302 + 8 * set slots");
+    HostOut out{nullptr, status, nullptr};
+    out.env = envelopes_out; out.env_len = envelope_len; out.env_stride = envelope_stride; out.scheme = 4;
+    out.with_sets = true; out.set_stride = set_stride;
+    return membership_batch_impl(pk, n_proofs, value, sets, set_len, set_stride, nullptr, r, s, out);
 }
 
 int lzkp_prove_equality_batch_device(lzkp_pk *pk, size_t n_proofs, const void *d_a, const void *d_b, const void *d_r,

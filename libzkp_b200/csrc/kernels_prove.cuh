@@ -387,6 +387,37 @@ __global__ void __launch_bounds__(192) k_assemble(const G1XYZZ *g1, const G2XYZZ
     }
 }
 
+// ---------------------------------------------------------------- libzkp envelopes
+// Proof::to_bytes (src/proof/mod.rs:23-36): [version = 2][scheme][proof_len u32 LE][comm_len u32 LE][proof][commitment].
+// Equality (scheme 2, equality_proof.rs:30-31): proof = the 256 Groth16 bytes -> 298 B per proof.
+// Membership (scheme 4, set_membership.rs:29-37): proof = u32 len || u64[len] set || 256 Groth16 bytes.
+// One warp per proof copies the pieces; failed proofs (status != 0) get out_len = 0.
+__global__ void __launch_bounds__(128) k_envelope(const uint8_t *proofs, const uint8_t *commit, const int32_t *status,
+                                                  const uint64_t *sets, const uint32_t *set_len, uint32_t set_stride,
+                                                  uint32_t scheme, uint32_t P, uint8_t *out, uint32_t out_stride,
+                                                  uint32_t *out_len) {
+    const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (p >= P) return;
+    uint8_t *o = out + (size_t)p * out_stride;
+    if (status[p] != 0) {
+        if (lane == 0) out_len[p] = 0;
+        return;
+    }
+    const uint32_t len = sets ? set_len[p] : 0, prefix = sets ? 4 + 8 * len : 0, payload = prefix + 256;
+    if (lane == 0) {
+        o[0] = 2; o[1] = (uint8_t)scheme;
+        for (int i = 0; i < 4; i++) { o[2 + i] = (uint8_t)(payload >> (8 * i)); o[6 + i] = (uint8_t)(32u >> (8 * i)); }
+        if (sets) for (int i = 0; i < 4; i++) o[10 + i] = (uint8_t)(len >> (8 * i));
+        out_len[p] = 10 + payload + 32;
+    }
+    if (sets) {
+        const uint8_t *sv = reinterpret_cast<const uint8_t *>(sets + (size_t)p * set_stride);
+        for (uint32_t i = lane; i < 8 * len; i += 32) o[14 + i] = sv[i];
+    }
+    for (uint32_t i = lane; i < 256; i += 32) o[10 + prefix + i] = proofs[(size_t)p * 256 + i];
+    o[10 + payload + lane] = commit[(size_t)p * 32 + lane];
+}
+
 // Sharded single proof: partial[i] = 4 G1 XYZZ sums (a, b1, l, h) then 1 G2 XYZZ sum (b2) of rank i's point ranges.
 // Thread q < 4 adds up slot q over the ranks, thread 4 the G2 slot.
 constexpr uint32_t kPartialBytes = 4 * sizeof(G1XYZZ) + sizeof(G2XYZZ);

@@ -211,6 +211,32 @@ class ProvingKey:
                                               _p(status)))
         return proofs, cm_out, status
 
+    def prove_equality_enveloped(self, a, b, r, s):
+        """n x prove_equality's final bytes (298 B envelopes built on the device) -> (envelopes[n, 298], lengths, status)."""
+        a = np.ascontiguousarray(a, np.uint64)
+        b = np.ascontiguousarray(b, np.uint64)
+        n = a.shape[0]
+        r, s = _u8(r, 32), _u8(s, 32)
+        env = np.zeros((n, 298), np.uint8)
+        lens = np.zeros(n, np.uint32)
+        status = np.zeros(n, np.int32)
+        check(lib().lzkp_prove_equality_enveloped(self._h, n, _p(a), _p(b), _p(r), _p(s), _p(env), _p(lens), _p(status)))
+        return env, lens, status
+
+    def prove_membership_enveloped(self, value, sets, set_len, r, s):
+        value = np.ascontiguousarray(value, np.uint64)
+        sets = np.ascontiguousarray(sets, np.uint64)
+        set_len = np.ascontiguousarray(set_len, np.uint32)
+        n, stride = value.shape[0], sets.shape[1]
+        r, s = _u8(r, 32), _u8(s, 32)
+        row = 302 + 8 * stride
+        env = np.zeros((n, row), np.uint8)
+        lens = np.zeros(n, np.uint32)
+        status = np.zeros(n, np.int32)
+        check(lib().lzkp_prove_membership_enveloped(self._h, n, _p(value), _p(sets), _p(set_len), stride, _p(r), _p(s),
+                                                    _p(env), row, _p(lens), _p(status)))
+        return env, lens, status
+
     def prove_membership_batch(self, value, sets, set_len, r, s, commitments=None):
         value = np.ascontiguousarray(value, np.uint64)
         sets = np.ascontiguousarray(sets, np.uint64)

@@ -99,14 +99,16 @@ def prove_membership(value: int, set_: Sequence[int], rng=None) -> bytes:   # se
 
 
 def prove_equality_many(pairs: Sequence[Sequence[int]], rng=None) -> List[bytes]:
-    """The grouped fast path behind process_batch: same results as [prove_equality(a, b) ...], with the MiMC
-    commitments computed on the device beside the witnesses instead of one host call per proof."""
+    """The grouped fast path behind process_batch: same results as [prove_equality(a, b) ...].  Commitments,
+    proofs and the envelope framing (Proof::to_bytes) all come back from one device call."""
     for a, b in pairs:
         _check_u64(a, b)
         validate_equality_params(a, b)
-    proofs, cms = SnarkBackend.prove_equality_zk_batch([p[0] for p in pairs], [p[1] for p in pairs], None, rng,
-                                                       return_commitments=True)
-    return [_wrap_equality(p, c) for p, c in zip(proofs, cms)]
+    out = SnarkBackend.prove_equality_enveloped_batch([p[0] for p in pairs], [p[1] for p in pairs], rng)
+    for e in out:
+        if not e:
+            raise ProofGenerationFailed("SNARK proof generation failed")
+    return out
 
 
 def prove_membership_many(items: Sequence, rng=None) -> List[bytes]:
@@ -114,6 +116,8 @@ def prove_membership_many(items: Sequence, rng=None) -> List[bytes]:
         _check_u64(v, *s)
         validate_membership_params(v, s)
         validate_set_size(s, MAX_SET_SIZE)
-    proofs, cms = SnarkBackend.prove_membership_zk_batch([v for v, _ in items], [list(s) for _, s in items], None, rng,
-                                                         return_commitments=True)
-    return [_wrap_membership(p, list(s), c) for p, (_, s), c in zip(proofs, items, cms)]
+    out = SnarkBackend.prove_membership_enveloped_batch([v for v, _ in items], [list(s) for _, s in items], rng)
+    for e in out:
+        if not e:
+            raise ProofGenerationFailed("SNARK membership proof generation failed")
+    return out

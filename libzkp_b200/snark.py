@@ -283,6 +283,54 @@ class SnarkBackend:
                 cms_out[i] = cb[32 * k:32 * k + 32]
         return done()
 
+    # ---- final libzkp bytes straight from the device (envelope framing fused into the batch call)
+    @staticmethod
+    def prove_equality_enveloped_batch(a: Sequence[int], b: Sequence[int], rng=None) -> List[bytes]:
+        """[prove_equality(a_i, b_i)] as 298-byte envelopes; b"" where the reference would fail."""
+        n = len(a)
+        out: List[bytes] = [b""] * n
+        live = [i for i in range(n) if a[i] == b[i]]
+        setup = SnarkBackend.get_universal_setup() if live else None
+        if not live or not isinstance(setup, Setup):
+            return out
+        rs = _scalars(rng or OsRng(), 2 * len(live))
+        try:
+            av = np.array([a[i] for i in live], np.uint64)
+            env, lens, status = setup.pk.prove_equality_enveloped(av, av, rs[0::2], rs[1::2])
+        except Exception:                           # noqa: BLE001
+            return out
+        eb = env.tobytes()
+        for k, i in enumerate(live):
+            if status[k] == 0:
+                out[i] = eb[298 * k:298 * k + int(lens[k])]
+        return out
+
+    @staticmethod
+    def prove_membership_enveloped_batch(values: Sequence[int], sets: Sequence[Sequence[int]], rng=None) -> List[bytes]:
+        n = len(values)
+        out: List[bytes] = [b""] * n
+        live = [i for i in range(n) if 1 <= len(sets[i]) <= MAX_SET_SIZE and values[i] in sets[i]]
+        setup = SnarkBackend.get_membership_setup() if live else None
+        if not live or not isinstance(setup, Setup):
+            return out
+        rs = _scalars(rng or OsRng(), 2 * len(live))
+        sets_arr = np.zeros((len(live), MAX_SET_SIZE), np.uint64)
+        lens_in = np.zeros(len(live), np.uint32)
+        for k, i in enumerate(live):
+            lens_in[k] = len(sets[i])
+            sets_arr[k, :lens_in[k]] = np.array(sets[i], np.uint64)
+        try:
+            env, lens, status = setup.pk.prove_membership_enveloped(
+                np.array([values[i] for i in live], np.uint64), sets_arr, lens_in, rs[0::2], rs[1::2])
+        except Exception:                           # noqa: BLE001
+            return out
+        row = env.shape[1]
+        eb = env.tobytes()
+        for k, i in enumerate(live):
+            if status[k] == 0:
+                out[i] = eb[row * k:row * k + int(lens[k])]
+        return out
+
     # ---- ZkpBackend trait (src/backend/mod.rs:5-8; impl snark.rs:587-611)
     @staticmethod
     def prove(data: bytes) -> bytes:

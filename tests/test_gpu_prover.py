@@ -304,3 +304,41 @@ def test_multi_chunk_batch_matches_oracle(eq_keys, co, po, frs):
     assert np.array_equal(proofs, want)
     assert cms[n - 1].tobytes() == co.mimc_hash(int(a[n - 1]))
     pk.close()
+
+
+def test_device_envelopes_equal_host_framing(eq_pk, mb_pk, frs, po):
+    # Proof::to_bytes framing written on the device == framing built on the host from the bare proofs
+    n = 40
+    rng = po.SplitMix64(8)
+    a = np.array([rng.next_u64() for _ in range(n)], np.uint64)
+    b = a.copy()
+    b[5] ^= 1
+    r, s = frs(51, n), frs(52, n)
+    env, lens, status = eq_pk.prove_equality_enveloped(a, b, r, s)
+    proofs, cms, st2 = eq_pk.prove_equality_batch(a, b, r, s)
+    assert np.array_equal(status, st2) and status[5] == 1 and lens[5] == 0
+    for i in range(n):
+        if status[i] == 0:
+            assert lens[i] == 298
+            assert env[i].tobytes() == zk.Proof(2, proofs[i].tobytes(), cms[i].tobytes()).to_bytes()
+    m = 20
+    sets = np.zeros((m, 64), np.uint64)
+    lens_in = np.zeros(m, np.uint32)
+    vals = np.zeros(m, np.uint64)
+    for i in range(m):
+        L = 1 + (i * 7) % 64
+        lens_in[i] = L
+        sets[i, :L] = [rng.next_u64() for _ in range(L)]
+        vals[i] = sets[i, i % L]
+    vals[3] = 424242                                          # not in its set
+    r, s = frs(53, m), frs(54, m)
+    env, lens, status = mb_pk.prove_membership_enveloped(vals, sets, lens_in, r, s)
+    proofs, cms, st2 = mb_pk.prove_membership_batch(vals, sets, lens_in, r, s)
+    assert np.array_equal(status, st2) and status[3] == 2 and lens[3] == 0
+    import struct
+    for i in range(m):
+        if status[i] == 0:
+            L = int(lens_in[i])
+            payload = struct.pack("<I", L) + sets[i, :L].astype("<u8").tobytes() + proofs[i].tobytes()
+            want = zk.Proof(4, payload, cms[i].tobytes()).to_bytes()
+            assert lens[i] == len(want) and env[i, :lens[i]].tobytes() == want
