@@ -163,7 +163,8 @@ int lzkp_prove_membership_enveloped(lzkp_pk *pk, size_t n_proofs, const uint64_t
                                     int32_t *status);
 /* Same as lzkp_prove_equality_batch with every buffer already in device memory (a, b: u64[n];
  * r, s: n x 32 B; proofs: n x 256 B; status: int32[n]) on CUDA stream `stream` (cudaStream_t or NULL).
- * Asynchronous: returns after enqueueing. */
+ * Asynchronous: returns after enqueueing.  Where status[i] != 0 the 256 bytes of proof i are unspecified (the
+ * host-buffer calls zero them). */
 int lzkp_prove_equality_batch_device(lzkp_pk *pk, size_t n_proofs, const void *d_a, const void *d_b, const void *d_r,
                                      const void *d_s, void *d_proofs, void *d_status, void *stream);
 

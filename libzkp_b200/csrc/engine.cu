@@ -549,6 +549,11 @@ static int circuit_install(lzkp_pk *pk, uint32_t m, uint32_t n_inst, uint32_t n_
 // Item granularity: many more CTAs than the 148 x 3 resident ones, so the last wave of a launch is a small
 // fraction of the kernel (measured: 512-unit items left the G1 kernel at 3.4 waves = 0.87 of peak).
 static inline int item_variant(uint32_t P) { return P >= 256 ? 1 : 0; }
+// the item index is the grid's y dimension (<= 65535): very wide keys fall back to coarser items
+static inline int fit_variant(const MsmPlan &pl, int v) {
+    while (v < 2 && pl.n_items[v] > 65535u) v++;
+    return v;
+}
 // G2 runs 64-thread CTAs at 255 registers: finer items keep every SM partition supplied with warps
 static inline int item_variant_g2(uint32_t P) { return P >= 2048 ? 1 : 0; }
 static int ensure_workspace(lzkp_pk *pk, Workspace &ws, uint32_t P) {
@@ -557,8 +562,8 @@ static int ensure_workspace(lzkp_pk *pk, Workspace &ws, uint32_t P) {
     for (uint32_t q : {1u, 256u, 2048u}) {
         if (q > P) break;
         uint32_t pp = q == 1u ? std::min(P, 255u) : (q == 256u ? std::min(P, 2047u) : P);
-        part1 = std::max(part1, (size_t)pk->g1.n_items[item_variant(pp)] * pp);
-        part2 = std::max(part2, (size_t)pk->g2.n_items[item_variant_g2(pp)] * pp);
+        part1 = std::max(part1, (size_t)pk->g1.n_items[fit_variant(pk->g1, item_variant(pp))] * pp);
+        part2 = std::max(part2, (size_t)pk->g2.n_items[fit_variant(pk->g2, item_variant_g2(pp))] * pp);
     }
     const size_t nv = pk->n_vars, n = pk->n;
     TRY(ws.z.ensure(P * nv * 32));
@@ -684,18 +689,20 @@ static int run_prove(lzkp_pk *pk, Workspace &ws, uint32_t P, const Fr *d_r, cons
     {
     Region reg(pk, LZKP_REGION_DIGITS, st);
     LAUNCH(k_fr_mul_canonical, gx, 128, 0, st, d_r, d_s, ws.rs.as<Fr>(), P);
-    LAUNCH(k_digits, dim3(gx, pk->nz), 128, 0, st, ws.z.as<Fr>(), pk->n_vars, 1u, dig, 0u, P, c, W, d_status);
-    LAUNCH(k_digits, dim3(gx, 1), 128, 0, st, d_r, 1u, 0u, dig, pk->nz, P, c, W, d_status);
-    LAUNCH(k_digits, dim3(gx, 1), 128, 0, st, d_s, 1u, 0u, dig, pk->nz + 1, P, c, W, d_status);
-    LAUNCH(k_digits, dim3(gx, 1), 128, 0, st, ws.rs.as<Fr>(), 1u, 0u, dig, pk->nz + 2, P, c, W, d_status);
-    LAUNCH(k_digits, dim3(gx, pk->n - 1), 128, 0, st, ws.h.as<Fr>(), pk->n, 0u, dig, pk->nz + 3, P, c, W, d_status);
+    const uint32_t ymax = 32768u;
+    LAUNCH(k_digits, dim3(gx, std::min(pk->nz, ymax)), 128, 0, st, ws.z.as<Fr>(), pk->n_vars, 1u, dig, 0u, P, c, W, d_status, pk->nz);
+    LAUNCH(k_digits, dim3(gx, 1), 128, 0, st, d_r, 1u, 0u, dig, pk->nz, P, c, W, d_status, 1u);
+    LAUNCH(k_digits, dim3(gx, 1), 128, 0, st, d_s, 1u, 0u, dig, pk->nz + 1, P, c, W, d_status, 1u);
+    LAUNCH(k_digits, dim3(gx, 1), 128, 0, st, ws.rs.as<Fr>(), 1u, 0u, dig, pk->nz + 2, P, c, W, d_status, 1u);
+    LAUNCH(k_digits, dim3(gx, std::min(pk->n - 1, ymax)), 128, 0, st, ws.h.as<Fr>(), pk->n, 0u, dig, pk->nz + 3, P, c, W, d_status,
+           pk->n - 1);
     }
     auto args = [&](MsmPlan &pl, int iv, void *partial, void *out) {
         return BatchMsmArgs{pl.table.p, pk->N, pl.unit_dig.as<uint32_t>(), pl.unit_tbl.as<uint32_t>(), pl.items[iv].p,
                             pl.n_items[iv], pl.msm_items[iv].p, pl.n_msm, dig, P, partial, out};
     };
-    { Region reg(pk, LZKP_REGION_MSM_G1, st); batch_msm_g1(args(pk->g1, item_variant(P), ws.part1.p, ws.res1.p), st); }
-    { Region reg(pk, LZKP_REGION_MSM_G2, st); batch_msm_g2(args(pk->g2, item_variant_g2(P), ws.part2.p, ws.res2.p), st); }
+    { Region reg(pk, LZKP_REGION_MSM_G1, st); batch_msm_g1(args(pk->g1, fit_variant(pk->g1, item_variant(P)), ws.part1.p, ws.res1.p), st); }
+    { Region reg(pk, LZKP_REGION_MSM_G2, st); batch_msm_g2(args(pk->g2, fit_variant(pk->g2, item_variant_g2(P)), ws.part2.p, ws.res2.p), st); }
     Region reg(pk, LZKP_REGION_ASSEMBLE, st);
     LAUNCH(k_assemble, (P + 31) / 32, 192, 0, st, ws.res1.as<G1XYZZ>(), ws.res2.as<G2XYZZ>(), pk->consts, d_r, d_s, P, d_proofs);
     return LZKP_OK;

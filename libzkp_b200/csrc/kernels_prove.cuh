@@ -305,18 +305,21 @@ __global__ void k_check_canonical(const Fr *v, uint32_t count, int32_t *status) 
 // windows u_w of s' give d_w = u_w - 2^(c-1) in [-2^(c-1), 2^(c-1)), independently per window.
 // dig[(row * W + w) * P + p].  grid (ceil(P/128), count), row = row0 + blockIdx.y.
 __global__ void __launch_bounds__(128) k_digits(const Fr *scalars, uint32_t stride, uint32_t first, int16_t *dig,
-                                                uint32_t row0, uint32_t P, uint32_t c, uint32_t W, int32_t *status) {
-    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+                                                uint32_t row0, uint32_t P, uint32_t c, uint32_t W, int32_t *status,
+                                                uint32_t count) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P) return;
-    Fr s = ld_vec(scalars + (size_t)p * stride + first + j);
-    if (!fr_is_canonical(s)) {
-        status[p] = 1;                  // non-canonical input: the reference's deserializer rejects it
-        s = Fr::zero();
+    for (uint32_t j = blockIdx.y; j < count; j += gridDim.y) {       // rows beyond the grid's y limit: stride loop
+        Fr s = ld_vec(scalars + (size_t)p * stride + first + j);
+        if (!fr_is_canonical(s)) {
+            status[p] = 1;                  // non-canonical input: the reference's deserializer rejects it
+            s = Fr::zero();
+        }
+        uint32_t v[10];
+        recode_offset(s, c, W, v);
+        const size_t base = ((size_t)(row0 + j) * W) * P + p;
+        for (uint32_t w = 0; w < W; w++) dig[base + (size_t)w * P] = (int16_t)recoded_digit(v, c, w);
     }
-    uint32_t v[10];
-    recode_offset(s, c, W, v);
-    const size_t base = ((size_t)(row0 + j) * W) * P + p;
-    for (uint32_t w = 0; w < W; w++) dig[base + (size_t)w * P] = (int16_t)recoded_digit(v, c, w);
 }
 // rs[p] = r[p] * s[p] mod r, canonical in / out
 __global__ void k_fr_mul_canonical(const Fr *r, const Fr *s, Fr *rs, uint32_t P) {

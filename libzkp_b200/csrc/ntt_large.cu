@@ -276,7 +276,14 @@ int large_ntt_device(void *d_in, void *d_out, uint32_t log_n, int inverse, int c
     A.coset = coset;
     A.batch_stride = batch_stride;
     if (batch == 0) return LZKP_OK;
-    if (batch > 65535) return fail(LZKP_E_INVALID, "NTT batch above 65535");
+    if (batch > 65535) {                     // the batch index is the grid's y dimension: run it in slices
+        for (uint32_t b0 = 0; b0 < batch; b0 += 65535) {
+            const uint32_t nb = std::min(65535u, batch - b0);
+            TRY(large_ntt_device((Fr *)d_in + (size_t)b0 * batch_stride, (Fr *)d_out + (size_t)b0 * batch_stride, log_n, inverse,
+                                 coset, st, nb, batch_stride));
+        }
+        return LZKP_OK;
+    }
     uint32_t log_stride = log_n;
     for (uint32_t q = 0; q < P->n_pass; q++) {
         const uint32_t b = P->bits[q];
