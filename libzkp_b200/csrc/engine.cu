@@ -863,7 +863,12 @@ int lzkp_init(const int *devices, int n_devices) {
     }
     return ensure_device();
 }
-int lzkp_shutdown(void) { return LZKP_OK; }
+int lzkp_shutdown(void) {        // releases the process-wide caches (NTT plans, generator tables); keys are freed by lzkp_pk_free
+    if (g_device >= 0) cudaSetDevice(g_device);
+    ntt_plans_free();
+    generator_tables_free();
+    return LZKP_OK;
+}
 const char *lzkp_last_error(void) { return g_err.c_str(); }
 uint64_t lzkp_kernel_launches(void) { return g_launches.load(); }
 

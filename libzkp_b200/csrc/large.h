@@ -11,6 +11,7 @@ int large_ntt_host(uint8_t *data, uint32_t log_n, int inverse, int coset);
 // `batch` polynomials, `batch_stride` elements apart, are transformed by the same launches.
 int large_ntt_device(void *d_in, void *d_out, uint32_t log_n, int inverse, int coset, cudaStream_t st, uint32_t batch = 1,
                      size_t batch_stride = 0);
+void ntt_plans_free();
 // Pippenger MSM over host buffers in ark-serialize layout (msm_large.cu).
 int large_msm_g1_host(const uint8_t *bases_affine, const uint8_t *scalars, size_t n, uint8_t *out_affine);
 int large_msm_g2_host(const uint8_t *bases_affine, const uint8_t *scalars, size_t n, uint8_t *out_affine);

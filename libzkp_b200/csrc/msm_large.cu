@@ -588,14 +588,6 @@ int msm_bases_load(int group, const uint8_t *bases, size_t n, int window_bits, i
         delete B;
         return rc;
     }
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(k_long_run<Fq2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * (int)sizeof(G2XYZZ));
-        cudaFuncSetAttribute(k_red_planes<Fq2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * (int)sizeof(G2XYZZ));
-        cudaFuncSetAttribute(k_red_direct1<Fq2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * (int)sizeof(G2XYZZ));
-        cudaFuncSetAttribute(k_red_direct2<Fq2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * (int)sizeof(G2XYZZ));
-        attr = true;
-    }
     *out = B;
     return LZKP_OK;
 }

@@ -257,6 +257,13 @@ static int get_plan(uint32_t log_n, int inverse, cudaStream_t st, NttPlan **out)
     return LZKP_OK;
 }
 
+// Releases the cached per-size tables (lzkp_shutdown).
+void ntt_plans_free() {
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    for (auto &kv : g_plans) delete kv.second;
+    g_plans.clear();
+}
+
 // d_in is clobbered when the transform needs more than one pass; the result is written to d_out
 // (d_out may equal d_in only for single-pass sizes, log_n <= 11).
 int large_ntt_device(void *d_in, void *d_out, uint32_t log_n, int inverse, int coset, cudaStream_t st, uint32_t batch,

@@ -63,11 +63,13 @@ struct GenTables {
     static constexpr uint32_t W = 16, N = 32768;
 };
 // window tables of the standard generators (built on first use, kept for the process lifetime)
+GenTables *g_gen = nullptr;
+bool g_gen_have2 = false;
+std::mutex g_gen_mu;
 int gen_tables(GenTables **out, int need_g2) {
-    static GenTables *T = nullptr;
-    static bool have2 = false;
-    static std::mutex mu;
-    std::lock_guard<std::mutex> lk(mu);
+    GenTables *&T = g_gen;
+    bool &have2 = g_gen_have2;
+    std::lock_guard<std::mutex> lk(g_gen_mu);
     if (!T) {
         GenTables *t = new GenTables();
         host::G1Canon g1c;
@@ -100,6 +102,13 @@ int gen_tables(GenTables **out, int need_g2) {
     return LZKP_OK;
 }
 }  // namespace
+
+void generator_tables_free() {
+    std::lock_guard<std::mutex> lk(g_gen_mu);
+    delete g_gen;
+    g_gen = nullptr;
+    g_gen_have2 = false;
+}
 
 // out[i] = scalars[i] * generator (ark-serialize affine bytes); scalars canonical, host buffers
 int generator_mul(int group, const uint8_t *scalars, size_t n, uint8_t *out) {

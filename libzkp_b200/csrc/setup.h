@@ -9,5 +9,6 @@ int setup_run(uint32_t m, uint32_t n_inst, uint32_t n_wit, const uint32_t *const
               const uint32_t *const col[3], const uint8_t *const val[3], const uint8_t *toxic,
               std::vector<uint8_t> &pk_out, std::vector<uint8_t> &vk_out);
 int generator_mul(int group, const uint8_t *scalars, size_t n, uint8_t *out);
+void generator_tables_free();
 }
 }  // namespace lzkp
