@@ -207,6 +207,19 @@ int lzkp_ntt(uint8_t *data, uint32_t log_n, int inverse, int coset);
  * (canonical in -> canonical out, Montgomery in -> Montgomery out). */
 int lzkp_ntt_device(void *d_in, void *d_out, uint32_t log_n, int inverse, int coset, void *stream);
 
+/* Batched verification on the device.  lzkp_vk_load parses an ark-serialize uncompressed
+ * VerifyingKey<Bn254> (what snark.rs:103-112 persists) and computes e(alpha, beta) once - the reference recomputes
+ * process_vk on every verify call (snark.rs:387,472).  lzkp_verify_batch decides, per proof, what
+ * Proof::deserialize_uncompressed + Groth16::verify_with_processed_vk decide (snark.rs:378-400, 463-494):
+ * proofs n x 256 B, public_inputs n x n_pub x 32 B canonical (equality: [commitment]; membership: [commitment,
+ * set[64], is_real[64]], snark.rs:398,482-492); ok_out[i] = 1 accept, 0 reject (malformed, off-curve, outside the
+ * subgroup, non-canonical, wrong input count, or failing the pairing equation). */
+typedef struct lzkp_vk lzkp_vk;
+int lzkp_vk_load(const uint8_t *vk_bytes, size_t len, lzkp_vk **out);
+void lzkp_vk_free(lzkp_vk *vk);
+int lzkp_verify_batch(lzkp_vk *vk, size_t n, const uint8_t *proofs, const uint8_t *public_inputs, size_t n_pub,
+                      uint8_t *ok_out);
+
 /* MiMC-5 commitment of a u64 (commit_value_snark), 32 B canonical LE.  Host arithmetic, no device. */
 int lzkp_commit_value_snark(uint64_t value, uint8_t out[32]);
 

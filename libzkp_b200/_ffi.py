@@ -70,6 +70,9 @@ SIGNATURES = {
     "lzkp_msm_device": (_int, [_vp, _vp, _sz, _vp, _vp]),
     "lzkp_ntt": (_int, [_vp, _u32, _int, _int]),
     "lzkp_ntt_device": (_int, [_vp, _vp, _u32, _int, _int, _vp]),
+    "lzkp_vk_load": (_int, [_vp, _sz, C.POINTER(_vp)]),
+    "lzkp_vk_free": (None, [_vp]),
+    "lzkp_verify_batch": (_int, [_vp, _sz, _vp, _vp, _sz, _vp]),
     "lzkp_commit_value_snark": (_int, [_u64, _vp]),
 }
 

@@ -18,6 +18,7 @@
 #include "tables.h"
 #include "large.h"
 #include "setup.h"
+#include "verify.h"
 
 using namespace lzkp;
 using namespace lzkp::eng;
@@ -1293,6 +1294,29 @@ int lzkp_ntt_device(void *d_in, void *d_out, uint32_t log_n, int inverse, int co
     if (log_n > 11 && d_in == d_out) return fail(LZKP_E_INVALID, "lzkp_ntt_device: d_out must differ from d_in above 2^11");
     TRY(ensure_device());
     return large_ntt_device(d_in, d_out, log_n, inverse, coset, (cudaStream_t)stream);
+}
+
+struct lzkp_vk { VerifyingKeyDev *v; };
+int lzkp_vk_load(const uint8_t *vk_bytes, size_t len, lzkp_vk **out) {
+    if (!vk_bytes || !out) return fail(LZKP_E_INVALID, "null argument");
+    *out = nullptr;
+    TRY(ensure_device());
+    VerifyingKeyDev *v = nullptr;
+    TRY(vk_load(vk_bytes, len, &v));
+    *out = new lzkp_vk{v};
+    return LZKP_OK;
+}
+void lzkp_vk_free(lzkp_vk *vk) {
+    if (!vk) return;
+    if (g_device >= 0) cudaSetDevice(g_device);
+    vk_free(vk->v);
+    delete vk;
+}
+int lzkp_verify_batch(lzkp_vk *vk, size_t n, const uint8_t *proofs, const uint8_t *public_inputs, size_t n_pub,
+                      uint8_t *ok_out) {
+    if (!vk || (n && (!proofs || !ok_out || (n_pub && !public_inputs)))) return fail(LZKP_E_INVALID, "null argument");
+    TRY(ensure_device());
+    return verify_batch(vk->v, n, proofs, public_inputs, n_pub, ok_out);
 }
 
 int lzkp_commit_value_snark(uint64_t value, uint8_t out[32]) {

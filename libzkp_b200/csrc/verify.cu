@@ -1,0 +1,186 @@
+// verify.cu — batched Groth16/BN254 verification on the device (lzkp_vk_load / lzkp_verify_batch).
+//
+// Replaces, for batches, what the reference does one proof at a time on the CPU (src/backend/snark.rs:377-401 and
+// :455-495): Proof::deserialize_uncompressed (validating), Groth16::process_vk — recomputed there on EVERY call,
+// here once per key at lzkp_vk_load —, the public-input accumulation and verify_with_processed_vk:
+//     e(A, B) * e(vk_x, -gamma) * e(C, -delta) == e(alpha, beta),   vk_x = gamma_abc[0] + sum_i x_i gamma_abc[i+1].
+// One proof per thread: three Miller loops sharing their squarings, one final exponentiation.
+#include <cstring>
+#include <vector>
+
+#include "dev_util.cuh"
+#include "host_util.h"
+#include "pairing.cuh"
+#include "verify.h"
+
+namespace lzkp {
+
+namespace {
+
+struct VkDev {
+    G1Affine alpha;
+    G2Affine beta, gamma_neg, delta_neg;
+    Fq12 alpha_beta;                 // e(alpha, beta), filled by k_vk_prepare
+};
+
+__device__ __forceinline__ bool read_fq_canonical(const uint8_t *b, Fq &out, uint32_t &flags) {
+    const uint4 *s = reinterpret_cast<const uint4 *>(b);
+    uint4 lo = s[0], hi = s[1];
+    flags = hi.w >> 30;
+    hi.w &= 0x3FFFFFFFu;
+    Fq c;
+    c.l[0] = lo.x; c.l[1] = lo.y; c.l[2] = lo.z; c.l[3] = lo.w; c.l[4] = hi.x; c.l[5] = hi.y; c.l[6] = hi.z; c.l[7] = hi.w;
+    uint32_t d[8];
+    Fq m = Fq::modulus();
+    bool ok = sub8(d, c.l, m.l) != 0;          // c < q
+    out = Fq::from_canonical(c);
+    return ok;
+}
+// ark-serialize uncompressed, validating: canonical coordinates, on the curve (infinity flag accepted)
+__device__ __noinline__ bool read_g1_checked(const uint8_t *b, G1Affine &p) {
+    uint32_t f0, f1;
+    bool ok = read_fq_canonical(b, p.x, f0) & read_fq_canonical(b + 32, p.y, f1);
+    if (f0) ok = false;
+    if (f1 & 1u) { p = G1Affine::inf(); return ok; }        // infinity flag (bit 6 of the last byte)
+    return ok && g1_on_curve(p);
+}
+__device__ __noinline__ bool read_g2_checked(const uint8_t *b, G2Affine &p) {
+    uint32_t f0, f1, f2, f3;
+    bool ok = read_fq_canonical(b, p.x.c0, f0) & read_fq_canonical(b + 32, p.x.c1, f1) &
+              read_fq_canonical(b + 64, p.y.c0, f2) & read_fq_canonical(b + 96, p.y.c1, f3);
+    if (f0 | f1 | f2) ok = false;
+    if (f3 & 1u) { p = G2Affine::inf(); return ok; }
+    if (!ok || !g2_on_curve(p)) return false;
+    // subgroup check (deserialize_uncompressed validates it): r * P == O  <=>  (r - 1) * P == -P
+    Fr rm1 = Fr::modulus();
+    rm1.l[0] -= 1;
+    G2XYZZ t = scalar_mul(G2XYZZ::from_affine(p), rm1);
+    t.madd_cold(p);
+    return t.is_inf();
+}
+
+// e(alpha, beta) once per key (what process_vk precomputes)
+__global__ void k_vk_prepare(VkDev *vk) {
+    G1Affine P[1] = {vk->alpha};
+    G2Affine Q[1] = {vk->beta};
+    bool skip[1] = {vk->alpha.is_inf() || vk->beta.is_inf()};
+    Fq12 f, e;
+    multi_miller_loop<1>(f, P, Q, skip);
+    final_exponentiation(e, f);
+    vk->alpha_beta = e;
+}
+
+// ok[p] = 1 iff proof p verifies against its public inputs
+__global__ void __launch_bounds__(64) k_verify(const VkDev *__restrict__ vk, const G1Affine *__restrict__ gamma_abc,
+                                              uint32_t n_pub, const uint8_t *__restrict__ proofs,
+                                              const Fr *__restrict__ inputs, uint32_t n, uint8_t *__restrict__ ok) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    G1Affine P[3];
+    G2Affine Q[3];
+    const uint8_t *pb = proofs + (size_t)p * 256;
+    bool good = read_g1_checked(pb, P[0]);
+    good = read_g2_checked(pb + 64, Q[0]) && good;
+    good = read_g1_checked(pb + 192, P[2]) && good;
+    // vk_x = gamma_abc[0] + sum x_i gamma_abc[i + 1]
+    G1XYZZ acc = G1XYZZ::from_affine(ldg_vec(gamma_abc));
+    const Fr *x = inputs + (size_t)p * n_pub;
+#pragma unroll 1
+    for (uint32_t i = 0; i < n_pub; i++) {
+        Fr xi = ld_vec(x + i);
+        if (!fr_is_canonical(xi)) { good = false; continue; }
+        if (xi.is_zero()) continue;
+        acc.add_cold(scalar_mul(G1XYZZ::from_affine(ldg_vec(gamma_abc + 1 + i)), xi));
+    }
+    if (!good) { ok[p] = 0; return; }
+    P[1] = acc.to_affine();
+    Q[1] = vk->gamma_neg;
+    Q[2] = vk->delta_neg;
+    bool skip[3];
+#pragma unroll 1
+    for (int k = 0; k < 3; k++) skip[k] = P[k].is_inf() || Q[k].is_inf();     // e(O, .) = e(., O) = 1
+    Fq12 f, e;
+    multi_miller_loop<3>(f, P, Q, skip);
+    final_exponentiation(e, f);
+    ok[p] = f12_eq(e, vk->alpha_beta) ? 1 : 0;
+}
+
+__global__ void k_fq_mont(Fq *v, size_t count) {
+    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    st_vec(v + k, Fq::from_canonical(ld_vec(v + k)));
+}
+
+}  // namespace
+
+namespace eng {
+
+struct VerifyingKeyDev {
+    DBuf vk, gamma_abc;
+    uint32_t n_pub = 0;
+    std::mutex mu;
+};
+
+int vk_load(const uint8_t *bytes, size_t len, VerifyingKeyDev **out) {
+    // ark-serialize VerifyingKey<Bn254>: alpha_g1, beta_g2, gamma_g2, delta_g2, Vec<gamma_abc_g1>
+    if (len < 64 + 3 * 128 + 8) return fail(LZKP_E_INVALID, "verifying key: truncated");
+    host::G1Canon alpha;
+    host::G2Canon beta, gamma, delta;
+    const uint8_t *p = bytes;
+    bool ok = host::read_g1(p, alpha) && host::read_g2(p + 64, beta) && host::read_g2(p + 192, gamma) && host::read_g2(p + 320, delta);
+    uint64_t cnt;
+    memcpy(&cnt, p + 448, 8);
+    if (!ok || cnt < 1 || cnt > (len - 456) / 64 || 456 + cnt * 64 != len) return fail(LZKP_E_INVALID, "verifying key: malformed bytes");
+    std::vector<host::G1Canon> abc(cnt);
+    for (uint64_t i = 0; i < cnt; i++)
+        if (!host::read_g1(p + 456 + 64 * i, abc[i])) return fail(LZKP_E_INVALID, "verifying key: non-canonical coordinate");
+    auto neg2 = [](host::G2Canon q) {
+        if (host::is_inf(q)) return q;
+        Fq m = Fq::modulus();
+        host::G2Canon r = q;
+        if (!q.y0.is_zero()) sub8(r.y0.l, m.l, q.y0.l);
+        if (!q.y1.is_zero()) sub8(r.y1.l, m.l, q.y1.l);
+        return r;
+    };
+    VerifyingKeyDev *V = new (std::nothrow) VerifyingKeyDev();
+    if (!V) return fail(LZKP_E_NOMEM, "host allocation failed");
+    V->n_pub = (uint32_t)cnt - 1;
+    struct Packed { host::G1Canon alpha; host::G2Canon beta, gneg, dneg; } pk{alpha, beta, neg2(gamma), neg2(delta)};
+    static_assert(sizeof(Packed) == sizeof(G1Affine) + 3 * sizeof(G2Affine), "layout");
+    int rc = V->vk.alloc(sizeof(VkDev));
+    if (rc == LZKP_OK) rc = upload(V->gamma_abc, abc);
+    if (rc != LZKP_OK) { delete V; return rc; }
+    cudaMemset(V->vk.p, 0, sizeof(VkDev));
+    cudaMemcpy(V->vk.p, &pk, sizeof(pk), cudaMemcpyHostToDevice);
+    k_fq_mont<<<1, 64>>>(V->vk.as<Fq>(), sizeof(pk) / 32);
+    k_fq_mont<<<(unsigned)((cnt * 2 + 127) / 128), 128>>>(V->gamma_abc.as<Fq>(), cnt * 2);
+    k_vk_prepare<<<1, 1>>>(V->vk.as<VkDev>());
+    g_launches.fetch_add(3, std::memory_order_relaxed);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { delete V; return fail(LZKP_E_CUDA, std::string("vk_load: ") + cudaGetErrorString(e)); }
+    *out = V;
+    return LZKP_OK;
+}
+void vk_free(VerifyingKeyDev *V) { delete V; }
+uint32_t vk_num_inputs(const VerifyingKeyDev *V) { return V->n_pub; }
+
+int verify_batch(VerifyingKeyDev *V, size_t n, const uint8_t *proofs, const uint8_t *inputs, size_t n_pub, uint8_t *ok_out) {
+    std::lock_guard<std::mutex> lk(V->mu);
+    if (n_pub != V->n_pub) {                   // wrong number of public inputs: nothing verifies (reference: Err -> false)
+        memset(ok_out, 0, n);
+        return LZKP_OK;
+    }
+    if (n == 0) return LZKP_OK;
+    DBuf d_p, d_x, d_ok;
+    TRY(d_p.alloc(n * 256)); TRY(d_x.alloc(n * std::max<size_t>(n_pub, 1) * 32)); TRY(d_ok.alloc(n));
+    CUDA_TRY(cudaMemcpy(d_p.p, proofs, n * 256, cudaMemcpyHostToDevice));
+    if (n_pub) CUDA_TRY(cudaMemcpy(d_x.p, inputs, n * n_pub * 32, cudaMemcpyHostToDevice));
+    LAUNCH(k_verify, (unsigned)((n + 63) / 64), 64, 0, 0, V->vk.as<VkDev>(), V->gamma_abc.as<G1Affine>(), (uint32_t)n_pub,
+           d_p.as<uint8_t>(), d_x.as<Fr>(), (uint32_t)n, d_ok.as<uint8_t>());
+    CUDA_TRY(cudaMemcpy(ok_out, d_ok.p, n, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaGetLastError());
+    return LZKP_OK;
+}
+
+}  // namespace eng
+}  // namespace lzkp

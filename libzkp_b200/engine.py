@@ -335,3 +335,34 @@ def generator_mul(group: int, scalars) -> np.ndarray:
     out = np.zeros((scalars.shape[0], 64 if group == 1 else 128), np.uint8)
     check(lib().lzkp_generator_mul(group, _p(scalars), scalars.shape[0], _p(out)))
     return out
+
+
+class VerifyingKey:
+    """A verifying key resident on the device with e(alpha, beta) precomputed (lzkp_vk)."""
+
+    def __init__(self, vk_bytes: bytes):
+        self._h = C.c_void_p()
+        buf = np.frombuffer(vk_bytes, dtype=np.uint8)
+        check(lib().lzkp_vk_load(_p(buf), len(vk_bytes), C.byref(self._h)))
+        self.n_pub = (len(vk_bytes) - 456) // 64 - 1
+
+    def verify_batch(self, proofs, public_inputs) -> np.ndarray:
+        """proofs (n, 256) bytes; public_inputs (n, n_pub, 32) canonical bytes -> bool array."""
+        proofs = _u8(proofs, 256)
+        n = proofs.shape[0]
+        x = np.ascontiguousarray(public_inputs, np.uint8).reshape(n, -1) if n else np.zeros((0, 0), np.uint8)
+        n_pub = x.shape[1] // 32 if n else self.n_pub
+        ok = np.zeros(n, np.uint8)
+        check(lib().lzkp_verify_batch(self._h, n, _p(proofs), _p(x) if x.size else None, n_pub, _p(ok)))
+        return ok.astype(bool)
+
+    def close(self):
+        if self._h:
+            lib().lzkp_vk_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -3,7 +3,7 @@ src/proof/equality_proof.rs, src/proof/set_membership.rs) over the device-backed
 from __future__ import annotations
 
 import struct
-from typing import List, Sequence
+from typing import List, Optional, Sequence
 
 from .errors import InvalidInput, InvalidProofFormat, ProofGenerationFailed
 from .snark import MAX_SET_SIZE, SnarkBackend, mimc_commitment
@@ -120,4 +120,70 @@ def prove_membership_many(items: Sequence, rng=None) -> List[bytes]:
     for e in out:
         if not e:
             raise ProofGenerationFailed("SNARK membership proof generation failed")
+    return out
+
+
+# ---------------------------------------------------------------- verification (equality_proof.rs:34-61, set_membership.rs:40-71)
+def _parse(proof_bytes: bytes, scheme: int) -> Optional[Proof]:
+    """parse_and_validate_proof (utils/proof_helpers.rs): envelope, version, scheme."""
+    try:
+        p = Proof.from_bytes(bytes(proof_bytes))
+    except InvalidProofFormat:
+        return None
+    if p.version != PROOF_VERSION or p.scheme != scheme:
+        return None
+    return p
+
+
+def _embedded_set(payload: bytes):
+    """deserialize_embedded_set_prefix: u32 len || u64[len] || rest, len <= MAX_SET_SIZE."""
+    if len(payload) < 4:
+        return None
+    n = struct.unpack_from("<I", payload, 0)[0]
+    if n > MAX_SET_SIZE or len(payload) < 4 + 8 * n:
+        return None
+    return list(struct.unpack_from("<%dQ" % n, payload, 4)), payload[4 + 8 * n:]
+
+
+def verify_equality_with_commitment(proof: bytes, expected_commitment: bytes) -> bool:
+    return verify_equality_many([(proof, expected_commitment)])[0]
+
+
+def verify_equality(proof: bytes, val1: int, val2: int) -> bool:
+    if val1 != val2:
+        return False
+    return verify_equality_with_commitment(proof, commit_value_snark(val1))
+
+
+def verify_equality_many(items: Sequence) -> List[bool]:
+    """items: (proof_bytes, expected_commitment).  One device call for all of them."""
+    out = [False] * len(items)
+    idx, proofs, cms = [], [], []
+    for i, (pb, cm) in enumerate(items):
+        p = _parse(pb, EQUALITY_SCHEME_ID)
+        if p is None or len(cm) != 32 or p.commitment != bytes(cm):
+            continue
+        idx.append(i); proofs.append(p.proof); cms.append(bytes(cm))
+    for i, ok in zip(idx, SnarkBackend.verify_equality_zk_batch(proofs, cms)):
+        out[i] = ok
+    return out
+
+
+def verify_membership(proof: bytes, set_: Sequence[int]) -> bool:
+    return verify_membership_many([(proof, set_)])[0]
+
+
+def verify_membership_many(items: Sequence) -> List[bool]:
+    out = [False] * len(items)
+    idx, proofs, sets, cms = [], [], [], []
+    for i, (pb, set_) in enumerate(items):
+        p = _parse(pb, MEMBERSHIP_SCHEME_ID)
+        if p is None or len(p.commitment) != 32:
+            continue
+        emb = _embedded_set(p.proof)
+        if emb is None or not emb[1] or len(set_) != len(emb[0]) or sorted(set_) != sorted(emb[0]):
+            continue
+        idx.append(i); proofs.append(emb[1]); sets.append(emb[0]); cms.append(p.commitment)
+    for i, ok in zip(idx, SnarkBackend.verify_membership_zk_batch(proofs, sets, cms)):
+        out[i] = ok
     return out

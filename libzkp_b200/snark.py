@@ -63,6 +63,14 @@ class Setup:
     def __init__(self, pk: engine.ProvingKey, vk_bytes: bytes):
         self.pk = pk
         self.vk_bytes = vk_bytes
+        self._vk: Optional[engine.VerifyingKey] = None
+
+    @property
+    def vk(self) -> engine.VerifyingKey:
+        """Device verifying key with e(alpha, beta) precomputed once (the reference recomputes process_vk per call)."""
+        if self._vk is None:
+            self._vk = engine.VerifyingKey(self.vk_bytes)
+        return self._vk
 
 
 def configure(window_bits: int = 0, table_budget_bytes: int = 0, max_chunk: int = 0, validate: bool = False,
@@ -82,6 +90,8 @@ def reset() -> None:
         for v in _setups.values():
             if isinstance(v, Setup):
                 v.pk.close()
+                if v._vk is not None:
+                    v._vk.close()
         _setups.clear()
         _key_dir_override = None
 
@@ -330,6 +340,61 @@ class SnarkBackend:
             if status[k] == 0:
                 out[i] = eb[row * k:row * k + int(lens[k])]
         return out
+
+    # ---- verification (snark.rs:377-401, 455-495), batched on the device
+    @staticmethod
+    def verify_equality_zk_batch(proofs: Sequence[bytes], hash_inputs: Sequence[bytes]) -> List[bool]:
+        n = len(proofs)
+        out = [False] * n
+        live = [i for i in range(n) if len(proofs[i]) == 256 and _fr_from_commitment(bytes(hash_inputs[i])) is not None]
+        setup = SnarkBackend.get_universal_setup() if live else None
+        if not live or not isinstance(setup, Setup):
+            return out
+        try:
+            ok = setup.vk.verify_batch(np.frombuffer(b"".join(bytes(proofs[i]) for i in live), np.uint8),
+                                       np.frombuffer(b"".join(bytes(hash_inputs[i]) for i in live), np.uint8))
+        except Exception:                           # noqa: BLE001
+            return out
+        for k, i in enumerate(live):
+            out[i] = bool(ok[k])
+        return out
+
+    @staticmethod
+    def verify_equality_zk(proof_data: bytes, hash_input: bytes) -> bool:
+        return SnarkBackend.verify_equality_zk_batch([proof_data], [hash_input])[0]
+
+    @staticmethod
+    def verify_membership_zk_batch(proofs: Sequence[bytes], sets: Sequence[Sequence[int]],
+                                   commitments: Sequence[bytes]) -> List[bool]:
+        n = len(proofs)
+        out = [False] * n
+        live = [i for i in range(n) if len(proofs[i]) == 256 and 1 <= len(sets[i]) <= MAX_SET_SIZE
+                and _fr_from_commitment(bytes(commitments[i])) is not None]
+        setup = SnarkBackend.get_membership_setup() if live else None
+        if not live or not isinstance(setup, Setup):
+            return out
+        # public inputs [commitment, set[0..64) zero-padded, is_real[0..64)] (snark.rs:482-492)
+        x = np.zeros((len(live), 1 + 2 * MAX_SET_SIZE, 32), np.uint8)
+        for k, i in enumerate(live):
+            x[k, 0] = np.frombuffer(bytes(commitments[i]), np.uint8)
+            L = len(sets[i])
+            x[k, 1:1 + L, :8] = np.array(sets[i], np.uint64).astype("<u8").view(np.uint8).reshape(L, 8)
+            x[k, 1 + MAX_SET_SIZE:1 + MAX_SET_SIZE + L, 0] = 1
+        try:
+            ok = setup.vk.verify_batch(np.frombuffer(b"".join(bytes(proofs[i]) for i in live), np.uint8), x)
+        except Exception:                           # noqa: BLE001
+            return out
+        for k, i in enumerate(live):
+            out[i] = bool(ok[k])
+        return out
+
+    @staticmethod
+    def verify_membership_zk(proof_data: bytes, set_: Sequence[int], commitment: bytes) -> bool:
+        return SnarkBackend.verify_membership_zk_batch([proof_data], [list(set_)], [commitment])[0]
+
+    @staticmethod
+    def verify(proof: bytes, data: bytes) -> bool:          # ZkpBackend::verify (snark.rs:608-610)
+        return SnarkBackend.verify_equality_zk(proof, data)
 
     # ---- ZkpBackend trait (src/backend/mod.rs:5-8; impl snark.rs:587-611)
     @staticmethod

@@ -1,0 +1,124 @@
+"""GPU tests of the batched verifier (lzkp_vk_load / lzkp_verify_batch): decisions equal the oracle's independent
+pairing verifier on valid, forged and malformed proofs, and the reference's own verify tests (snark.rs:634-641,
+tests/integration.rs:19-44,86-90, examples/demo.rs:66-105) pass through the Python mirror."""
+import numpy as np
+import pytest
+
+import libzkp_b200 as zk
+from libzkp_b200 import engine, snark
+
+pytestmark = pytest.mark.gpu
+WINDOW_BITS = 10
+
+
+def test_verify_golden_and_forgeries(eq_keys, mb_keys, golden, po, co):
+    vk = engine.VerifyingKey(eq_keys.vk_bytes)
+    assert vk.n_pub == 1
+    cases = [c for c in golden["equality"]["proofs"] if "z_sha256" in c]
+    proofs = np.stack([np.frombuffer(bytes.fromhex(c["proof"]), np.uint8) for c in cases])
+    cms = np.stack([np.frombuffer(co.mimc_hash(c["a"]), np.uint8) for c in cases])
+    assert vk.verify_batch(proofs, cms).all()
+    wrong = np.roll(cms, 1, axis=0)
+    assert not vk.verify_batch(proofs, wrong).any()                       # wrong public input (snark.rs:639-640)
+    ovk = po.vk_from_bytes(eq_keys.vk_bytes)
+    forged = []
+    for k in range(12):
+        b = proofs[k % len(proofs)].copy()
+        if k < 4:
+            b[[5, 70, 200, 255][k]] ^= 1                                  # bit flips: off-curve / non-canonical / flag
+        elif k < 8:                                                       # a valid but different curve point for A / C
+            other = po.g1_to_bytes(po.G1.mul(po.G1_GEN, 1000 + k))
+            off = 0 if k % 2 else 192
+            b[off:off + 64] = np.frombuffer(other, np.uint8)
+        elif k == 8:
+            b[64:192] = np.frombuffer(po.g2_to_bytes(po.G2.mul(po.G2_GEN, 77)), np.uint8)
+        elif k == 9:
+            b[:64] = 0
+            b[63] = 0x40                                                  # A = infinity
+        elif k == 10:
+            b[:] = 0
+        else:
+            b[31] |= 0x3F                                                 # x >= q
+        forged.append(b)
+    forged = np.stack(forged)
+    fc = np.stack([cms[k % len(cms)] for k in range(12)])
+    got = vk.verify_batch(forged, fc)
+    for k in range(12):
+        try:
+            want = po.verify(ovk, po.equality_public_inputs(int.from_bytes(fc[k].tobytes(), "little")),
+                             po.proof_from_bytes(forged[k].tobytes()))
+        except Exception:
+            want = False
+        assert bool(got[k]) == bool(want) == False, k
+    # non-canonical public input and wrong input count
+    bad = cms.copy()
+    bad[0] = 0xFF
+    assert not vk.verify_batch(proofs[:1], bad[:1])[0]
+    assert not vk.verify_batch(proofs[:2], np.zeros((2, 2, 32), np.uint8)).any()
+    assert vk.verify_batch(np.zeros((0, 256), np.uint8), np.zeros((0, 1, 32), np.uint8)).shape == (0,)
+    vk.close()
+    # membership golden proofs
+    vkm = engine.VerifyingKey(mb_keys.vk_bytes)
+    assert vkm.n_pub == 129
+    mc = golden["membership"]["proofs"]
+    mp = np.stack([np.frombuffer(bytes.fromhex(c["proof"]), np.uint8) for c in mc])
+    x = np.zeros((len(mc), 129, 32), np.uint8)
+    for k, c in enumerate(mc):
+        pub = po.membership_public_inputs(int.from_bytes(co.mimc_hash(c["value"]), "little"), c["set"])
+        x[k] = co.fr_array(pub)
+    assert vkm.verify_batch(mp, x).all()
+    x[1, 5, 0] ^= 1
+    assert list(vkm.verify_batch(mp, x)) == [True, False, True, True]
+    vkm.close()
+
+
+@pytest.fixture(scope="module")
+def api(eq_keys, mb_keys):
+    keys = {"equality_mimc": (eq_keys.pk_bytes, eq_keys.vk_bytes), "membership_mimc": (mb_keys.pk_bytes, mb_keys.vk_bytes)}
+    snark.reset()
+    snark.configure(window_bits=WINDOW_BITS, generator=lambda prefix: keys[prefix])
+    yield zk
+    snark.reset()
+    snark.configure()
+
+
+def test_reference_verify_tests_through_the_mirror(api, po, eq_keys):
+    proof = api.prove_equality(3, 3)                                    # tests/integration.rs:19-23
+    assert api.verify_equality(proof, 3, 3)
+    proof = api.prove_equality(42, 42)                                  # tests/integration.rs:25-32
+    assert api.verify_equality_with_commitment(proof, api.snark_commit_value(42))
+    assert not api.verify_equality(proof, 43, 43)                       # tests/integration.rs:86-90
+    assert not api.verify_equality(proof, 42, 43)
+    assert not api.verify_equality(proof[:-1], 42, 42)
+    tampered = bytearray(proof)
+    tampered[100] ^= 1
+    assert not api.verify_equality(bytes(tampered), 42, 42)
+    cm = api.snark_commit_value(42)                                     # snark.rs:634-641
+    raw = api.SnarkBackend.prove_equality_zk(42, 42, cm)
+    assert api.SnarkBackend.verify_equality_zk(raw, cm)
+    assert not api.SnarkBackend.verify_equality_zk(raw, api.snark_commit_value(99))
+    assert api.SnarkBackend.verify(raw, cm)
+    # agreement with the oracle's pairing verifier on the same bytes
+    assert po.verify(po.vk_from_bytes(eq_keys.vk_bytes), [int.from_bytes(cm, "little")], po.proof_from_bytes(raw))
+    mp = api.prove_membership(2, [1, 2, 3])                             # tests/integration.rs:40-44
+    assert api.verify_membership(mp, [1, 2, 3]) and api.verify_membership(mp, [3, 1, 2])
+    assert not api.verify_membership(mp, [1, 2, 4]) and not api.verify_membership(mp, [1, 2])
+
+
+def test_batch_then_verify_proofs_parallel(api):
+    bid = api.create_proof_batch()                                      # examples/demo.rs:66-105 (SNARK kinds)
+    kinds = []
+    for i in range(6):
+        if i % 2 == 0:
+            api.batch_add_equality_proof(bid, 100 + i, 100 + i)
+            kinds.append("equality")
+        else:
+            api.batch_add_membership_proof(bid, 25, [10, 20, 25, 30, 40][: 3 + i % 3] if 25 in [10, 20, 25, 30, 40][: 3 + i % 3] else [25])
+            kinds.append("membership")
+    proofs = api.process_batch(bid)
+    res = api.verify_proofs_parallel(list(zip(proofs, kinds)))
+    assert res == [True] * 6
+    broken = bytearray(proofs[2])
+    broken[50] ^= 4
+    res = api.verify_proofs_parallel([(bytes(broken), "equality"), (proofs[1], "membership"), (proofs[0], "membership")])
+    assert res == [False, True, False]

@@ -1,0 +1,197 @@
+#!/usr/bin/env python3
+"""Big-int prototype of the tower-field optimal-ate pairing the GPU verifier implements (libzkp_b200/csrc/
+pairing.cuh), checked against the oracle's textbook pairing over Fq[w]/(w^12 - 18 w^6 + 82).  It also derives the
+Frobenius / twist constants the device code embeds.  Test infrastructure: run  python tools/pairing_proto.py
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import zkp_oracle as O  # noqa: E402
+
+P = O.Q_MOD
+R = O.R_MOD
+XI = (9, 1)
+
+
+# ---- Fq2
+def f2add(a, b): return ((a[0] + b[0]) % P, (a[1] + b[1]) % P)
+def f2sub(a, b): return ((a[0] - b[0]) % P, (a[1] - b[1]) % P)
+def f2neg(a): return ((-a[0]) % P, (-a[1]) % P)
+def f2mul(a, b): return ((a[0] * b[0] - a[1] * b[1]) % P, (a[0] * b[1] + a[1] * b[0]) % P)
+def f2sqr(a): return f2mul(a, a)
+def f2conj(a): return (a[0], (-a[1]) % P)
+def f2scal(a, k): return (a[0] * k % P, a[1] * k % P)
+def f2inv(a):
+    n = pow((a[0] * a[0] + a[1] * a[1]) % P, P - 2, P)
+    return (a[0] * n % P, (-a[1]) * n % P)
+def f2pow(a, e):
+    r = (1, 0)
+    for bit in bin(e)[2:]:
+        r = f2sqr(r)
+        if bit == '1':
+            r = f2mul(r, a)
+    return r
+F2_ZERO, F2_ONE = (0, 0), (1, 0)
+
+
+# ---- Fq6 = Fq2[v]/(v^3 - xi): (c0, c1, c2)
+def f6add(a, b): return tuple(f2add(x, y) for x, y in zip(a, b))
+def f6sub(a, b): return tuple(f2sub(x, y) for x, y in zip(a, b))
+def f6neg(a): return tuple(f2neg(x) for x in a)
+def f6mul(a, b):
+    a0, a1, a2 = a
+    b0, b1, b2 = b
+    t0, t1, t2 = f2mul(a0, b0), f2mul(a1, b1), f2mul(a2, b2)
+    c0 = f2add(t0, f2mul(XI, f2sub(f2sub(f2mul(f2add(a1, a2), f2add(b1, b2)), t1), t2)))
+    c1 = f2add(f2sub(f2sub(f2mul(f2add(a0, a1), f2add(b0, b1)), t0), t1), f2mul(XI, t2))
+    c2 = f2add(f2sub(f2sub(f2mul(f2add(a0, a2), f2add(b0, b2)), t0), t2), t1)
+    return (c0, c1, c2)
+def f6mulv(a): return (f2mul(XI, a[2]), a[0], a[1])          # times v
+def f6inv(a):
+    a0, a1, a2 = a
+    c0 = f2sub(f2sqr(a0), f2mul(XI, f2mul(a1, a2)))
+    c1 = f2sub(f2mul(XI, f2sqr(a2)), f2mul(a0, a1))
+    c2 = f2sub(f2sqr(a1), f2mul(a0, a2))
+    t = f2inv(f2add(f2mul(a0, c0), f2mul(XI, f2add(f2mul(a2, c1), f2mul(a1, c2)))))
+    return (f2mul(c0, t), f2mul(c1, t), f2mul(c2, t))
+F6_ZERO, F6_ONE = (F2_ZERO,) * 3, (F2_ONE, F2_ZERO, F2_ZERO)
+
+
+# ---- Fq12 = Fq6[w]/(w^2 - v): (c0, c1)
+def f12mul(a, b):
+    t0, t1 = f6mul(a[0], b[0]), f6mul(a[1], b[1])
+    c1 = f6sub(f6sub(f6mul(f6add(a[0], a[1]), f6add(b[0], b[1])), t0), t1)
+    return (f6add(t0, f6mulv(t1)), c1)
+def f12sqr(a): return f12mul(a, a)
+def f12conj(a): return (a[0], f6neg(a[1]))
+def f12inv(a):
+    t = f6inv(f6sub(f6mul(a[0], a[0]), f6mulv(f6mul(a[1], a[1]))))
+    return (f6mul(a[0], t), f6neg(f6mul(a[1], t)))
+def f12pow(a, e):
+    r = F12_ONE
+    for bit in bin(e)[2:]:
+        r = f12sqr(r)
+        if bit == '1':
+            r = f12mul(r, a)
+    return r
+F12_ONE = (F6_ONE, F6_ZERO)
+
+# Frobenius^2 on Fq12: coefficient of v^i w^j is multiplied by xi^((p^2 - 1) (2i + j) / 6), an element of Fq
+G2C = [f2pow(XI, (P * P - 1) * k // 6) for k in range(6)]
+assert all(c[1] == 0 for c in G2C)
+def f12frob2(a):
+    return tuple(tuple(f2scal(a[j][i], G2C[2 * i + j][0]) for i in range(3)) for j in range(2))
+
+# twist Frobenius constants (mul_by_char): pi(x, y) = (conj(x) * xi^((p-1)/3), conj(y) * xi^((p-1)/2))
+TW_X, TW_Y = f2pow(XI, (P - 1) // 3), f2pow(XI, (P - 1) // 2)
+B_TWIST = f2mul((3, 0), f2inv(XI))
+TWO_INV = pow(2, P - 2, P)
+
+
+def sparse(c0, c3, c4):
+    """c0 + c3 * w + c4 * v w as a full Fq12 element (D-twist line)."""
+    return ((c0, F2_ZERO, F2_ZERO), (c3, c4, F2_ZERO))
+
+
+def dbl_step(Rp):
+    X, Y, Z = Rp
+    a = f2scal(f2mul(X, Y), TWO_INV)
+    b, c = f2sqr(Y), f2sqr(Z)
+    e = f2mul(B_TWIST, f2add(f2add(c, c), c))
+    f = f2add(f2add(e, e), e)
+    g = f2scal(f2add(b, f), TWO_INV)
+    h = f2sub(f2sqr(f2add(Y, Z)), f2add(b, c))
+    i = f2sub(e, b)
+    j = f2sqr(X)
+    e2 = f2sqr(e)
+    Xn = f2mul(a, f2sub(b, f))
+    Yn = f2sub(f2sqr(g), f2add(f2add(e2, e2), e2))
+    Zn = f2mul(b, h)
+    return (Xn, Yn, Zn), (f2neg(h), f2add(f2add(j, j), j), i)
+
+
+def add_step(Rp, Q):
+    X, Y, Z = Rp
+    theta = f2sub(Y, f2mul(Q[1], Z))
+    lam = f2sub(X, f2mul(Q[0], Z))
+    c, d = f2sqr(theta), f2sqr(lam)
+    e = f2mul(lam, d)
+    f = f2mul(Z, c)
+    g = f2mul(X, d)
+    h = f2sub(f2add(e, f), f2add(g, g))
+    Xn = f2mul(lam, h)
+    Yn = f2sub(f2mul(theta, f2sub(g, h)), f2mul(e, Y))
+    Zn = f2mul(Z, e)
+    j = f2sub(f2mul(theta, Q[0]), f2mul(lam, Q[1]))
+    return (Xn, Yn, Zn), (lam, f2neg(theta), j)
+
+
+def ell(f, coeffs, Pt):
+    c0 = f2scal(coeffs[0], Pt[1])
+    c1 = f2scal(coeffs[1], Pt[0])
+    return f12mul(f, sparse(c0, c1, coeffs[2]))
+
+
+def miller(Pt, Q):
+    Rp = (Q[0], Q[1], F2_ONE)
+    f = F12_ONE
+    for i in range(O.ATE_LOOP.bit_length() - 2, -1, -1):
+        f = f12sqr(f)
+        Rp, co = dbl_step(Rp)
+        f = ell(f, co, Pt)
+        if (O.ATE_LOOP >> i) & 1:
+            Rp, co = add_step(Rp, Q)
+            f = ell(f, co, Pt)
+    q1 = (f2mul(f2conj(Q[0]), TW_X), f2mul(f2conj(Q[1]), TW_Y))
+    q2 = (f2mul(f2conj(q1[0]), TW_X), f2neg(f2mul(f2conj(q1[1]), TW_Y)))
+    Rp, co = add_step(Rp, q1)
+    f = ell(f, co, Pt)
+    Rp, co = add_step(Rp, q2)
+    f = ell(f, co, Pt)
+    return f
+
+
+HARD = (P ** 4 - P ** 2 + 1) // R
+
+
+def final_exp(f):
+    f1 = f12mul(f12conj(f), f12inv(f))          # f^(p^6 - 1)
+    f2 = f12mul(f12frob2(f1), f1)               # ^(p^2 + 1)
+    return f12pow(f2, HARD)
+
+
+def to_poly(a):
+    out = [0] * 12
+    for j in range(2):
+        for i in range(3):
+            out = O._f12_add(out, O._f12_from_f2(a[j][i], 2 * i + j))
+    return out
+
+
+def limbs(v):
+    return ", ".join("0x%08xu" % ((v >> (32 * i)) & 0xFFFFFFFF) for i in range(8))
+
+
+if __name__ == "__main__":
+    # Frobenius^2 really is x -> x^(p^2)
+    x = (((3, 5), (7, 11), (13, 17)), ((19, 23), (29, 31), (37, 41)))
+    assert f12frob2(x) == f12pow(x, P * P)
+    assert f12mul(x, f12inv(x)) == F12_ONE
+    Pt, Q = O.G1.mul(O.G1_GEN, 12345), O.G2.mul(O.G2_GEN, 67890)
+    mine = final_exp(miller(Pt, Q))
+    ref = O.final_exp(O.miller_loop(Q, Pt))
+    print("matches oracle pairing:", to_poly(mine) == ref)
+    # bilinearity: e(aP, bQ) == e(P, Q)^(ab)
+    e1 = final_exp(miller(O.G1_GEN, O.G2_GEN))
+    assert mine == f12pow(e1, 12345 * 67890 % R)
+    print("bilinear: True")
+    Rm = 1 << 256
+    print("// generated by tools/pairing_proto.py")
+    for name, c in (("TW_X", TW_X), ("TW_Y", TW_Y), ("B_TWIST", B_TWIST)):
+        print(f"{name}_C0 {limbs(c[0] * Rm % P)}\n{name}_C1 {limbs(c[1] * Rm % P)}")
+    for k in range(1, 6):
+        print(f"FROB2_{k} {limbs(G2C[k][0] * Rm % P)}")
+    print("TWO_INV", limbs(TWO_INV * Rm % P))
+    print("HARD bits", HARD.bit_length())
+    print("HARD limbs", ", ".join("0x%08xu" % ((HARD >> (32 * i)) & 0xFFFFFFFF) for i in range((HARD.bit_length() + 31) // 32)))
