@@ -50,6 +50,12 @@ def test_verify_golden_and_forgeries(eq_keys, mb_keys, golden, po, co):
         except Exception:
             want = False
         assert bool(got[k]) == bool(want) == False, k
+    # B on the twist but outside the r-torsion subgroup (tools/pairing_proto.py): deserialization must reject it
+    offsub = bytes.fromhex("02000000000000000000000000000000000000000000000000000000000000000100000000000000000000000000000000000000000000000000000000000000ce0141067f1657f01323d6d1264d1f38c5e0ce2da0ec9950b908934178721f10de5f8f80b5b618595db7a7f6137c7f775a006a5485ac3d962ab99b5979c176ab")
+    assert po.G2.on_curve(po.g2_from_bytes(offsub, validate=False))
+    b = proofs[0].copy()
+    b[64:192] = np.frombuffer(offsub, np.uint8)
+    assert not vk.verify_batch(b[None], cms[:1])[0]
     # non-canonical public input and wrong input count
     bad = cms.copy()
     bad[0] = 0xFF

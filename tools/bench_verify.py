@@ -1,0 +1,24 @@
+import json, sys, time
+import numpy as np
+sys.path.insert(0, '.')
+from libzkp_b200 import engine, transforms
+engine.init(0)
+pk_bytes, vk_bytes = engine.setup_builtin(engine.EQUALITY, 110, transforms._toxic(1))
+pk = engine.ProvingKey(pk_bytes, window_bits=12)
+pk.circuit_builtin(engine.EQUALITY, 110)
+n = 4096
+rng = np.random.default_rng(3)
+a = rng.integers(0, 2**63, size=n, dtype=np.uint64)
+r = np.zeros((n, 32), np.uint8); r[:, 0] = 7
+s = np.zeros((n, 32), np.uint8); s[:, 0] = 9
+proofs, cms, st = pk.prove_equality_batch(a, a, r, s)
+vk = engine.VerifyingKey(vk_bytes)
+for nb in (1, 64, 4096):
+    ok = vk.verify_batch(proofs[:nb], cms[:nb])
+    assert ok.all()
+    t0 = time.perf_counter()
+    K = 3
+    for _ in range(K):
+        vk.verify_batch(proofs[:nb], cms[:nb])
+    dt = (time.perf_counter() - t0) / K
+    print(json.dumps({"batch": nb, "ms": round(1e3 * dt, 2), "verifies_per_s": round(nb / dt, 1)}))

@@ -195,3 +195,89 @@ if __name__ == "__main__":
     print("TWO_INV", limbs(TWO_INV * Rm % P))
     print("HARD bits", HARD.bit_length())
     print("HARD limbs", ", ".join("0x%08xu" % ((HARD >> (32 * i)) & 0xFFFFFFFF) for i in range((HARD.bit_length() + 31) // 32)))
+
+
+# ---------------------------------------------------------------- fast hard part (BN addition chain, x > 0)
+BN_X = O.BN_X
+G1C = [f2pow(XI, (P - 1) * k // 6) for k in range(6)]          # Frobenius^1 coefficients (Fq2)
+G3C = [f2pow(XI, (P ** 3 - 1) * k // 6) for k in range(6)]      # Frobenius^3 coefficients (Fq2)
+
+
+def f12frob_odd(a, C):
+    """x -> x^(p^k) for odd k: conjugate every Fq2 coefficient, scale the v^i w^j one by xi^((p^k-1)(2i+j)/6)."""
+    return tuple(tuple(f2mul(f2conj(a[j][i]), C[2 * i + j]) for i in range(3)) for j in range(2))
+
+
+def exp_by_neg_x(f):
+    return f12conj(f12pow(f, BN_X))         # f^(-x) in the cyclotomic subgroup: inverse == conjugate
+
+
+def hard_part_chain(r):
+    y0 = exp_by_neg_x(r)
+    y1 = f12sqr(y0)
+    y2 = f12sqr(y1)
+    y3 = f12mul(y2, y1)
+    y4 = exp_by_neg_x(y3)
+    y5 = f12sqr(y4)
+    y6 = exp_by_neg_x(y5)
+    y3 = f12conj(y3)
+    y6 = f12conj(y6)
+    y7 = f12mul(y6, y4)
+    y8 = f12mul(y7, y3)
+    y9 = f12mul(y8, y1)
+    y10 = f12mul(y8, y4)
+    y11 = f12mul(y10, r)
+    y12 = f12frob_odd(y9, G1C)
+    y13 = f12mul(y12, y11)
+    y8 = f12frob2(y8)
+    y14 = f12mul(y8, y13)
+    r = f12conj(r)
+    y15 = f12mul(r, y9)
+    y15 = f12frob_odd(y15, G3C)
+    return f12mul(y15, y14)
+
+
+def proto_fast():
+    x = (((3, 5), (7, 11), (13, 17)), ((19, 23), (29, 31), (37, 41)))
+    assert f12frob_odd(x, G1C) == f12pow(x, P) and f12frob_odd(x, G3C) == f12pow(x, P ** 3)
+    Pt, Q = O.G1.mul(O.G1_GEN, 12345), O.G2.mul(O.G2_GEN, 67890)
+    f = miller(Pt, Q)
+    f1 = f12mul(f12conj(f), f12inv(f))
+    f2 = f12mul(f12frob2(f1), f1)
+    slow = f12pow(f2, HARD)
+    fast = hard_part_chain(f2)
+    k = next((k for k in range(1, 40) if f12pow(slow, k) == fast), None)
+    print("fast hard part == slow hard part ^", k)
+    Rm = 1 << 256
+    for name, C in (("FROB1", G1C), ("FROB3", G3C)):
+        for i in range(1, 6):
+            print(f"{name}_{i}_C0 {limbs(C[i][0] * Rm % P)}\n{name}_{i}_C1 {limbs(C[i][1] * Rm % P)}")
+    print("BN_X", hex(BN_X), bin(BN_X).count("1"))
+    # subgroup test used on the device: psi(P) == [6 x^2] P  for P in G2 and not for a point outside it
+    psi = lambda T: (f2mul(f2conj(T[0]), TW_X), f2mul(f2conj(T[1]), TW_Y))
+    assert psi(Q) == O.G2.mul(Q, 6 * BN_X * BN_X)
+    # a curve point outside the r-torsion (the twist has a large cofactor): the psi test must reject it
+    def f2sqrt(a):                      # p = 3 mod 4 (Adj / Rodriguez-Henriquez, Alg. 9)
+        a1 = f2pow(a, (P - 3) // 4)
+        alpha = f2mul(a1, f2mul(a1, a))
+        x0 = f2mul(a1, a)
+        if alpha == ((-1) % P, 0):
+            x = f2mul((0, 1), x0)
+        else:
+            x = f2mul(f2pow(f2add(F2_ONE, alpha), (P - 1) // 2), x0)
+        return x if f2sqr(x) == a else None
+    for t in range(1, 50):
+        xx = (t, 1)
+        rhs = f2add(f2mul(f2sqr(xx), xx), B_TWIST)
+        y = f2sqrt(rhs)
+        if y is not None:
+            T = (xx, y)
+            assert O.G2.on_curve(T)
+            in_sub = O.G2.mul(T, R) is None
+            print("off-subgroup point found:", not in_sub, "psi test rejects it:", psi(T) != O.G2.mul(T, 6 * BN_X * BN_X))
+            print("OFFSUB", O.g2_to_bytes(T).hex())
+            break
+
+
+if __name__ == "__main__":
+    proto_fast()
