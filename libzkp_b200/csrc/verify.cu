@@ -5,6 +5,7 @@
 // here once per key at lzkp_vk_load —, the public-input accumulation and verify_with_processed_vk:
 //     e(A, B) * e(vk_x, -gamma) * e(C, -delta) == e(alpha, beta),   vk_x = gamma_abc[0] + sum_i x_i gamma_abc[i+1].
 // One proof per thread: three Miller loops sharing their squarings, one final exponentiation.
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -44,13 +45,17 @@ __device__ __noinline__ bool read_g1_checked(const uint8_t *b, G1Affine &p) {
     if (f1 & 1u) { p = G1Affine::inf(); return ok; }        // infinity flag (bit 6 of the last byte)
     return ok && g1_on_curve(p);
 }
-__device__ __noinline__ bool read_g2_checked(const uint8_t *b, G2Affine &p) {
+__device__ __noinline__ bool read_g2_on_curve(const uint8_t *b, G2Affine &p) {
     uint32_t f0, f1, f2, f3;
     bool ok = read_fq_canonical(b, p.x.c0, f0) & read_fq_canonical(b + 32, p.x.c1, f1) &
               read_fq_canonical(b + 64, p.y.c0, f2) & read_fq_canonical(b + 96, p.y.c1, f3);
     if (f0 | f1 | f2) ok = false;
     if (f3 & 1u) { p = G2Affine::inf(); return ok; }
-    if (!ok || !g2_on_curve(p)) return false;
+    return ok && g2_on_curve(p);
+}
+__device__ __noinline__ bool read_g2_checked(const uint8_t *b, G2Affine &p) {
+    if (!read_g2_on_curve(b, p)) return false;
+    if (p.is_inf()) return true;
     // subgroup check (deserialize_uncompressed validates it).  On BN curves the untwist-Frobenius-twist map psi
     // acts on G2 as multiplication by p = t - 1 = 6 x^2 (mod r), and psi(P) == [6 x^2] P characterises G2 among the
     // points of the twist (the test gnark-crypto uses for bn254): a 127-bit ladder instead of a 254-bit one.
@@ -106,6 +111,70 @@ __global__ void __launch_bounds__(64) k_verify(const VkDev *__restrict__ vk, con
     multi_miller_loop<3>(f, P, Q, skip);
     final_exponentiation(e, f);
     ok[p] = f12_eq(e, vk->alpha_beta) ? 1 : 0;
+}
+
+// The same decision with the independent strands of one proof on four warps of the CTA (warp-uniform roles,
+// lane = proof): the three Miller loops and the G2 subgroup test run side by side, then warp 0 multiplies the three
+// Miller values, runs the final exponentiation and compares.  Shortens the dependent chain of a proof ~3x.
+//   warp 0: A, B (curve checks), Miller(A, B)           warp 2: C, Miller(C, -delta)
+//   warp 1: vk_x, Miller(vk_x, -gamma)                   warp 3: B in the r-torsion subgroup?
+__global__ void __launch_bounds__(128) k_verify4(const VkDev *__restrict__ vk, const G1Affine *__restrict__ gamma_abc,
+                                                 uint32_t n_pub, const uint8_t *__restrict__ proofs,
+                                                 const Fr *__restrict__ inputs, uint32_t n, uint8_t *__restrict__ ok) {
+    extern __shared__ uint4 smem_raw[];
+    Fq12 *sf = reinterpret_cast<Fq12 *>(smem_raw);                       // [2][32] Miller values of warps 1, 2
+    __shared__ uint8_t sgood[4][32];
+    const uint32_t role = threadIdx.x >> 5, lane = threadIdx.x & 31, p = blockIdx.x * 32 + lane;
+    const bool live = p < n;
+    const uint8_t *pb = proofs + (size_t)p * 256;
+    Fq12 f;
+    bool good = true;
+    if (live) {
+        G1Affine P[1];
+        G2Affine Q[1];
+        bool skip[1];
+        if (role == 0) {
+            good = read_g1_checked(pb, P[0]);
+            good = read_g2_on_curve(pb + 64, Q[0]) && good;
+            skip[0] = !good || P[0].is_inf() || Q[0].is_inf();
+            multi_miller_loop<1>(f, P, Q, skip);
+        } else if (role == 1) {
+            G1XYZZ acc = G1XYZZ::from_affine(ldg_vec(gamma_abc));
+            const Fr *x = inputs + (size_t)p * n_pub;
+#pragma unroll 1
+            for (uint32_t i = 0; i < n_pub; i++) {
+                Fr xi = ld_vec(x + i);
+                if (!fr_is_canonical(xi)) { good = false; continue; }
+                if (xi.is_zero()) continue;
+                acc.add_cold(scalar_mul(G1XYZZ::from_affine(ldg_vec(gamma_abc + 1 + i)), xi));
+            }
+            P[0] = acc.to_affine();
+            Q[0] = vk->gamma_neg;
+            skip[0] = !good || P[0].is_inf() || Q[0].is_inf();
+            multi_miller_loop<1>(f, P, Q, skip);
+            sf[lane] = f;
+        } else if (role == 2) {
+            good = read_g1_checked(pb + 192, P[0]);
+            Q[0] = vk->delta_neg;
+            skip[0] = !good || P[0].is_inf() || Q[0].is_inf();
+            multi_miller_loop<1>(f, P, Q, skip);
+            sf[32 + lane] = f;
+        } else {
+            G2Affine B;
+            good = read_g2_checked(pb + 64, B);
+        }
+    }
+    sgood[role][lane] = good ? 1 : 0;
+    __syncthreads();
+    if (role == 0 && live) {
+        good = sgood[0][lane] && sgood[1][lane] && sgood[2][lane] && sgood[3][lane];
+        if (!good) { ok[p] = 0; return; }
+        Fq12 t, e;
+        f12_mul(t, f, sf[lane]);
+        f12_mul(f, t, sf[32 + lane]);
+        final_exponentiation(e, f);
+        ok[p] = f12_eq(e, vk->alpha_beta) ? 1 : 0;
+    }
 }
 
 __global__ void k_fq_mont(Fq *v, size_t count) {
@@ -178,8 +247,14 @@ int verify_batch(VerifyingKeyDev *V, size_t n, const uint8_t *proofs, const uint
     TRY(d_p.alloc(n * 256)); TRY(d_x.alloc(n * std::max<size_t>(n_pub, 1) * 32)); TRY(d_ok.alloc(n));
     CUDA_TRY(cudaMemcpy(d_p.p, proofs, n * 256, cudaMemcpyHostToDevice));
     if (n_pub) CUDA_TRY(cudaMemcpy(d_x.p, inputs, n * n_pub * 32, cudaMemcpyHostToDevice));
-    LAUNCH(k_verify, (unsigned)((n + 63) / 64), 64, 0, 0, V->vk.as<VkDev>(), V->gamma_abc.as<G1Affine>(), (uint32_t)n_pub,
-           d_p.as<uint8_t>(), d_x.as<Fr>(), (uint32_t)n, d_ok.as<uint8_t>());
+    static const bool one_thread = getenv("LZKP_VERIFY_ONE_THREAD") != nullptr;     // the single-strand kernel, kept for comparison
+    if (one_thread) {
+        LAUNCH(k_verify, (unsigned)((n + 63) / 64), 64, 0, 0, V->vk.as<VkDev>(), V->gamma_abc.as<G1Affine>(), (uint32_t)n_pub,
+               d_p.as<uint8_t>(), d_x.as<Fr>(), (uint32_t)n, d_ok.as<uint8_t>());
+    } else {
+        LAUNCH(k_verify4, (unsigned)((n + 31) / 32), 128, 64 * sizeof(Fq12), 0, V->vk.as<VkDev>(), V->gamma_abc.as<G1Affine>(),
+               (uint32_t)n_pub, d_p.as<uint8_t>(), d_x.as<Fr>(), (uint32_t)n, d_ok.as<uint8_t>());
+    }
     CUDA_TRY(cudaMemcpy(ok_out, d_ok.p, n, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaGetLastError());
     return LZKP_OK;
