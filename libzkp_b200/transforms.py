@@ -187,6 +187,33 @@ def bench_mixed(torch, dev, n=8192, iters=3):
     return out
 
 
+def bench_verify(torch, dev, n=4096, iters=3):
+    """Batched device verification (lzkp_verify_batch) of n equality proofs produced by the engine, host buffers."""
+    import time
+    pk_bytes, vk_bytes = engine.setup_builtin(engine.EQUALITY, 110, _toxic(1))
+    pk = engine.ProvingKey(pk_bytes, window_bits=12)
+    pk.circuit_builtin(engine.EQUALITY, 110)
+    rng = np.random.default_rng(3)
+    a = rng.integers(0, 2**63, size=n, dtype=np.uint64)
+    fr = lambda seed: _uniform_fr(torch, dev, n, seed).cpu().numpy().view(np.uint8).reshape(n, 32)
+    proofs, cms, st = pk.prove_equality_batch(a, a, fr(1), fr(2))
+    pk.close()
+    vk = engine.VerifyingKey(vk_bytes)
+    out = {}
+    for nb in (1, n):
+        ok = vk.verify_batch(proofs[:nb], cms[:nb])
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            ok = vk.verify_batch(proofs[:nb], cms[:nb])
+        dt = (time.perf_counter() - t0) / iters
+        out[f"batch_{nb}"] = {"ms": 1e3 * dt, "verifies_per_s": nb / dt, "all_accepted": bool(ok.all())}
+    bad = cms.copy()
+    bad[:, 0] ^= 1
+    out["wrong_inputs_rejected"] = bool(not vk.verify_batch(proofs[:64], bad[:64]).any())
+    vk.close()
+    return out
+
+
 def bench(torch, dev, imad_peak, hbm_gbs):
     return {"msm_g1_2^20": bench_msm(torch, dev, imad_peak, 20, 1),
             "msm_g1_2^20_witness_like": bench_msm(torch, dev, imad_peak, 20, 1, witness_like=True),
@@ -198,4 +225,5 @@ def bench(torch, dev, imad_peak, hbm_gbs):
             "membership_batch_1024": bench_membership(torch, dev),
             "membership_1024_slots_batch_1024": bench_membership(torch, dev, iters=2, slots=1024),
             "mixed_batch_8192": bench_mixed(torch, dev),
+            "verify_batch": bench_verify(torch, dev),
             "proof_2^20_constraints": bench_large_proof(torch, dev)}
