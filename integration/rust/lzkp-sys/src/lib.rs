@@ -10,6 +10,10 @@ pub struct lzkp_pk {
     _private: [u8; 0],
 }
 #[repr(C)]
+pub struct lzkp_vk {
+    _private: [u8; 0],
+}
+#[repr(C)]
 #[derive(Default, Clone, Copy)]
 pub struct lzkp_pk_options {
     pub window_bits: c_int,
@@ -40,6 +44,17 @@ extern "C" {
                                        set_len: *const u32, set_stride: u32, commitments: *const u8,
                                        r: *const u8, s: *const u8, proofs_out: *mut u8,
                                        commitments_out: *mut u8, status: *mut i32) -> c_int;
+    pub fn lzkp_prove_equality_enveloped(pk: *mut lzkp_pk, n: usize, a: *const u64, b: *const u64, r: *const u8,
+                                         s: *const u8, envelopes_out: *mut u8, envelope_len: *mut u32,
+                                         status: *mut i32) -> c_int;
+    pub fn lzkp_prove_membership_enveloped(pk: *mut lzkp_pk, n: usize, value: *const u64, sets: *const u64,
+                                           set_len: *const u32, set_stride: u32, r: *const u8, s: *const u8,
+                                           envelopes_out: *mut u8, envelope_stride: u32, envelope_len: *mut u32,
+                                           status: *mut i32) -> c_int;
+    pub fn lzkp_vk_load(vk: *const u8, len: usize, out: *mut *mut lzkp_vk) -> c_int;
+    pub fn lzkp_vk_free(vk: *mut lzkp_vk);
+    pub fn lzkp_verify_batch(vk: *mut lzkp_vk, n: usize, proofs: *const u8, public_inputs: *const u8, n_pub: usize,
+                             ok_out: *mut u8) -> c_int;
     pub fn lzkp_commit_value_snark(value: u64, out: *mut u8) -> c_int;
     pub fn lzkp_msm_g1(bases: *const u8, scalars: *const u8, n: usize, out: *mut u8) -> c_int;
     pub fn lzkp_msm_g2(bases: *const u8, scalars: *const u8, n: usize, out: *mut u8) -> c_int;
