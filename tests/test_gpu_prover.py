@@ -342,3 +342,41 @@ def test_device_envelopes_equal_host_framing(eq_pk, mb_pk, frs, po):
             payload = struct.pack("<I", L) + sets[i, :L].astype("<u8").tobytes() + proofs[i].tobytes()
             want = zk.Proof(4, payload, cms[i].tobytes()).to_bytes()
             assert lens[i] == len(want) and env[i, :lens[i]].tobytes() == want
+
+
+def test_explicit_csr_circuit_and_error_paths(eq_keys, mb_keys, co, golden):
+    # lzkp_circuit_load with caller-supplied CSR matrices (what a Rust shim would pass from cs.to_matrices())
+    (m, n_inst, n_wit), mats = engine.builtin_circuit_csr(engine.EQUALITY, 110)
+    pk = engine.ProvingKey(eq_keys.pk_bytes, window_bits=WINDOW_BITS)
+    with pytest.raises(zk.EngineError):                       # proving before a circuit is bound
+        pk.prove_batch(np.zeros((1, pk.n_vars * 32), np.uint8), np.zeros((1, 32), np.uint8), np.zeros((1, 32), np.uint8))
+    with pytest.raises(zk.EngineError):                       # equality batch needs the builtin equality circuit
+        pk.prove_equality_batch(np.zeros(1, np.uint64), np.zeros(1, np.uint64), np.zeros((1, 32), np.uint8), np.zeros((1, 32), np.uint8))
+    with pytest.raises(zk.EngineError):                       # shape mismatch with the key
+        pk.circuit_load(m, n_inst + 1, n_wit - 1, mats)
+    pk.circuit_load(m, n_inst, n_wit, mats)
+    case = golden["equality"]["proofs"][0]
+    z = eq_keys.circuit.assign(case["a"], case["a"])[None]
+    proofs, status = pk.prove_batch(z, co.fr_array([int(case["r"])]), co.fr_array([int(case["s"])]))
+    assert not status.any() and proofs[0].tobytes().hex() == case["proof"]
+    pk.close()
+    # a membership key cannot take the equality circuit
+    pkm = engine.ProvingKey(mb_keys.pk_bytes, window_bits=8)
+    with pytest.raises(zk.EngineError):
+        pkm.circuit_builtin(engine.EQUALITY, 110)
+    pkm.close()
+
+
+def test_pk_validation_rejects_corrupted_keys(eq_keys):
+    good = bytearray(eq_keys.pk_bytes)
+    with pytest.raises(zk.EngineError):
+        engine.ProvingKey(bytes(good[:-7]), window_bits=8)                 # truncated
+    bad = bytearray(good)
+    off = 64 + 3 * 128 + 8 + 2 * 64 + 64 + 64 + 8 + 5 * 64                  # x of a_query[5]
+    bad[off] ^= 1
+    with pytest.raises(zk.EngineError, match="off-curve"):
+        engine.ProvingKey(bytes(bad), validate=True, window_bits=8)
+    bad = bytearray(good)
+    bad[off + 31] |= 0x3F                                                    # coordinate >= q
+    with pytest.raises(zk.EngineError):
+        engine.ProvingKey(bytes(bad), window_bits=8)
