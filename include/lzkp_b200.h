@@ -93,6 +93,10 @@ int lzkp_pk_load_ex(const uint8_t *pk_bytes, size_t len, int validate, const lzk
 void lzkp_pk_free(lzkp_pk *pk);
 /* info[0..8) = n_vars, n_inst, n_wit, domain n, window bits c, windows W, table bytes, max_chunk */
 int lzkp_pk_info(const lzkp_pk *pk, uint64_t info[8]);
+/* Work per proof on the batched path: work[0] / work[1] = (base, window) units of the G1 / G2 table MSMs, i.e. the
+ * mixed additions one proof performs (identity points of the key are dropped at load and are not counted);
+ * work[2] / work[3] = table rows (distinct bases).  Zeros for a large-domain key. */
+int lzkp_pk_work(const lzkp_pk *pk, uint64_t work[4]);
 
 /* R1CS matrices, once per circuit: CSR with m rows over z = instance || witness (column 0 = One);
  * coefficients 32 B canonical LE. */

@@ -929,6 +929,12 @@ int lzkp_pk_info(const lzkp_pk *pk, uint64_t info[8]) {
     return LZKP_OK;
 }
 
+int lzkp_pk_work(const lzkp_pk *pk, uint64_t work[4]) {
+    if (!pk || !work) return fail(LZKP_E_INVALID, "null argument");
+    work[0] = pk->g1.n_units; work[1] = pk->g2.n_units; work[2] = pk->g1.n_rows; work[3] = pk->g2.n_rows;
+    return LZKP_OK;
+}
+
 int lzkp_circuit_load(lzkp_pk *pk, uint32_t m, uint32_t n_inst, uint32_t n_wit, const uint32_t *a_rowptr,
                       const uint32_t *a_col, const uint8_t *a_val, const uint32_t *b_rowptr, const uint32_t *b_col,
                       const uint8_t *b_val, const uint32_t *c_rowptr, const uint32_t *c_col, const uint8_t *c_val) {

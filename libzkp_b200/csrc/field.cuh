@@ -394,10 +394,15 @@ struct Fq2 {
     LZ_HD friend Fq2 operator-(const Fq2 &a, const Fq2 &b) { return Fq2{a.c0 - b.c0, a.c1 - b.c1}; }
     LZ_HD Fq2 neg() const { return Fq2{c0.neg(), c1.neg()}; }
     LZ_HD Fq2 dbl() const { return Fq2{c0.dbl(), c1.dbl()}; }
-    LZ_HD friend Fq2 operator*(const Fq2 &a, const Fq2 &b) {   // Karatsuba, 3 Fq products
-        Fq v0 = a.c0 * b.c0, v1 = a.c1 * b.c1;
+    LZ_HD friend Fq2 operator*(const Fq2 &a, const Fq2 &b) {
+#ifdef LZKP_FQ2_SCHOOLBOOK
+        // four independent products, two additions: more multiplies than Karatsuba but no dependent add chains
+        return Fq2{a.c0 * b.c0 - a.c1 * b.c1, a.c0 * b.c1 + a.c1 * b.c0};
+#else
+        Fq v0 = a.c0 * b.c0, v1 = a.c1 * b.c1;                 // Karatsuba, 3 Fq products
         Fq s = (a.c0 + a.c1) * (b.c0 + b.c1);
         return Fq2{v0 - v1, s - v0 - v1};
+#endif
     }
     LZ_HD Fq2 sqr() const {                                     // 2 Fq products
         Fq m = c0 * c1;

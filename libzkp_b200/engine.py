@@ -133,6 +133,12 @@ class ProvingKey:
         (self.n_vars, self.n_inst, self.n_wit, self.n, self.window_bits, self.windows, self.table_bytes,
          self.max_chunk) = [int(x) for x in info]
 
+    def work(self):
+        """(G1 units, G2 units, G1 table rows, G2 table rows): mixed additions per proof on the batched path."""
+        w = (C.c_uint64 * 4)()
+        check(lib().lzkp_pk_work(self._h, w))
+        return tuple(int(x) for x in w)
+
     def close(self):
         if self._h:
             lib().lzkp_pk_free(self._h)
