@@ -281,3 +281,37 @@ def proto_fast():
 
 if __name__ == "__main__":
     proto_fast()
+
+
+# ---------------------------------------------------------------- Granger-Scott squaring in the cyclotomic subgroup
+def f12cyclo_sqr(a):
+    r0, r4, r3 = a[0]
+    r2, r1, r5 = a[1]
+    def sq(x, y):                 # (x + y*s)^2 over Fq2[s]/(s^2 - xi): returns (t0, t1)
+        tmp = f2mul(x, y)
+        t0 = f2sub(f2sub(f2mul(f2add(x, y), f2add(f2mul(XI, y), x)), tmp), f2mul(XI, tmp))
+        return t0, f2add(tmp, tmp)
+    t0, t1 = sq(r0, r1)
+    t2, t3 = sq(r2, r3)
+    t4, t5 = sq(r4, r5)
+    three_minus = lambda t, z: f2add(f2add(f2sub(t, z), f2sub(t, z)), t)     # 3t - 2z
+    three_plus = lambda t, z: f2add(f2add(f2add(t, z), f2add(t, z)), t)      # 3t + 2z
+    z0 = three_minus(t0, r0)
+    z1 = three_plus(t1, r1)
+    z2 = three_plus(f2mul(XI, t5), r2)
+    z3 = three_minus(t4, r3)
+    z4 = three_minus(t2, r4)
+    z5 = three_plus(t3, r5)
+    return ((z0, z4, z3), (z2, z1, z5))
+
+
+def proto_cyclo():
+    Pt, Q = O.G1.mul(O.G1_GEN, 777), O.G2.mul(O.G2_GEN, 999)
+    f = miller(Pt, Q)
+    f1 = f12mul(f12conj(f), f12inv(f))
+    g = f12mul(f12frob2(f1), f1)             # in the cyclotomic subgroup after the easy part
+    print("cyclotomic squaring == squaring:", f12cyclo_sqr(g) == f12sqr(g), f12cyclo_sqr(f12sqr(g)) == f12sqr(f12sqr(g)))
+
+
+if __name__ == "__main__":
+    proto_cyclo()
