@@ -56,7 +56,7 @@ extern "C" {
 typedef struct lzkp_pk lzkp_pk;
 
 typedef struct lzkp_pk_options {
-    int window_bits;          /* fixed-base table window c in [8,16]; 0 = choose from the memory budget */
+    int window_bits;          /* fixed-base table window c in [8,17]; 0 = choose from the memory budget (<= 16) */
     uint64_t table_budget_bytes; /* cap for the resident window tables; 0 = 60% of free device memory */
     uint32_t max_chunk;       /* proofs per device pass; 0 = default (8192) */
     /* Single-proof sharding over several GPUs (large domains only): this process keeps only shard

@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "liblzkp_b200.so")
+# LZKP_B200_LIB selects another build of the same library (kernel A/B runs); there is still no fallback.
+LIB_PATH = os.environ.get("LZKP_B200_LIB") or os.path.join(_HERE, "_lib", "liblzkp_b200.so")
 
 LZKP_OK = 0
 LZKP_E_INVALID = -1

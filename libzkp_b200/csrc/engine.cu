@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <mutex>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "common.h"
@@ -209,6 +210,11 @@ static int finish_plan(MsmPlan &pl, const std::vector<std::vector<BaseRef>> &msm
     return LZKP_OK;
 }
 
+// Signed c-bit windows of an Fr scalar by the offset trick (dev_util.cuh recode_offset): s + K must stay below
+// 2^(c*W) with K = sum_w 2^(c*w + c-1) < 2^(c*W - 1) * (1 + 2^(1-c)).  BN254's r is 0.756 * 2^254, so c * W >= 255
+// is enough: W = ceil(255 / c) (15 windows at c = 17, 16 at c = 16, 17 at c = 15).
+static inline uint32_t window_count(int c) { return (uint32_t)((255 + c - 1) / c); }
+
 // ------------------------------------------------------------------------ pk load
 namespace {
 struct Reader {
@@ -398,17 +404,17 @@ static int pk_load_impl(const uint8_t *bytes, size_t len, int validate, const lz
     int c = opt && opt->window_bits ? opt->window_bits : 0;
     if (const char *e = getenv("LZKP_WINDOW_BITS")) if (!c) c = atoi(e);
     auto bytes_for = [&](int cc) {
-        uint64_t W = (256 + cc - 1) / cc, N = 1ull << (cc - 1);
+        uint64_t W = window_count(cc), N = 1ull << (cc - 1);
         return (rows1.size() * 64ull + rows2.size() * 128ull) * W * N;
     };
     if (c == 0) {
         c = 16;
         while (c > 8 && bytes_for(c) > budget) c--;
     }
-    if (c < 8 || c > 16) return fail(LZKP_E_INVALID, "window_bits must be in [8,16]");
+    if (c < 8 || c > 17) return fail(LZKP_E_INVALID, "window_bits must be in [8,17]");
     if (bytes_for(c) > free_b) return fail(LZKP_E_NOMEM, "window tables do not fit in device memory");
     pk->c = c;
-    pk->W = (256 + c - 1) / c;
+    pk->W = window_count(c);
     pk->N = 1u << (c - 1);
     pk->table_bytes = bytes_for(c);
     pk->max_chunk = opt && opt->max_chunk ? opt->max_chunk : 8192;
@@ -475,7 +481,7 @@ static int pk_load_impl(const uint8_t *bytes, size_t len, int validate, const lz
     TRY(finish_plan(pk->g2, msm2, pk->W));
     // proofs per device pass: two workspaces must fit beside the tables
     {
-        const uint64_t per_proof = (uint64_t)nv * 32 + 7ull * n * 32 + (uint64_t)pk->n_dig_rows * pk->W * 2 +
+        const uint64_t per_proof = (uint64_t)nv * 32 + 7ull * n * 32 + (uint64_t)pk->n_dig_rows * pk->W * (c > 16 ? 4 : 2) +
                                    (uint64_t)pk->g1.n_items[1] * sizeof(G1XYZZ) + (uint64_t)pk->g2.n_items[0] * sizeof(G2XYZZ) +
                                    4 * sizeof(G1XYZZ) + sizeof(G2XYZZ) + 1024;
         size_t free_now = 0, total_now = 0;
@@ -574,7 +580,7 @@ static int ensure_workspace(lzkp_pk *pk, Workspace &ws, uint32_t P) {
     if (pk->large) {
         TRY(pk->L_sa.ensure(nv * 32)); TRY(pk->L_sb.ensure(nv * 32)); TRY(pk->L_sl.ensure(((size_t)pk->n_wit + 1) * 32));
     } else {
-        TRY(ws.dig.ensure((size_t)pk->n_dig_rows * pk->W * P * sizeof(int16_t)));
+        TRY(ws.dig.ensure((size_t)pk->n_dig_rows * pk->W * P * (pk->c > 16 ? 4 : 2)));
     }
     TRY(ws.r.ensure(P * 32)); TRY(ws.s.ensure(P * 32)); TRY(ws.rs.ensure(P * 32));
     TRY(ws.part1.ensure(part1 * sizeof(G1XYZZ)));
@@ -681,7 +687,8 @@ static int run_prove(lzkp_pk *pk, Workspace &ws, uint32_t P, const Fr *d_r, cons
         return LZKP_OK;
     }
     const uint32_t c = pk->c, W = pk->W, gx = (P + 127) / 128;
-    int16_t *dig = ws.dig.as<int16_t>();
+    void *dig = ws.dig.p;
+    const uint32_t dig_bytes = pk->c > 16 ? 4u : 2u;      // signed c-bit digits: int16 up to c = 16
     // One stream, stage after stage.  (Measured on B200: running the witness map and the G1 half of the assembly on
     // a side stream underneath the MSM kernels gains < 2 % without stream priority - their CTAs only get SMs in the
     // MSM kernel's last wave - and LOSES 2 % with priority, because a latency-bound CTA that holds 17k registers
@@ -691,16 +698,21 @@ static int run_prove(lzkp_pk *pk, Workspace &ws, uint32_t P, const Fr *d_r, cons
     Region reg(pk, LZKP_REGION_DIGITS, st);
     LAUNCH(k_fr_mul_canonical, gx, 128, 0, st, d_r, d_s, ws.rs.as<Fr>(), P);
     const uint32_t ymax = 32768u;
-    LAUNCH(k_digits, dim3(gx, std::min(pk->nz, ymax)), 128, 0, st, ws.z.as<Fr>(), pk->n_vars, 1u, dig, 0u, P, c, W, d_status, pk->nz);
-    LAUNCH(k_digits, dim3(gx, 1), 128, 0, st, d_r, 1u, 0u, dig, pk->nz, P, c, W, d_status, 1u);
-    LAUNCH(k_digits, dim3(gx, 1), 128, 0, st, d_s, 1u, 0u, dig, pk->nz + 1, P, c, W, d_status, 1u);
-    LAUNCH(k_digits, dim3(gx, 1), 128, 0, st, ws.rs.as<Fr>(), 1u, 0u, dig, pk->nz + 2, P, c, W, d_status, 1u);
-    LAUNCH(k_digits, dim3(gx, std::min(pk->n - 1, ymax)), 128, 0, st, ws.h.as<Fr>(), pk->n, 0u, dig, pk->nz + 3, P, c, W, d_status,
-           pk->n - 1);
+    auto digits = [&](auto *dg) -> int {
+        using DigT = std::remove_pointer_t<decltype(dg)>;
+        LAUNCH(k_digits<DigT>, dim3(gx, std::min(pk->nz, ymax)), 128, 0, st, ws.z.as<Fr>(), pk->n_vars, 1u, dg, 0u, P, c, W, d_status, pk->nz);
+        LAUNCH(k_digits<DigT>, dim3(gx, 1), 128, 0, st, d_r, 1u, 0u, dg, pk->nz, P, c, W, d_status, 1u);
+        LAUNCH(k_digits<DigT>, dim3(gx, 1), 128, 0, st, d_s, 1u, 0u, dg, pk->nz + 1, P, c, W, d_status, 1u);
+        LAUNCH(k_digits<DigT>, dim3(gx, 1), 128, 0, st, ws.rs.as<Fr>(), 1u, 0u, dg, pk->nz + 2, P, c, W, d_status, 1u);
+        LAUNCH(k_digits<DigT>, dim3(gx, std::min(pk->n - 1, ymax)), 128, 0, st, ws.h.as<Fr>(), pk->n, 0u, dg, pk->nz + 3, P, c, W, d_status,
+               pk->n - 1);
+        return LZKP_OK;
+    };
+    if (dig_bytes == 2) TRY(digits((int16_t *)dig)); else TRY(digits((int32_t *)dig));
     }
     auto args = [&](MsmPlan &pl, int iv, void *partial, void *out) {
         return BatchMsmArgs{pl.table.p, pk->N, pl.unit_dig.as<uint32_t>(), pl.unit_tbl.as<uint32_t>(), pl.items[iv].p,
-                            pl.n_items[iv], pl.msm_items[iv].p, pl.n_msm, dig, P, partial, out};
+                            pl.n_items[iv], pl.msm_items[iv].p, pl.n_msm, dig, dig_bytes, P, partial, out};
     };
     { Region reg(pk, LZKP_REGION_MSM_G1, st); batch_msm_g1(args(pk->g1, fit_variant(pk->g1, item_variant(P)), ws.part1.p, ws.res1.p), st); }
     { Region reg(pk, LZKP_REGION_MSM_G2, st); batch_msm_g2(args(pk->g2, fit_variant(pk->g2, item_variant_g2(P)), ws.part2.p, ws.res2.p), st); }

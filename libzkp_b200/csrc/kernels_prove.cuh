@@ -304,7 +304,9 @@ __global__ void k_check_canonical(const Fr *v, uint32_t count, int32_t *status) 
 // Signed c-bit digits via the offset trick: s' = s + K, K = sum_w 2^(c*w + c-1); the unsigned
 // windows u_w of s' give d_w = u_w - 2^(c-1) in [-2^(c-1), 2^(c-1)), independently per window.
 // dig[(row * W + w) * P + p].  grid (ceil(P/128), count), row = row0 + blockIdx.y.
-__global__ void __launch_bounds__(128) k_digits(const Fr *scalars, uint32_t stride, uint32_t first, int16_t *dig,
+// DigT: int16_t for c <= 16 (half the digit traffic: the digit matrix of a 4096-proof batch then stays in L2), int32_t for c = 17.
+template <class DigT>
+__global__ void __launch_bounds__(128) k_digits(const Fr *scalars, uint32_t stride, uint32_t first, DigT *dig,
                                                 uint32_t row0, uint32_t P, uint32_t c, uint32_t W, int32_t *status,
                                                 uint32_t count) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -318,7 +320,7 @@ __global__ void __launch_bounds__(128) k_digits(const Fr *scalars, uint32_t stri
         uint32_t v[10];
         recode_offset(s, c, W, v);
         const size_t base = ((size_t)(row0 + j) * W) * P + p;
-        for (uint32_t w = 0; w < W; w++) dig[base + (size_t)w * P] = (int16_t)recoded_digit(v, c, w);
+        for (uint32_t w = 0; w < W; w++) dig[base + (size_t)w * P] = (DigT)recoded_digit(v, c, w);
     }
 }
 // rs[p] = r[p] * s[p] mod r, canonical in / out

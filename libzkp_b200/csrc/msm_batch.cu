@@ -16,29 +16,49 @@ namespace lzkp {
 // contiguous run of units of one MSM.  Thread (p, item) gathers table[unit][|d|-1] for its proof's
 // digit d of every unit in the item and accumulates in XYZZ.  Lanes of a warp are 32 different proofs
 // walking the same units, so a warp-step touches one N*sizeof(point) slab (2 MiB for G1 at c=16).
-template <class F, int BLOCK>
+template <class F, int BLOCK, class DigT>
 __global__ void __launch_bounds__(BLOCK, LZKP_G2_MINB_SEL(F)) k_msm_batch(const Affine<F> *__restrict__ table, uint32_t N,
                                                      const uint32_t *__restrict__ unit_dig,
                                                      const uint32_t *__restrict__ unit_tbl,
-                                                     const uint2 *__restrict__ items, const int16_t *__restrict__ dig,
+                                                     const uint2 *__restrict__ items, const DigT *__restrict__ dig,
                                                      uint32_t P, XYZZ<F> *__restrict__ partial) {
     const uint32_t p = blockIdx.x * BLOCK + threadIdx.x, item = blockIdx.y;
     if (p >= P) return;
     const uint2 range = items[item];
     XYZZ<F> acc = XYZZ<F>::inf();
-    int d = dig[(size_t)__ldg(unit_dig + range.x) * P + p];
-    Affine<F> pt = Affine<F>::inf();
-    if (d) pt = gather_point(table, N, __ldg(unit_tbl + range.x), d);
-    for (uint32_t u = range.x; u < range.y; u++) {
-        int dn = 0;
-        Affine<F> ptn = Affine<F>::inf();
-        if (u + 1 < range.y) {
-            dn = dig[(size_t)__ldg(unit_dig + u + 1) * P + p];
+    // Software pipeline: digit -> address -> point is a dependent chain of two memory latencies; the point of unit
+    // u+1 is in flight under the add of unit u.  With 4-byte digits (c = 17) the digit matrix of a large batch no
+    // longer stays in L2, so the G1 kernel also keeps the digit of unit u+2 in flight (measured -2 %; the G2 kernel
+    // sits at 255 registers and loses more to the extra live value than it gains).
+    if constexpr (sizeof(F) == sizeof(Fq) && sizeof(DigT) == 4) {
+        auto digit_of = [&](uint32_t u) { return u < range.y ? (int)dig[(size_t)__ldg(unit_dig + u) * P + p] : 0; };
+        int d = digit_of(range.x), dn = digit_of(range.x + 1);
+        Affine<F> pt = Affine<F>::inf();
+        if (d) pt = gather_point(table, N, __ldg(unit_tbl + range.x), d);
+        for (uint32_t u = range.x; u < range.y; u++) {
+            const int dnn = digit_of(u + 2);
+            Affine<F> ptn = Affine<F>::inf();
             if (dn) ptn = gather_point(table, N, __ldg(unit_tbl + u + 1), dn);
+            if (d) acc.madd(pt);
+            d = dn;
+            dn = dnn;
+            pt = ptn;
         }
-        if (d) acc.madd(pt);
-        d = dn;
-        pt = ptn;
+    } else {
+        int d = dig[(size_t)__ldg(unit_dig + range.x) * P + p];
+        Affine<F> pt = Affine<F>::inf();
+        if (d) pt = gather_point(table, N, __ldg(unit_tbl + range.x), d);
+        for (uint32_t u = range.x; u < range.y; u++) {
+            int dn = 0;
+            Affine<F> ptn = Affine<F>::inf();
+            if (u + 1 < range.y) {
+                dn = dig[(size_t)__ldg(unit_dig + u + 1) * P + p];
+                if (dn) ptn = gather_point(table, N, __ldg(unit_tbl + u + 1), dn);
+            }
+            if (d) acc.madd(pt);
+            d = dn;
+            pt = ptn;
+        }
     }
     st_vec(partial + (size_t)item * P + p, acc);
 }
@@ -75,8 +95,12 @@ namespace eng {
 // gather + accumulate the items [item0, item0 + count) (partial sums land at their global item index)
 void batch_msm_g1_items(const BatchMsmArgs &a, uint32_t item0, uint32_t count, cudaStream_t st) {
     if (!count) return;
-    LAUNCH((k_msm_batch<Fq, 128>), dim3((a.P + 127) / 128, count), 128, 0, st, (const G1Affine *)a.table, a.N, a.unit_dig,
-           a.unit_tbl, (const uint2 *)a.items + item0, a.dig, a.P, (G1XYZZ *)a.partial + (size_t)item0 * a.P);
+    if (a.dig_bytes == 2)
+        LAUNCH((k_msm_batch<Fq, 128, int16_t>), dim3((a.P + 127) / 128, count), 128, 0, st, (const G1Affine *)a.table, a.N, a.unit_dig,
+               a.unit_tbl, (const uint2 *)a.items + item0, (const int16_t *)a.dig, a.P, (G1XYZZ *)a.partial + (size_t)item0 * a.P);
+    else
+        LAUNCH((k_msm_batch<Fq, 128, int32_t>), dim3((a.P + 127) / 128, count), 128, 0, st, (const G1Affine *)a.table, a.N, a.unit_dig,
+               a.unit_tbl, (const uint2 *)a.items + item0, (const int32_t *)a.dig, a.P, (G1XYZZ *)a.partial + (size_t)item0 * a.P);
 }
 constexpr uint32_t kReduceFan = 8;
 void batch_msm_g1_reduce(const BatchMsmArgs &a, cudaStream_t st) {
@@ -90,8 +114,12 @@ void batch_msm_g1(const BatchMsmArgs &a, cudaStream_t st) {
     batch_msm_g1_reduce(a, st);
 }
 void batch_msm_g2(const BatchMsmArgs &a, cudaStream_t st) {
-    LAUNCH((k_msm_batch<Fq2, 64>), dim3((a.P + 63) / 64, a.n_items), 64, 0, st, (const G2Affine *)a.table, a.N,
-           a.unit_dig, a.unit_tbl, (const uint2 *)a.items, a.dig, a.P, (G2XYZZ *)a.partial);
+    if (a.dig_bytes == 2)
+        LAUNCH((k_msm_batch<Fq2, 64, int16_t>), dim3((a.P + 63) / 64, a.n_items), 64, 0, st, (const G2Affine *)a.table, a.N,
+               a.unit_dig, a.unit_tbl, (const uint2 *)a.items, (const int16_t *)a.dig, a.P, (G2XYZZ *)a.partial);
+    else
+        LAUNCH((k_msm_batch<Fq2, 64, int32_t>), dim3((a.P + 63) / 64, a.n_items), 64, 0, st, (const G2Affine *)a.table, a.N,
+               a.unit_dig, a.unit_tbl, (const uint2 *)a.items, (const int32_t *)a.dig, a.P, (G2XYZZ *)a.partial);
     LAUNCH((k_msm_reduce1<Fq2>), dim3((a.P + 127) / 128, a.n_msm, 2 * kReduceFan), 128, 0, st, (G2XYZZ *)a.partial,
            (const uint2 *)a.msm_items, a.P, 2 * kReduceFan);
     LAUNCH((k_msm_reduce<Fq2>), dim3((a.P + 127) / 128, a.n_msm), 128, 0, st, (const G2XYZZ *)a.partial,

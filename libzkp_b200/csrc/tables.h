@@ -19,7 +19,8 @@ struct BatchMsmArgs {
     uint32_t n_items;
     const void *msm_items;        // uint2[n_msm]
     uint32_t n_msm;
-    const int16_t *dig;
+    const void *dig;             // int16_t[...] if dig_bytes == 2 (c <= 16), int32_t[...] if 4
+    uint32_t dig_bytes;
     uint32_t P;
     void *partial;                // XYZZ<F>[n_items * P]
     void *out;                    // XYZZ<F>[n_msm * P]

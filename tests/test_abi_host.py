@@ -217,3 +217,18 @@ def test_builtin_witness_equals_oracle(co):
         assert np.array_equal(engine.builtin_witness(engine.MEMBERSHIP, 64, v, set_=s), m.assign(v, set_=s))
     with pytest.raises(zk.EngineError):
         engine.builtin_witness(engine.MEMBERSHIP, 64, 7, set_=[1, 2, 3])
+
+
+def test_window_count_covers_every_scalar():
+    # engine.cu window_count(): W = ceil(255 / c) windows of the offset recoding (dev_util.cuh recode_offset) need
+    # s + K < 2^(c*W) for every canonical s, with K = sum_w 2^(c*w + c-1); holds for BN254's r, and W-1 would not do.
+    r = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+    for c in range(8, 18):
+        W = (255 + c - 1) // c
+        K = sum(1 << (c * w + c - 1) for w in range(W))
+        assert (r - 1) + K < 1 << (c * W), c
+        digits = [(((r - 1) + K) >> (c * w)) % (1 << c) - (1 << (c - 1)) for w in range(W)]
+        assert sum(d << (c * w) for w, d in enumerate(digits)) == r - 1
+        assert all(-(1 << (c - 1)) <= d < (1 << (c - 1)) for d in digits)
+        K1 = sum(1 << (c * w + c - 1) for w in range(W - 1))
+        assert not (r - 1) + K1 < 1 << (c * (W - 1)), c

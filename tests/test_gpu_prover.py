@@ -237,11 +237,13 @@ def test_seeded_rng_gives_reproducible_bytes(api, po, eq_keys, co):
     assert p1 == co.prove(eq_keys.circuit, eq_keys.opk, z, r, s)
 
 
-def test_window_sizes_agree(eq_keys, co, frs):
+def test_window_sizes_agree(eq_keys, co, frs, po):
     a = np.arange(1, 9, dtype=np.uint64)
     r, s = frs(31, 8), frs(32, 8)
+    top = np.frombuffer((po.R_MOD - 1).to_bytes(32, "little"), np.uint8)
+    r[0], s[1], r[2], s[2] = top, top, top, top      # largest canonical scalars: worst case of the offset recoding
     want, _ = co.prove_batch(eq_keys.circuit, eq_keys.opk, a, a, None, None, r, s)
-    for c in (8, 11, 16):
+    for c in (8, 11, 15, 16, 17):                    # 17: 4-byte digits, 15 windows
         pk = engine.ProvingKey(eq_keys.pk_bytes, window_bits=c)
         pk.circuit_builtin(engine.EQUALITY, 110)
         assert pk.window_bits == c
