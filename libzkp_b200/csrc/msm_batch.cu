@@ -5,7 +5,7 @@
 #include "dev_util.cuh"
 
 #ifndef LZKP_G2_MINB
-#define LZKP_G2_MINB 4
+#define LZKP_G2_MINB 6
 #endif
 // minimum resident CTAs per SM: G1 kernels leave it to ptxas, G2 kernels (64-thread CTAs) trade registers for warps
 #define LZKP_G2_MINB_SEL(F) (sizeof(F) == sizeof(::lzkp::Fq) ? 1 : LZKP_G2_MINB)

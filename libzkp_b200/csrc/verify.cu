@@ -155,6 +155,7 @@ namespace eng {
 
 struct VerifyingKeyDev {
     DBuf vk, gamma_abc;
+    DBuf d_p, d_x, d_ok;          // grow-only staging of a batch (calls on one key serialize on mu)
     uint32_t n_pub = 0;
     std::mutex mu;
 };
@@ -209,8 +210,8 @@ int verify_batch(VerifyingKeyDev *V, size_t n, const uint8_t *proofs, const uint
         return LZKP_OK;
     }
     if (n == 0) return LZKP_OK;
-    DBuf d_p, d_x, d_ok;
-    TRY(d_p.alloc(n * 256)); TRY(d_x.alloc(n * std::max<size_t>(n_pub, 1) * 32)); TRY(d_ok.alloc(n));
+    DBuf &d_p = V->d_p, &d_x = V->d_x, &d_ok = V->d_ok;
+    TRY(d_p.ensure(n * 256)); TRY(d_x.ensure(n * std::max<size_t>(n_pub, 1) * 32)); TRY(d_ok.ensure(n));
     CUDA_TRY(cudaMemcpy(d_p.p, proofs, n * 256, cudaMemcpyHostToDevice));
     if (n_pub) CUDA_TRY(cudaMemcpy(d_x.p, inputs, n * n_pub * 32, cudaMemcpyHostToDevice));
     LAUNCH(k_verify4, (unsigned)((n + 31) / 32), 128, 64 * sizeof(Fq12), 0, V->vk.as<VkDev>(), V->gamma_abc.as<G1Affine>(),
