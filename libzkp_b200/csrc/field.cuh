@@ -186,6 +186,183 @@ LZ_HD uint32_t sub8(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b
 }
 
 // --------------------------------------------------------------------------
+// Double-width arithmetic (lazy reduction in Fq2): a 16-limb product without reduction, and the Montgomery reduction
+// of a 16-limb value, so that c0 = a0 b0 - a1 b1 and c1 = (a0+a1)(b0+b1) - a0 b0 - a1 b1 take three multiplications
+// and TWO reductions (336 multiply-adds) instead of three full Montgomery products (408).
+// --------------------------------------------------------------------------
+// A[W..W+7] += (s0,s1,s2,s3) * k as one carry chain (pair t lands on A[W+2t], A[W+2t+1]); returns the carry out.
+template <int W>
+LZ_HD uint32_t row_mad_at(uint32_t (&A)[16], uint32_t s0, uint32_t s1, uint32_t s2, uint32_t s3, uint32_t k) {
+    uint32_t cy;
+#ifdef __CUDA_ARCH__
+    asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "+r"(A[W + 0]), "+r"(A[W + 1]), "+r"(A[W + 2]), "+r"(A[W + 3]), "+r"(A[W + 4]), "+r"(A[W + 5]), "+r"(A[W + 6]),
+          "+r"(A[W + 7]), "=r"(cy)
+        : "r"(s0), "r"(s1), "r"(s2), "r"(s3), "r"(k));
+#else
+    const uint32_t s[4] = {s0, s1, s2, s3};
+    uint64_t c = 0;
+    for (int t = 0; t < 4; t++) {
+        uint64_t pr = (uint64_t)s[t] * k;
+        uint64_t lo = (uint64_t)A[W + 2 * t] + (uint32_t)pr + c;
+        A[W + 2 * t] = (uint32_t)lo;
+        uint64_t hi = (uint64_t)A[W + 2 * t + 1] + (uint32_t)(pr >> 32) + (lo >> 32);
+        A[W + 2 * t + 1] = (uint32_t)hi;
+        c = hi >> 32;
+    }
+    cy = (uint32_t)c;
+#endif
+    return cy;
+}
+// One b-limb of the wide product: products a_j * b_i sit at limb position i + j.  E holds the pairs that start on
+// even positions, O those that start on odd positions (O[k] is position k + 1).  Windows advance by two limbs every
+// two rows, so the carry out of a row always lands on a limb nothing has written yet.
+template <int I>
+LZ_HD void wide_row(uint32_t (&E)[16], uint32_t (&O)[16], const uint32_t (&a)[8], uint32_t k) {
+    if (I % 2 == 0) {
+        uint32_t ce = row_mad_at<I>(E, a[0], a[2], a[4], a[6], k);
+        uint32_t co = row_mad_at<I>(O, a[1], a[3], a[5], a[7], k);
+        if (I + 8 < 16) { E[I + 8] = ce; O[I + 8] = co; }
+    } else {
+        uint32_t co = row_mad_at<I - 1>(O, a[0], a[2], a[4], a[6], k);
+        uint32_t ce = row_mad_at<I + 1>(E, a[1], a[3], a[5], a[7], k);
+        if (I + 7 < 16) O[I + 7] = co;
+        if (I + 9 < 16) E[I + 9] = ce;
+    }
+}
+// T = a * b (16 limbs), a, b < 2^256
+LZ_HD void mul_wide(uint32_t (&T)[16], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+    uint32_t E[16], O[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) { E[i] = 0; O[i] = 0; }
+    wide_row<0>(E, O, a, b[0]); wide_row<1>(E, O, a, b[1]); wide_row<2>(E, O, a, b[2]); wide_row<3>(E, O, a, b[3]);
+    wide_row<4>(E, O, a, b[4]); wide_row<5>(E, O, a, b[5]); wide_row<6>(E, O, a, b[6]); wide_row<7>(E, O, a, b[7]);
+    // T = E + (O << 32)
+    T[0] = E[0];
+#ifdef __CUDA_ARCH__
+    asm("add.cc.u32 %0, %15, %30;\n\t"
+        "addc.cc.u32 %1, %16, %31;\n\t"
+        "addc.cc.u32 %2, %17, %32;\n\t"
+        "addc.cc.u32 %3, %18, %33;\n\t"
+        "addc.cc.u32 %4, %19, %34;\n\t"
+        "addc.cc.u32 %5, %20, %35;\n\t"
+        "addc.cc.u32 %6, %21, %36;\n\t"
+        "addc.cc.u32 %7, %22, %37;\n\t"
+        "addc.cc.u32 %8, %23, %38;\n\t"
+        "addc.cc.u32 %9, %24, %39;\n\t"
+        "addc.cc.u32 %10, %25, %40;\n\t"
+        "addc.cc.u32 %11, %26, %41;\n\t"
+        "addc.cc.u32 %12, %27, %42;\n\t"
+        "addc.cc.u32 %13, %28, %43;\n\t"
+        "addc.u32 %14, %29, %44;"
+        : "=r"(T[1]), "=r"(T[2]), "=r"(T[3]), "=r"(T[4]), "=r"(T[5]), "=r"(T[6]), "=r"(T[7]), "=r"(T[8]), "=r"(T[9]),
+          "=r"(T[10]), "=r"(T[11]), "=r"(T[12]), "=r"(T[13]), "=r"(T[14]), "=r"(T[15])
+        : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(E[8]), "r"(E[9]), "r"(E[10]),
+          "r"(E[11]), "r"(E[12]), "r"(E[13]), "r"(E[14]), "r"(E[15]),
+          "r"(O[0]), "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]), "r"(O[8]), "r"(O[9]),
+          "r"(O[10]), "r"(O[11]), "r"(O[12]), "r"(O[13]), "r"(O[14]));
+#else
+    uint64_t c = 0;
+    for (int i = 1; i < 16; i++) {
+        c += (uint64_t)E[i] + O[i - 1];
+        T[i] = (uint32_t)c;
+        c >>= 32;
+    }
+#endif
+}
+// r = a + b / a - b over 16 limbs; return carry / borrow
+LZ_HD uint32_t add16(uint32_t (&r)[16], const uint32_t (&a)[16], const uint32_t (&b)[16]) {
+    uint32_t lo_a[8], lo_b[8], hi_a[8], hi_b[8], lo[8], hi[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { lo_a[i] = a[i]; lo_b[i] = b[i]; hi_a[i] = a[i + 8]; hi_b[i] = b[i + 8]; }
+    uint32_t c = add8(lo, lo_a, lo_b);
+    // hi = hi_a + hi_b + c
+    uint32_t cv[8] = {c, 0, 0, 0, 0, 0, 0, 0}, t[8];
+    uint32_t c1 = add8(t, hi_a, cv);
+    uint32_t c2 = add8(hi, t, hi_b);
+#pragma unroll
+    for (int i = 0; i < 8; i++) { r[i] = lo[i]; r[i + 8] = hi[i]; }
+    return c1 | c2;
+}
+LZ_HD uint32_t sub16(uint32_t (&r)[16], const uint32_t (&a)[16], const uint32_t (&b)[16]) {
+    uint32_t bw;
+#ifdef __CUDA_ARCH__
+    asm("sub.cc.u32 %0, %17, %33;\n\t"
+        "subc.cc.u32 %1, %18, %34;\n\t"
+        "subc.cc.u32 %2, %19, %35;\n\t"
+        "subc.cc.u32 %3, %20, %36;\n\t"
+        "subc.cc.u32 %4, %21, %37;\n\t"
+        "subc.cc.u32 %5, %22, %38;\n\t"
+        "subc.cc.u32 %6, %23, %39;\n\t"
+        "subc.cc.u32 %7, %24, %40;\n\t"
+        "subc.cc.u32 %8, %25, %41;\n\t"
+        "subc.cc.u32 %9, %26, %42;\n\t"
+        "subc.cc.u32 %10, %27, %43;\n\t"
+        "subc.cc.u32 %11, %28, %44;\n\t"
+        "subc.cc.u32 %12, %29, %45;\n\t"
+        "subc.cc.u32 %13, %30, %46;\n\t"
+        "subc.cc.u32 %14, %31, %47;\n\t"
+        "subc.cc.u32 %15, %32, %48;\n\t"
+        "subc.u32 %16, 0, 0;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(bw)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(a[8]), "r"(a[9]),
+          "r"(a[10]), "r"(a[11]), "r"(a[12]), "r"(a[13]), "r"(a[14]), "r"(a[15]),
+          "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]), "r"(b[8]), "r"(b[9]),
+          "r"(b[10]), "r"(b[11]), "r"(b[12]), "r"(b[13]), "r"(b[14]), "r"(b[15]));
+    bw &= 1u;
+#else
+    uint64_t c = 0;
+    for (int i = 0; i < 16; i++) {
+        uint64_t d = (uint64_t)a[i] - b[i] - c;
+        r[i] = (uint32_t)d;
+        c = (d >> 32) & 1;
+    }
+    bw = (uint32_t)c;
+#endif
+    return bw;
+}
+
+// One-limb right shift between two rounds of reduce_wide: A0 (limb 0 of the array that becomes aligned) takes D[1];
+// D moves down two limbs and becomes the offset array; its top two limbs take (t + c2) and c with the running carry.
+LZ_HD void wide_shift(uint32_t &A0, uint32_t (&D)[8], uint32_t c2, uint32_t t, uint32_t c) {
+#ifdef __CUDA_ARCH__
+    asm("add.cc.u32 %0, %0, %2;\n\t"
+        "addc.cc.u32 %1, %3, 0;\n\t"
+        "addc.cc.u32 %2, %4, 0;\n\t"
+        "addc.cc.u32 %3, %5, 0;\n\t"
+        "addc.cc.u32 %4, %6, 0;\n\t"
+        "addc.cc.u32 %5, %7, 0;\n\t"
+        "addc.cc.u32 %6, %8, 0;\n\t"
+        "addc.cc.u32 %7, %9, %10;\n\t"
+        "addc.u32 %8, %11, 0;"
+        : "+r"(A0), "+r"(D[0]), "+r"(D[1]), "+r"(D[2]), "+r"(D[3]), "+r"(D[4]), "+r"(D[5]), "+r"(D[6]), "+r"(D[7])
+        : "r"(t), "r"(c2), "r"(c));
+#else
+    uint64_t s = (uint64_t)A0 + D[1];
+    A0 = (uint32_t)s;
+    s >>= 32;
+    for (int j = 0; j < 6; j++) {
+        s += D[j + 2];
+        D[j] = (uint32_t)s;
+        s >>= 32;
+    }
+    s += (uint64_t)t + c2;
+    D[6] = (uint32_t)s;
+    s >>= 32;
+    D[7] = (uint32_t)(s + c);
+#endif
+}
+
+// --------------------------------------------------------------------------
 // Field element.  P supplies INV, MOD(i), ONE(i), R2(i), ...
 // --------------------------------------------------------------------------
 template <class P>
@@ -302,6 +479,38 @@ struct alignas(16) Fp {
         return reduce_once(s);
     }
     LZ_HD Fp sqr() const { return *this * *this; }
+    // Montgomery reduction of a 16-limb T < p * 2^256: T * R^-1 mod p.  Same aligned / offset accumulators as the
+    // product above, with the limbs of T's upper half joining one per round where the product adds a row of a * b_i.
+    LZ_HD static Fp reduce_wide(const uint32_t (&T)[16]) {
+        uint32_t X[8], Y[8];
+        uint32_t m, c;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { X[j] = T[j]; Y[j] = 0; }
+        // Value V = X + (Y << 32) + (upper limbs of T not yet taken in).  Round i: V += m p (m clears limb 0), V >>= 32.
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if ((i & 1) == 0) {
+                m = X[0] * P::INV;
+                c = row_mad(Y, P::MOD(1), P::MOD(3), P::MOD(5), P::MOD(7), m);      // positions 1..8 (carry: position 9)
+                uint32_t c2 = row_mad(X, P::MOD(0), P::MOD(2), P::MOD(4), P::MOD(6), m);   // positions 0..7, X[0] == 0 now
+                // shift down one limb: Y becomes aligned (positions 1..8 -> 0..7), X[1..7] the offset array (-> 0..6);
+                // position 8 receives X's carry, T[8 + i] and the carry out of Y
+                wide_shift(Y[0], X, c2, T[8 + i], c);
+            } else {
+                m = Y[0] * P::INV;
+                c = row_mad(X, P::MOD(1), P::MOD(3), P::MOD(5), P::MOD(7), m);
+                uint32_t c2 = row_mad(Y, P::MOD(0), P::MOD(2), P::MOD(4), P::MOD(6), m);
+                wide_shift(X[0], Y, c2, T[8 + i], c);
+            }
+        }
+        // after 8 rounds (even count) X is aligned again and Y the offset array
+        uint32_t hi[8], s_[8];
+#pragma unroll
+        for (int j = 0; j < 7; j++) hi[j + 1] = Y[j];
+        hi[0] = 0;
+        add8(s_, X, hi);
+        return reduce_once(s_);
+    }
 
     // canonical (plain integer, < p) <-> Montgomery
     LZ_HD static Fp from_canonical(const Fp &c) { return c * r2(); }
@@ -423,16 +632,34 @@ struct Fq2 {
         return Fq2{c0 * n, (c1 * n).neg()};
     }
 };
+// Karatsuba with lazy reduction: three 16-limb products, two Montgomery reductions.
+//   c1 = (a0 + a1)(b0 + b1) - a0 b0 - a1 b1 = a0 b1 + a1 b0 in [0, 2 p^2)            (the sums stay unreduced, < 2^255)
+//   c0 = a0 b0 - a1 b1, plus p * 2^256 when negative,        in [0, p * 2^256)
+// both below p * 2^256, so reduce_wide returns the canonical Montgomery residues.
+LZ_HD Fq2 fq2_mul_lazy(const Fq2 &a, const Fq2 &b) {
+    uint32_t t0[16], t1[16], t2[16], sa[8], sb[8];
+    mul_wide(t0, a.c0.l, b.c0.l);
+    mul_wide(t1, a.c1.l, b.c1.l);
+    add8(sa, a.c0.l, a.c1.l);
+    add8(sb, b.c0.l, b.c1.l);
+    mul_wide(t2, sa, sb);
+    sub16(t2, t2, t0);
+    sub16(t2, t2, t1);
+    const uint32_t bw = sub16(t0, t0, t1);
+    uint32_t hi[8], pm[8], fix[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { hi[i] = t0[8 + i]; pm[i] = bw ? FqParams::MOD(i) : 0u; }
+    add8(fix, hi, pm);
+#pragma unroll
+    for (int i = 0; i < 8; i++) t0[8 + i] = fix[i];
+    return Fq2{Fq::reduce_wide(t0), Fq::reduce_wide(t2)};
+}
 #if !defined(LZKP_FQ2_INLINE) && defined(__CUDA_ARCH__)
 // Out-of-line Fq2 product / square (operands and result in registers).  A G2 mixed addition with its 28 Montgomery
 // products inlined is ~110 KB of SASS, more than the instruction cache holds: ncu showed 11 % of the G2 gather
 // kernel's stall samples as no_instruction.  As calls the loop body is ~15 KB; measured -19 % on the G2 bucket
 // accumulation and -5 % on the G2 table-gather kernel.  -DLZKP_FQ2_INLINE restores the inlined form.
-static __device__ __noinline__ Fq2 fq2_mul_call(Fq2 a, Fq2 b) {
-    Fq v0 = a.c0 * b.c0, v1 = a.c1 * b.c1;
-    Fq s = (a.c0 + a.c1) * (b.c0 + b.c1);
-    return Fq2{v0 - v1, s - v0 - v1};
-}
+static __device__ __noinline__ Fq2 fq2_mul_call(Fq2 a, Fq2 b) { return fq2_mul_lazy(a, b); }
 static __device__ __noinline__ Fq2 fq2_sqr_call(Fq2 a) {
     Fq m = a.c0 * a.c1;
     return Fq2{(a.c0 + a.c1) * (a.c0 - a.c1), m.dbl()};

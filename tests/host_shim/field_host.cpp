@@ -19,6 +19,23 @@ void fq_op(int op, const uint8_t *a, const uint8_t *b, uint8_t *o) {
         case 4: r = Fq::from_canonical(x); break; case 5: r = x.to_canonical(); break; case 6: r = x.inverse(); break; default: r = x.sqr(); }
     st(o, r);
 }
+// Fq2 product with lazy reduction (field.cuh fq2_mul_lazy) and the wide primitives under it; a, b, o: c0 || c1 (64 B)
+void fq2_mul_lazy_host(const uint8_t *a, const uint8_t *b, uint8_t *o) {
+    Fq2 x, y; ld(x.c0, a); ld(x.c1, a + 32); ld(y.c0, b); ld(y.c1, b + 32);
+    Fq2 r = fq2_mul_lazy(x, y);
+    st(o, r.c0); st(o + 32, r.c1);
+}
+void fq_mul_wide_host(const uint8_t *a, const uint8_t *b, uint8_t *o64) {
+    Fq x, y; ld(x, a); ld(y, b);
+    uint32_t T[16];
+    mul_wide(T, x.l, y.l);
+    std::memcpy(o64, T, 64);
+}
+void fq_reduce_wide_host(const uint8_t *t64, uint8_t *o) {
+    uint32_t T[16];
+    std::memcpy(T, t64, 64);
+    st(o, Fq::reduce_wide(T));
+}
 int fq_gt(const uint8_t *a, const uint8_t *b) { Fq x, y; ld(x, a); ld(y, b); return Fq::gt_canonical(x, y); }
 // GLV split (ec.cuh): out = k1 (16 B) || k2 (16 B); returns neg1 | neg2 << 1 | ok << 2
 int glv_split_host(const uint8_t *k, uint8_t *out) {

@@ -111,6 +111,35 @@ def test_device_field_composition_on_host(field_shim, po):
     assert field_shim.fq_gt((C.c_uint8 * 32)(*(4).to_bytes(32, "little")), (C.c_uint8 * 32)(*(4).to_bytes(32, "little"))) == 0
 
 
+def test_lazy_fq2_product_on_host(field_shim, po):
+    """field.cuh's double-width path (mul_wide, reduce_wide, fq2_mul_lazy: Karatsuba with two reductions)."""
+    q, R = po.Q_MOD, 1 << 256
+    rinv = pow(R, -1, q)
+    rng = po.SplitMix64(91)
+    b32 = lambda v: (C.c_uint8 * 32)(*v.to_bytes(32, "little"))
+    b64 = lambda v: (C.c_uint8 * 64)(*v.to_bytes(64, "little"))
+    edge = [0, 1, q - 1, q - 2, R % q, (1 << 254) % q, 0xffffffff, q >> 1]
+    vals = edge + [rng.next_fr() % q for _ in range(300)]
+    for i, a in enumerate(vals):                       # 16-limb product, also of unreduced operands (sums < 2^256)
+        for b in (vals[(i * 5 + 1) % len(vals)], (1 << 256) - 1, 2 * q - 2):
+            o = (C.c_uint8 * 64)()
+            field_shim.fq_mul_wide_host(b32(a), b32(b), o)
+            assert int.from_bytes(bytes(o), "little") == a * b
+    wide = [0, 1, q * R - 1, q * R - q, (q - 1) * (q - 1), 2 * (q - 1) * (q - 1), R - 1, R, q] + \
+           [rng.next_fr() * rng.next_fr() % (q * R) for _ in range(300)]
+    for t in wide:                                     # reduction of any T < q * 2^256
+        o = (C.c_uint8 * 32)()
+        field_shim.fq_reduce_wide_host(b64(t), o)
+        assert int.from_bytes(bytes(o), "little") == t * rinv % q
+    for i in range(len(vals)):                         # Fq2 product in Montgomery form: (a0 + a1 u)(b0 + b1 u), u^2 = -1
+        a0, a1, b0, b1 = (vals[(i * k + k) % len(vals)] for k in (1, 3, 7, 11))
+        o = (C.c_uint8 * 64)()
+        field_shim.fq2_mul_lazy_host((C.c_uint8 * 64)(*(a0.to_bytes(32, "little") + a1.to_bytes(32, "little"))),
+                                     (C.c_uint8 * 64)(*(b0.to_bytes(32, "little") + b1.to_bytes(32, "little"))), o)
+        c0, c1 = int.from_bytes(bytes(o[:32]), "little"), int.from_bytes(bytes(o[32:]), "little")
+        assert c0 == (a0 * b0 - a1 * b1) * rinv % q and c1 == (a0 * b1 + a1 * b0) * rinv % q
+
+
 def test_glv_split_on_host(field_shim, po):
     """ec.cuh's GLV split: k == +-k1 +- k2 * lambda (mod r) with both halves below 2^128."""
     lam = 0x30644e72e131a029048b6e193fd84104cc37a73fec2bc5e9b8ca0b2d36636f23
