@@ -42,7 +42,7 @@ struct XYZZ {
         F xx = p.x.sqr(), M = xx.dbl() + xx;
         XYZZ r;
         r.x = M.sqr() - S.dbl();
-        r.y = M * (S - r.x) - W * p.y;
+        r.y = F::msub(M, S - r.x, W, p.y);
         r.zz = V;
         r.zzz = W;
         return r;
@@ -54,7 +54,7 @@ struct XYZZ {
         F U = y.dbl(), V = U.sqr(), W = U * V, S = x * V;
         F xx = x.sqr(), M = xx.dbl() + xx;
         F X3 = M.sqr() - S.dbl();
-        F Y3 = M * (S - X3) - W * y;
+        F Y3 = F::msub(M, S - X3, W, y);
         x = X3; y = Y3;
         zz = V * zz;
         zzz = W * zzz;
@@ -75,7 +75,7 @@ struct XYZZ {
         }
         F PP = Pp.sqr(), PPP = Pp * PP, Q = x * PP;
         F X3 = R.sqr() - PPP - Q.dbl();
-        F Y3 = R * (Q - X3) - y * PPP;
+        F Y3 = F::msub(R, Q - X3, y, PPP);
         x = X3; y = Y3;
         zz = zz * PP;
         zzz = zzz * PPP;
@@ -93,7 +93,7 @@ struct XYZZ {
         }
         F PP = Pp.sqr(), PPP = Pp * PP, Q = U1 * PP;
         F X3 = R.sqr() - PPP - Q.dbl();
-        F Y3 = R * (Q - X3) - S1 * PPP;
+        F Y3 = F::msub(R, Q - X3, S1, PPP);
         x = X3; y = Y3;
         zz = zz * q.zz * PP;
         zzz = zzz * q.zzz * PPP;

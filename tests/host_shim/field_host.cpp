@@ -25,6 +25,11 @@ void fq2_mul_lazy_host(const uint8_t *a, const uint8_t *b, uint8_t *o) {
     Fq2 r = fq2_mul_lazy(x, y);
     st(o, r.c0); st(o + 32, r.c1);
 }
+// a*b - c*d with one reduction (Fp::msub)
+void fq_msub_host(const uint8_t *a, const uint8_t *b, const uint8_t *c, const uint8_t *d, uint8_t *o) {
+    Fq x, y, z, w; ld(x, a); ld(y, b); ld(z, c); ld(w, d);
+    st(o, Fq::msub(x, y, z, w));
+}
 void fq_mul_wide_host(const uint8_t *a, const uint8_t *b, uint8_t *o64) {
     Fq x, y; ld(x, a); ld(y, b);
     uint32_t T[16];

@@ -138,6 +138,14 @@ def test_lazy_fq2_product_on_host(field_shim, po):
                                      (C.c_uint8 * 64)(*(b0.to_bytes(32, "little") + b1.to_bytes(32, "little"))), o)
         c0, c1 = int.from_bytes(bytes(o[:32]), "little"), int.from_bytes(bytes(o[32:]), "little")
         assert c0 == (a0 * b0 - a1 * b1) * rinv % q and c1 == (a0 * b1 + a1 * b0) * rinv % q
+    # a*b - c*d with the reductions shared (the Y3 of the XYZZ formulas), extremes of both signs included
+    pick = lambda i, k: vals[(i * k + k) % len(vals)]
+    cases = [(q - 1, q - 1, 0, 0), (0, 0, q - 1, q - 1), (q - 1, q - 1, q - 1, q - 1), (1, 0, q - 1, q - 1)] + \
+            [(pick(i, 1), pick(i, 3), pick(i, 7), pick(i, 11)) for i in range(len(vals))]
+    for a, b, c, d in cases:
+        o = (C.c_uint8 * 32)()
+        field_shim.fq_msub_host(b32(a), b32(b), b32(c), b32(d), o)
+        assert int.from_bytes(bytes(o), "little") == (a * b - c * d) * rinv % q
 
 
 def test_glv_split_on_host(field_shim, po):
