@@ -35,6 +35,10 @@ R_MOD = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
 IMAD_PER_MUL = 272            # 136 32x32 multiply-accumulates = 272 mad.lo/mad.hi issues
 M_MADD_G1 = 10                # XYZZ mixed add: 8M + 2S
 M_MADD_G2 = 28                # over Fq2: 8 * 3 + 2 * 2 base-field products
+# What the kernels execute per mixed add since lazy reduction went in (field.cuh): G1 = 8 products + one a*b - c*d with
+# a shared reduction (2 * 128 + 144); G2 = 8 Fq2 products of 3 * 128 + 2 * 144 and 2 Fq2 squares of 2 * 272.
+IMAD_EXEC_MADD_G1 = 8 * 272 + 400
+IMAD_EXEC_MADD_G2 = 8 * 672 + 2 * 544
 IMAD_PEAK_FALLBACK = 17.25e12  # measured: tools/microbench on this pool (profiles/r1_microbench.jsonl)
 
 
@@ -307,6 +311,11 @@ def run_ours(args, rank, world, local_rank):
         "traffic_note": "DRAM bytes per launch from profiles/r1_ncu_msm_batch.txt (ncu --set full); algorithmic bytes "
                         "are in hbm.algorithmic_bytes_per_launch - 64 B table entries are fetched as 128 B lines",
         "algorithmic_imad_per_launch": imad_per_launch, "avg_launch_ms": ms_g1 / max(n_g1, 1),
+        "algorithmic_note": "SURVEY.md 8d unit: a mixed add = 10 Montgomery products of 272 IMAD; the kernel executes "
+                            "fewer (executed.*: shared reductions), so frac is useful work over peak, executed.frac is "
+                            "the pipe utilisation",
+        "executed": {"imad_per_launch": P * g1_units * IMAD_EXEC_MADD_G1,
+                     "frac": (P * g1_units * IMAD_EXEC_MADD_G1 / (ms_g1 / max(n_g1, 1) * 1e-3) / peak) if ms_g1 else 0.0},
         "mixed_adds_per_proof": {"g1": g1_units, "g2": g2_units, "g1_bases": g1_rows, "g2_bases": g2_rows,
                                  "note": "non-identity bases x windows; the key's identity points are not counted"},
         "share_of_step": ms_g1 / ms,
@@ -316,7 +325,9 @@ def run_ours(args, rank, world, local_rank):
         "stage_ms_per_step": {k: v[0] / args.steps for k, v in regions.items()},
         "g2_msm": {"algorithmic_imad_per_launch": P * g2_units * M_MADD_G2 * IMAD_PER_MUL,
                    "achieved": (P * g2_units * M_MADD_G2 * IMAD_PER_MUL) / (regions["msm_g2"][0] / max(regions["msm_g2"][1], 1) * 1e-3) / 1e12
-                   if regions["msm_g2"][0] else 0.0, "unit": "T IMAD/s"},
+                   if regions["msm_g2"][0] else 0.0, "unit": "T IMAD/s",
+                   "executed_frac": (P * g2_units * IMAD_EXEC_MADD_G2) / (regions["msm_g2"][0] / max(regions["msm_g2"][1], 1) * 1e-3) / peak
+                   if regions["msm_g2"][0] else 0.0},
     }
 
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only)

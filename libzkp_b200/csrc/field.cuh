@@ -331,35 +331,42 @@ LZ_HD uint32_t sub16(uint32_t (&r)[16], const uint32_t (&a)[16], const uint32_t 
     return bw;
 }
 
-// One-limb right shift between two rounds of reduce_wide: A0 (limb 0 of the array that becomes aligned) takes D[1];
-// D moves down two limbs and becomes the offset array; its top two limbs take (t + c2) and c with the running carry.
-LZ_HD void wide_shift(uint32_t &A0, uint32_t (&D)[8], uint32_t c2, uint32_t t, uint32_t c) {
+// One round of reduce_wide, fused the way row_mad_shift fuses a product row: the limb that drops to column 0 joins
+// the aligned array (A0 += D[1]), the Montgomery factor m = A0 * inv follows from it, and D moves down two limbs while
+// taking the row (p1, p3, p5, p7) * m:  D[j] = p*m + D[j+2] + carry.  mul.lo leaves the carry flag alone.
+LZ_HD uint32_t red_shift_row(uint32_t &A0, uint32_t (&D)[8], uint32_t p1, uint32_t p3, uint32_t p5, uint32_t p7,
+                             uint32_t inv) {
+    uint32_t m;
 #ifdef __CUDA_ARCH__
     asm("add.cc.u32 %0, %0, %2;\n\t"
-        "addc.cc.u32 %1, %3, 0;\n\t"
-        "addc.cc.u32 %2, %4, 0;\n\t"
-        "addc.cc.u32 %3, %5, 0;\n\t"
-        "addc.cc.u32 %4, %6, 0;\n\t"
-        "addc.cc.u32 %5, %7, 0;\n\t"
-        "addc.cc.u32 %6, %8, 0;\n\t"
-        "addc.cc.u32 %7, %9, %10;\n\t"
-        "addc.u32 %8, %11, 0;"
-        : "+r"(A0), "+r"(D[0]), "+r"(D[1]), "+r"(D[2]), "+r"(D[3]), "+r"(D[4]), "+r"(D[5]), "+r"(D[6]), "+r"(D[7])
-        : "r"(t), "r"(c2), "r"(c));
+        "mul.lo.u32 %9, %0, %14;\n\t"
+        "madc.lo.cc.u32 %1, %10, %9, %3;\n\t"
+        "madc.hi.cc.u32 %2, %10, %9, %4;\n\t"
+        "madc.lo.cc.u32 %3, %11, %9, %5;\n\t"
+        "madc.hi.cc.u32 %4, %11, %9, %6;\n\t"
+        "madc.lo.cc.u32 %5, %12, %9, %7;\n\t"
+        "madc.hi.cc.u32 %6, %12, %9, %8;\n\t"
+        "madc.lo.cc.u32 %7, %13, %9, 0;\n\t"
+        "madc.hi.u32 %8, %13, %9, 0;"
+        : "+r"(A0), "+r"(D[0]), "+r"(D[1]), "+r"(D[2]), "+r"(D[3]), "+r"(D[4]), "+r"(D[5]), "+r"(D[6]), "+r"(D[7]), "=&r"(m)
+        : "r"(p1), "r"(p3), "r"(p5), "r"(p7), "r"(inv));
 #else
-    uint64_t s = (uint64_t)A0 + D[1];
-    A0 = (uint32_t)s;
-    s >>= 32;
-    for (int j = 0; j < 6; j++) {
-        s += D[j + 2];
-        D[j] = (uint32_t)s;
-        s >>= 32;
+    const uint32_t s[4] = {p1, p3, p5, p7};
+    uint64_t c = (uint64_t)A0 + D[1];
+    A0 = (uint32_t)c;
+    c >>= 32;
+    m = A0 * inv;
+    for (int t = 0; t < 4; t++) {
+        uint64_t pr = (uint64_t)s[t] * m;
+        uint32_t alo = t < 3 ? D[2 * t + 2] : 0, ahi = t < 3 ? D[2 * t + 3] : 0;
+        uint64_t lo = (uint64_t)alo + (uint32_t)pr + c;
+        uint64_t hi = (uint64_t)ahi + (uint32_t)(pr >> 32) + (lo >> 32);
+        D[2 * t] = (uint32_t)lo;
+        D[2 * t + 1] = (uint32_t)hi;
+        c = hi >> 32;
     }
-    s += (uint64_t)t + c2;
-    D[6] = (uint32_t)s;
-    s >>= 32;
-    D[7] = (uint32_t)(s + c);
 #endif
+    return m;
 }
 
 // T += p * 2^256 if neg (T is a difference of products that came out negative, above -p * 2^256)
@@ -490,36 +497,39 @@ struct alignas(16) Fp {
         return reduce_once(s);
     }
     LZ_HD Fp sqr() const { return *this * *this; }
-    // Montgomery reduction of a 16-limb T < p * 2^256: T * R^-1 mod p.  Same aligned / offset accumulators as the
-    // product above, with the limbs of T's upper half joining one per round where the product adds a row of a * b_i.
+    // Montgomery reduction of a 16-limb T < p * 2^256: T * R^-1 mod p = (T_lo + M p) / R + T_hi, where the eight
+    // rounds run on the lower half alone (U = (T_lo + M p) / R <= p) in the product's aligned / offset accumulators,
+    // and T_hi < p joins at the end: U + T_hi < 2p.
     LZ_HD static Fp reduce_wide(const uint32_t (&T)[16]) {
         uint32_t X[8], Y[8];
         uint32_t m, c;
 #pragma unroll
-        for (int j = 0; j < 8; j++) { X[j] = T[j]; Y[j] = 0; }
-        // Value V = X + (Y << 32) + (upper limbs of T not yet taken in).  Round i: V += m p (m clears limb 0), V >>= 32.
+        for (int j = 0; j < 8; j++) X[j] = T[j];
+        m = X[0] * P::INV;
+        row_mul(Y, P::MOD(1), P::MOD(3), P::MOD(5), P::MOD(7), m);
+        c = row_mad(X, P::MOD(0), P::MOD(2), P::MOD(4), P::MOD(6), m);
+        Y[7] += c;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            if ((i & 1) == 0) {
-                m = X[0] * P::INV;
-                c = row_mad(Y, P::MOD(1), P::MOD(3), P::MOD(5), P::MOD(7), m);      // positions 1..8 (carry: position 9)
-                uint32_t c2 = row_mad(X, P::MOD(0), P::MOD(2), P::MOD(4), P::MOD(6), m);   // positions 0..7, X[0] == 0 now
-                // shift down one limb: Y becomes aligned (positions 1..8 -> 0..7), X[1..7] the offset array (-> 0..6);
-                // position 8 receives X's carry, T[8 + i] and the carry out of Y
-                wide_shift(Y[0], X, c2, T[8 + i], c);
+        for (int i = 1; i < 8; i++) {
+            if (i & 1) {
+                m = red_shift_row(Y[0], X, P::MOD(1), P::MOD(3), P::MOD(5), P::MOD(7), P::INV);
+                c = row_mad(Y, P::MOD(0), P::MOD(2), P::MOD(4), P::MOD(6), m);
+                X[7] += c;
             } else {
-                m = Y[0] * P::INV;
-                c = row_mad(X, P::MOD(1), P::MOD(3), P::MOD(5), P::MOD(7), m);
-                uint32_t c2 = row_mad(Y, P::MOD(0), P::MOD(2), P::MOD(4), P::MOD(6), m);
-                wide_shift(X[0], Y, c2, T[8 + i], c);
+                m = red_shift_row(X[0], Y, P::MOD(1), P::MOD(3), P::MOD(5), P::MOD(7), P::INV);
+                c = row_mad(X, P::MOD(0), P::MOD(2), P::MOD(4), P::MOD(6), m);
+                Y[7] += c;
             }
         }
-        // after 8 rounds (even count) X is aligned again and Y the offset array
-        uint32_t hi[8], s_[8];
+        // after i = 7: Y aligned with Y[0] == 0, X offset: U = X + (Y >> 32)
+        uint32_t hi[8], th[8], u[8], s_[8];
 #pragma unroll
-        for (int j = 0; j < 7; j++) hi[j + 1] = Y[j];
-        hi[0] = 0;
-        add8(s_, X, hi);
+        for (int j = 0; j < 7; j++) hi[j] = Y[j + 1];
+        hi[7] = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) th[j] = T[8 + j];
+        add8(u, X, hi);
+        add8(s_, u, th);
         return reduce_once(s_);
     }
     // a*b - c*d with ONE reduction (the Y3 of every XYZZ formula): two 16-limb products, the difference brought back
