@@ -5,10 +5,12 @@ import collections, csv, io, re, subprocess, sys
 txt = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "source", "--csv"], capture_output=True, text=True).stdout
 want = sys.argv[2] if len(sys.argv) > 2 else ""
 blocks = re.split(r'(?m)^"Kernel Name",', txt)[1:]
+seen = set()
 for blk in blocks:
     name, rest = blk.split("\n", 1)
-    if want not in name:
+    if want not in name or blk in seen:        # the source page lists every kernel once per view
         continue
+    seen.add(blk)
     rows = list(csv.reader(io.StringIO(rest)))
     h, data = rows[0], rows[1:]
     ix = {k: i for i, k in enumerate(h)}
