@@ -31,7 +31,10 @@
 #define LZKP_G2_MINB 6
 #endif
 // minimum resident CTAs per SM: G1 kernels leave it to ptxas, G2 kernels (64-thread CTAs) trade registers for warps
-#define LZKP_G2_MINB_SEL(F) (sizeof(F) == sizeof(::lzkp::Fq) ? 1 : LZKP_G2_MINB)
+#ifndef LZKP_G1_MINB
+#define LZKP_G1_MINB 1
+#endif
+#define LZKP_G2_MINB_SEL(F) (sizeof(F) == sizeof(::lzkp::Fq) ? LZKP_G1_MINB : LZKP_G2_MINB)
 namespace lzkp {
 
 namespace {
