@@ -29,39 +29,21 @@ __global__ void __launch_bounds__(BLOCK, LZKP_G2_MINB_SEL(F)) k_msm_batch(const 
     if (p >= P) return;
     const uint2 range = items[item];
     XYZZ<F> acc = XYZZ<F>::inf();
-    // Software pipeline: digit -> address -> point is a dependent chain of two memory latencies; the point of unit
-    // u+1 is in flight under the add of unit u.  With 4-byte digits (c = 17) the digit matrix of a large batch no
-    // longer stays in L2, so the G1 kernel also keeps the digit of unit u+2 in flight (measured -2 %; the G2 kernel
-    // sits at 255 registers and loses more to the extra live value than it gains).
-    if constexpr (sizeof(F) == sizeof(Fq) && sizeof(DigT) == 4) {
-        auto digit_of = [&](uint32_t u) { return u < range.y ? (int)dig[(size_t)__ldg(unit_dig + u) * P + p] : 0; };
-        int d = digit_of(range.x), dn = digit_of(range.x + 1);
-        Affine<F> pt = Affine<F>::inf();
-        if (d) pt = gather_point(table, N, __ldg(unit_tbl + range.x), d);
-        for (uint32_t u = range.x; u < range.y; u++) {
-            const int dnn = digit_of(u + 2);
-            Affine<F> ptn = Affine<F>::inf();
+    // Software pipeline: the table point of unit u+1 is in flight under the add of unit u.  (Also keeping the digit of
+    // unit u+2 in flight gained 2 % with 4-byte digits at 156 registers, but costs the fourth resident CTA: dropped.)
+    int d = dig[(size_t)__ldg(unit_dig + range.x) * P + p];
+    Affine<F> pt = Affine<F>::inf();
+    if (d) pt = gather_point(table, N, __ldg(unit_tbl + range.x), d);
+    for (uint32_t u = range.x; u < range.y; u++) {
+        int dn = 0;
+        Affine<F> ptn = Affine<F>::inf();
+        if (u + 1 < range.y) {
+            dn = dig[(size_t)__ldg(unit_dig + u + 1) * P + p];
             if (dn) ptn = gather_point(table, N, __ldg(unit_tbl + u + 1), dn);
-            if (d) acc.madd(pt);
-            d = dn;
-            dn = dnn;
-            pt = ptn;
         }
-    } else {
-        int d = dig[(size_t)__ldg(unit_dig + range.x) * P + p];
-        Affine<F> pt = Affine<F>::inf();
-        if (d) pt = gather_point(table, N, __ldg(unit_tbl + range.x), d);
-        for (uint32_t u = range.x; u < range.y; u++) {
-            int dn = 0;
-            Affine<F> ptn = Affine<F>::inf();
-            if (u + 1 < range.y) {
-                dn = dig[(size_t)__ldg(unit_dig + u + 1) * P + p];
-                if (dn) ptn = gather_point(table, N, __ldg(unit_tbl + u + 1), dn);
-            }
-            if (d) acc.madd(pt);
-            d = dn;
-            pt = ptn;
-        }
+        if (d) acc.madd(pt);
+        d = dn;
+        pt = ptn;
     }
     st_vec(partial + (size_t)item * P + p, acc);
 }
