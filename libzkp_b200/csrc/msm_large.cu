@@ -112,11 +112,14 @@ __global__ void __launch_bounds__(BLOCK, LZKP_G2_MINB_SEL(F)) k_bucket_accum(con
     constexpr bool kRegPrefetch = sizeof(F) == sizeof(Fq);
     Affine<F> pt = Affine<F>::inf();
     if constexpr (kRegPrefetch) pt = fetch_point(points, vp[0]);
+    uint32_t vn = len > 1 ? vp[1] : 0u;                                  // point ref of pair j + 1, one step ahead of its use
     for (uint32_t j = 0; j < len; j++) {
         uint32_t k = kp[j];
         Affine<F> nxt = Affine<F>::inf();
         if constexpr (kRegPrefetch) {
-            if (j + 1 < len) nxt = fetch_point(points, vp[j + 1]);       // prefetch under the current add
+            const uint32_t vnn = j + 2 < len ? vp[j + 2] : 0u;
+            if (j + 1 < len) nxt = fetch_point(points, vn);              // prefetch under the current add
+            vn = vnn;
         } else {
             if (j + 1 < len) {
                 const char *np_ = reinterpret_cast<const char *>(points + (vp[j + 1] & 0x7FFFFFFFu));
