@@ -85,14 +85,14 @@ int ensure_device() {
 struct MsmPlan {                 // one curve
     DBuf table;                  // Affine<F>[rows * W * N]
     DBuf unit_dig, unit_tbl;     // uint32[n_units]
-    DBuf items[3];               // uint2[n_items[v]] for the three granularities
-    DBuf msm_items[3];           // uint2[n_msm]: item range of each MSM
-    uint32_t n_items[3] = {0, 0, 0};
+    DBuf items[4];               // uint2[n_items[v]] for the four granularities
+    DBuf msm_items[4];           // uint2[n_msm]: item range of each MSM
+    uint32_t n_items[4] = {0, 0, 0, 0};
     uint32_t n_units = 0, n_rows = 0, n_msm = 0;
     std::vector<uint32_t> msm_unit_begin;   // host: first unit of each MSM (+ end)
-    std::vector<uint2> msm_items_host[3];   // host copy of msm_items per granularity
+    std::vector<uint2> msm_items_host[4];   // host copy of msm_items per granularity
 };
-static const uint32_t kUnitsPerItem[3] = {32, 128, 512};
+static const uint32_t kUnitsPerItem[4] = {8, 32, 128, 512};
 
 // Host memory the device can DMA to without an intermediate copy (results of a chunk land here asynchronously).
 struct HBuf {
@@ -194,7 +194,7 @@ static int finish_plan(MsmPlan &pl, const std::vector<std::vector<BaseRef>> &msm
     pl.n_msm = (uint32_t)msms.size();
     TRY(upload(pl.unit_dig, ud));
     TRY(upload(pl.unit_tbl, ut));
-    for (int v = 0; v < 3; v++) {
+    for (int v = 0; v < 4; v++) {
         std::vector<uint2> items, mi;
         for (uint32_t q = 0; q < pl.n_msm; q++) {
             uint32_t first = (uint32_t)items.size();
@@ -482,7 +482,7 @@ static int pk_load_impl(const uint8_t *bytes, size_t len, int validate, const lz
     // proofs per device pass: two workspaces must fit beside the tables
     {
         const uint64_t per_proof = (uint64_t)nv * 32 + 7ull * n * 32 + (uint64_t)pk->n_dig_rows * pk->W * (c > 16 ? 4 : 2) +
-                                   (uint64_t)pk->g1.n_items[1] * sizeof(G1XYZZ) + (uint64_t)pk->g2.n_items[0] * sizeof(G2XYZZ) +
+                                   (uint64_t)pk->g1.n_items[2] * sizeof(G1XYZZ) + (uint64_t)pk->g2.n_items[1] * sizeof(G2XYZZ) +
                                    4 * sizeof(G1XYZZ) + sizeof(G2XYZZ) + 1024;
         size_t free_now = 0, total_now = 0;
         CUDA_TRY(cudaMemGetInfo(&free_now, &total_now));
@@ -555,20 +555,20 @@ static int circuit_install(lzkp_pk *pk, uint32_t m, uint32_t n_inst, uint32_t n_
 // ------------------------------------------------------------------------ proving pipeline
 // Item granularity: many more CTAs than the 148 x 3 resident ones, so the last wave of a launch is a small
 // fraction of the kernel (measured: 512-unit items left the G1 kernel at 3.4 waves = 0.87 of peak).
-static inline int item_variant(uint32_t P) { return P >= 256 ? 1 : 0; }
+// Calls of at most small_batch_limit() proofs are latency-bound: 8-unit items and a tree reduction keep the serial chain per thread
+// short (msm_batch.cu kSmallBatch).
+static inline int item_variant(uint32_t P) { return P > small_batch_limit() ? (P >= 256 ? 2 : 1) : 0; }
 // the item index is the grid's y dimension (<= 65535): very wide keys fall back to coarser items
 static inline int fit_variant(const MsmPlan &pl, int v) {
-    while (v < 2 && pl.n_items[v] > 65535u) v++;
+    while (v < 3 && pl.n_items[v] > 65535u) v++;
     return v;
 }
-// G2 runs 64-thread CTAs at 255 registers: finer items keep every SM partition supplied with warps
-static inline int item_variant_g2(uint32_t P) { return P >= 2048 ? 1 : 0; }
+// G2 runs 64-thread CTAs: finer items keep every SM partition supplied with warps
+static inline int item_variant_g2(uint32_t P) { return P > small_batch_limit() ? (P >= 2048 ? 2 : 1) : 0; }
 static int ensure_workspace(lzkp_pk *pk, Workspace &ws, uint32_t P) {
     if (P <= ws.chunk) return LZKP_OK;
     size_t part1 = 0, part2 = 0;       // worst case over the batch sizes <= P
-    for (uint32_t q : {1u, 256u, 2048u}) {
-        if (q > P) break;
-        uint32_t pp = q == 1u ? std::min(P, 255u) : (q == 256u ? std::min(P, 2047u) : P);
+    for (uint32_t pp : {std::min(P, small_batch_limit()), std::min(P, 255u), std::min(P, 2047u), P}) {
         part1 = std::max(part1, (size_t)pk->g1.n_items[fit_variant(pk->g1, item_variant(pp))] * pp);
         part2 = std::max(part2, (size_t)pk->g2.n_items[fit_variant(pk->g2, item_variant_g2(pp))] * pp);
     }
@@ -592,6 +592,11 @@ static int ensure_workspace(lzkp_pk *pk, Workspace &ws, uint32_t P) {
     TRY(ws.a.ensure(P * 8)); TRY(ws.b.ensure(P * 8)); TRY(ws.commit.ensure(P * 32));
     ws.chunk = P;
     return LZKP_OK;
+}
+
+static inline void wires_to_canonical(Fr *z, uint32_t P, uint32_t nv, uint32_t first, uint32_t count, cudaStream_t st) {
+    const size_t total = (size_t)P * count;
+    LAUNCH(k_wires_to_canonical, (unsigned)((total + 127) / 128), 128, 0, st, z, P, nv, first, count);
 }
 
 struct Region {           // RAII: brackets the kernels of one pipeline stage with two events when profiling is on
@@ -1107,6 +1112,7 @@ static int equality_batch_impl(lzkp_pk *pk, size_t n_proofs, const uint64_t *a, 
         LAUNCH(k_witgen_equality, (P + 127) / 128, 128, 0, st, ws.a.as<uint64_t>(), ws.b.as<uint64_t>(),
                commitments ? ws.commit.as<Fr>() : nullptr, ws.z.as<Fr>(), ws.commit.as<Fr>(), ws.status.as<int32_t>(), P,
                pk->kind_param, pk->n_vars);
+        wires_to_canonical(ws.z.as<Fr>(), P, pk->n_vars, 4u, 3u * pk->kind_param, st);
         return LZKP_OK;
     });
 }
@@ -1146,6 +1152,7 @@ static int membership_batch_impl(lzkp_pk *pk, size_t n_proofs, const uint64_t *v
         LAUNCH(k_witgen_membership, (P + 127) / 128, 128, 0, st, ws.a.as<uint64_t>(), ws.sets.as<uint64_t>(),
                ws.setlen.as<uint32_t>(), set_stride, commitments ? ws.commit.as<Fr>() : nullptr, ws.z.as<Fr>(),
                ws.commit.as<Fr>(), ws.status.as<int32_t>(), P, pk->kind_param, pk->n_vars);
+        wires_to_canonical(ws.z.as<Fr>(), P, pk->n_vars, 2u + 2u * pk->kind_param + 1u, 330u, st);
         return LZKP_OK;
     });
 }
@@ -1183,6 +1190,7 @@ int lzkp_prove_equality_batch_device(lzkp_pk *pk, size_t n_proofs, const void *d
         Region reg(pk, LZKP_REGION_WITGEN, st);
         LAUNCH(k_witgen_equality, (P + 127) / 128, 128, 0, st, (const uint64_t *)d_a + off, (const uint64_t *)d_b + off,
                (const Fr *)nullptr, ws.z.as<Fr>(), ws.commit.as<Fr>(), stat, P, pk->kind_param, pk->n_vars);
+        wires_to_canonical(ws.z.as<Fr>(), P, pk->n_vars, 4u, 3u * pk->kind_param, st);
         return LZKP_OK;
     });
 }

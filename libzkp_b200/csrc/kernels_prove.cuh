@@ -69,13 +69,21 @@ __global__ void k_witgen_equality(const uint64_t *a, const uint64_t *b, const Fr
         Fr t = x + c_mimc[i % 110];
         Fr t2 = t.sqr(), t4 = t2.sqr();
         x = t4 * t;
-        st_vec(zp + 4 + 3 * i, t2.to_canonical());
-        st_vec(zp + 5 + 3 * i, t4.to_canonical());
-        st_vec(zp + 6 + 3 * i, x.to_canonical());
+        st_vec(zp + 4 + 3 * i, t2);           // Montgomery form: k_wires_to_canonical converts the wires in parallel,
+        st_vec(zp + 5 + 3 * i, t4);           // off this thread's serial chain of 3 products per round
+        st_vec(zp + 6 + 3 * i, x);
     }
     Fr cm = commit_in ? ld_vec(commit_in + p) : x.to_canonical();
     st_vec(zp + 1, cm);
     if (commit_out) st_vec(commit_out + p, cm);
+}
+
+// z[p][first .. first + count) : Montgomery -> canonical (the MiMC wires the witness kernels leave in Montgomery form)
+__global__ void __launch_bounds__(128) k_wires_to_canonical(Fr *z, uint32_t P, uint32_t nv, uint32_t first, uint32_t count) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)P * count) return;
+    Fr *e = z + (i / count) * nv + first + (uint32_t)(i % count);
+    st_vec(e, ld_vec(e).to_canonical());
 }
 
 // z = [1, commitment, set[S], is_real[S], value, 330 MiMC wires, sel[S], sel*(1-is_real)[S],
@@ -109,9 +117,9 @@ __global__ void k_witgen_membership(const uint64_t *value, const uint64_t *sets,
         Fr t = x + c_mimc[i];
         Fr t2 = t.sqr(), t4 = t2.sqr();
         x = t4 * t;
-        st_vec(zp + w0 + 1 + 3 * i, t2.to_canonical());
-        st_vec(zp + w0 + 2 + 3 * i, t4.to_canonical());
-        st_vec(zp + w0 + 3 + 3 * i, x.to_canonical());
+        st_vec(zp + w0 + 1 + 3 * i, t2);      // Montgomery form, see k_wires_to_canonical
+        st_vec(zp + w0 + 2 + 3 * i, t4);
+        st_vec(zp + w0 + 3 + 3 * i, x);
     }
     Fr cm = commit_in ? ld_vec(commit_in + p) : x.to_canonical();
     st_vec(zp + 1, cm);

@@ -1,6 +1,7 @@
 // msm_batch.cu — the five MSMs of a batch of proofs as fixed-base table gathers + XYZZ mixed adds
 // (replaces VariableBaseMSM::msm_bigint inside ark-groth16's prover,
 // reached from src/backend/snark.rs:364 and :442).
+#include <cstdlib>
 #include "tables.h"
 #include "dev_util.cuh"
 
@@ -72,14 +73,54 @@ __global__ void __launch_bounds__(128) k_msm_reduce(const XYZZ<F> *partial, cons
     st_vec(out + (size_t)q * P + p, acc);
 }
 
+// Small batches (P <= kSmallBatch): one CTA per (proof, MSM) folds the partial sums through shared memory in
+// log2(T) levels instead of two serial chains.
+template <class F, int T>
+__global__ void __launch_bounds__(T) k_msm_reduce_tree(const XYZZ<F> *__restrict__ partial, const uint2 *__restrict__ msm_items,
+                                                       uint32_t P, XYZZ<F> *__restrict__ out) {
+    __shared__ uint4 raw[T * sizeof(XYZZ<F>) / 16];
+    XYZZ<F> *sm = reinterpret_cast<XYZZ<F> *>(raw);
+    const uint32_t p = blockIdx.x, q = blockIdx.y, t = threadIdx.x;
+    const uint2 r = msm_items[q];
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t it = r.x + t; it < r.y; it += T) acc.add_cold(ld_vec(partial + (size_t)it * P + p));
+    st_vec(sm + t, acc);
+    __syncthreads();
+    for (uint32_t s = T / 2; s > 0; s >>= 1) {
+        if (t < s) {
+            XYZZ<F> a = ld_vec(sm + t);
+            a.add_cold(ld_vec(sm + t + s));
+            st_vec(sm + t, a);
+        }
+        __syncthreads();
+    }
+    if (t == 0) st_vec(out + (size_t)q * P + p, ld_vec(sm));
+}
+
 }  // namespace lzkp
 
 namespace lzkp {
 namespace eng {
+uint32_t small_batch_limit() {
+    static const uint32_t v = [] {
+        const char *e = getenv("LZKP_SMALL_BATCH");
+        return e ? (uint32_t)atoi(e) : 512u;     // measured crossover on B200: equal at 512 proofs, 12 % slower at 1024
+    }();
+    return v;
+}
 
 // gather + accumulate the items [item0, item0 + count) (partial sums land at their global item index)
 void batch_msm_g1_items(const BatchMsmArgs &a, uint32_t item0, uint32_t count, cudaStream_t st) {
     if (!count) return;
+    if (a.P <= small_batch_limit()) {          // a few warps of proofs: 32-thread CTAs so that the items spread over every SM partition
+        if (a.dig_bytes == 2)
+            LAUNCH((k_msm_batch<Fq, 32, int16_t>), dim3((a.P + 31) / 32, count), 32, 0, st, (const G1Affine *)a.table, a.N, a.unit_dig, a.unit_tbl,
+                   (const uint2 *)a.items + item0, (const int16_t *)a.dig, a.P, (G1XYZZ *)a.partial + (size_t)item0 * a.P);
+        else
+            LAUNCH((k_msm_batch<Fq, 32, int32_t>), dim3((a.P + 31) / 32, count), 32, 0, st, (const G1Affine *)a.table, a.N, a.unit_dig, a.unit_tbl,
+                   (const uint2 *)a.items + item0, (const int32_t *)a.dig, a.P, (G1XYZZ *)a.partial + (size_t)item0 * a.P);
+        return;
+    }
     if (a.dig_bytes == 2)
         LAUNCH((k_msm_batch<Fq, 128, int16_t>), dim3((a.P + 127) / 128, count), 128, 0, st, (const G1Affine *)a.table, a.N, a.unit_dig,
                a.unit_tbl, (const uint2 *)a.items + item0, (const int16_t *)a.dig, a.P, (G1XYZZ *)a.partial + (size_t)item0 * a.P);
@@ -89,6 +130,11 @@ void batch_msm_g1_items(const BatchMsmArgs &a, uint32_t item0, uint32_t count, c
 }
 constexpr uint32_t kReduceFan = 8;
 void batch_msm_g1_reduce(const BatchMsmArgs &a, cudaStream_t st) {
+    if (a.P <= small_batch_limit()) {
+        LAUNCH((k_msm_reduce_tree<Fq, 128>), dim3(a.P, a.n_msm), 128, 0, st, (const G1XYZZ *)a.partial, (const uint2 *)a.msm_items,
+               a.P, (G1XYZZ *)a.out);
+        return;
+    }
     LAUNCH((k_msm_reduce1<Fq>), dim3((a.P + 127) / 128, a.n_msm, kReduceFan), 128, 0, st, (G1XYZZ *)a.partial,
            (const uint2 *)a.msm_items, a.P, kReduceFan);
     LAUNCH((k_msm_reduce<Fq>), dim3((a.P + 127) / 128, a.n_msm), 128, 0, st, (const G1XYZZ *)a.partial,
@@ -99,6 +145,17 @@ void batch_msm_g1(const BatchMsmArgs &a, cudaStream_t st) {
     batch_msm_g1_reduce(a, st);
 }
 void batch_msm_g2(const BatchMsmArgs &a, cudaStream_t st) {
+    if (a.P <= small_batch_limit()) {
+        if (a.dig_bytes == 2)
+            LAUNCH((k_msm_batch<Fq2, 32, int16_t>), dim3((a.P + 31) / 32, a.n_items), 32, 0, st, (const G2Affine *)a.table, a.N, a.unit_dig,
+                   a.unit_tbl, (const uint2 *)a.items, (const int16_t *)a.dig, a.P, (G2XYZZ *)a.partial);
+        else
+            LAUNCH((k_msm_batch<Fq2, 32, int32_t>), dim3((a.P + 31) / 32, a.n_items), 32, 0, st, (const G2Affine *)a.table, a.N, a.unit_dig,
+                   a.unit_tbl, (const uint2 *)a.items, (const int32_t *)a.dig, a.P, (G2XYZZ *)a.partial);
+        LAUNCH((k_msm_reduce_tree<Fq2, 128>), dim3(a.P, a.n_msm), 128, 0, st, (const G2XYZZ *)a.partial, (const uint2 *)a.msm_items,
+               a.P, (G2XYZZ *)a.out);
+        return;
+    }
     if (a.dig_bytes == 2)
         LAUNCH((k_msm_batch<Fq2, 64, int16_t>), dim3((a.P + 63) / 64, a.n_items), 64, 0, st, (const G2Affine *)a.table, a.N,
                a.unit_dig, a.unit_tbl, (const uint2 *)a.items, (const int16_t *)a.dig, a.P, (G2XYZZ *)a.partial);
