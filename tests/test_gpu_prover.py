@@ -77,7 +77,7 @@ def test_golden_proofs_bit_exact(eq_pk, mb_pk, eq_keys, mb_keys, co, golden):
         assert proofs[i].tobytes().hex() == c["proof"], f"membership case {i}"
 
 
-@pytest.mark.parametrize("n", [1, 3, 130, 300])
+@pytest.mark.parametrize("n", [1, 3, 33, 130, 300, 512, 513])      # 512 | 513: latency shape | throughput shape
 def test_equality_batch_device_witness_vs_oracle(eq_pk, eq_keys, co, po, frs, n):
     rng = po.SplitMix64(3)
     a = np.array([rng.next_u64() for _ in range(n)], np.uint64)
