@@ -558,8 +558,6 @@ static int circuit_install(lzkp_pk *pk, uint32_t m, uint32_t n_inst, uint32_t n_
 // Calls of at most small_batch_limit() proofs are latency-bound: 8-unit items and a tree reduction keep the serial chain per thread
 // short (msm_batch.cu kSmallBatch).
 static inline int item_variant(uint32_t P) {
-    static const int forced = getenv("LZKP_G1_ITEMS") ? atoi(getenv("LZKP_G1_ITEMS")) : -1;     // experiments
-    if (forced >= 0 && P > small_batch_limit()) return forced;
     return P > small_batch_limit() ? (P >= 256 ? 2 : 1) : 0;
 }
 // the item index is the grid's y dimension (<= 65535): very wide keys fall back to coarser items
@@ -568,10 +566,8 @@ static inline int fit_variant(const MsmPlan &pl, int v) {
     return v;
 }
 static inline int item_variant_g2(uint32_t P) {
-    static const int forced = getenv("LZKP_G2_ITEMS") ? atoi(getenv("LZKP_G2_ITEMS")) : -1;     // experiments
-    if (forced >= 0 && P > small_batch_limit()) return forced;
     // 32-unit items at every batch size: the G2 grid then is several waves of its 148 x 6 resident CTAs (with 128-unit
-    // items a 4096-proof batch was 1.87 waves and paid for 2: measured 7.59 -> 7.06 ms)
+    // items a 4096-proof batch was 1.87 waves and paid for 2: measured 7.59 -> 7.06 ms; lengths 24..37 are within 2 %)
     return P > small_batch_limit() ? 1 : 0;
 }
 static int ensure_workspace(lzkp_pk *pk, Workspace &ws, uint32_t P) {
