@@ -40,7 +40,11 @@ namespace lzkp {
 namespace {
 
 constexpr uint32_t SENT = 0xFFFFFFFFu;
-constexpr int kChunk = 32;          // sorted pairs per thread in k_bucket_accum
+#ifndef LZKP_G2_CHUNK
+#define LZKP_G2_CHUNK 32
+#endif
+// sorted pairs per thread in k_bucket_accum
+template <class F> constexpr int chunk_of() { return sizeof(F) == sizeof(Fq) ? 32 : LZKP_G2_CHUNK; }
 constexpr int kSeg = 8;             // partial slots per thread in k_seg_reduce
 constexpr int kSegLevels = 2;       // balanced partial-reduction passes before the final merge
 constexpr int kMergeCap = 48;       // partials merged serially before a run counts as "long"
@@ -480,7 +484,7 @@ static int bases_prepare(MsmBases *B, const uint8_t *bases_bytes, size_t n, int 
     const size_t total = (size_t)n1 * B->W;
     B->key_bits = 1;
     while ((1ull << B->key_bits) < (uint64_t)B->sets * B->NB) B->key_bits++;
-    B->T = (uint32_t)((total + kChunk - 1) / kChunk);
+    B->T = (uint32_t)((total + chunk_of<F>() - 1) / chunk_of<F>());
     B->NG = B->NB / kGroup;
     B->LP = 0;
     while ((1u << B->LP) < B->NG) B->LP++;
@@ -548,22 +552,22 @@ static int msm_run(MsmBases *B, const Fr *d_scalars, uint32_t n_used, uint8_t *d
     uint32_t *count = B->count.as<uint32_t>();
     LAUNCH(k_find_count, 1, 1, 0, st, keys, (uint32_t)total, count);
     constexpr int AB = sizeof(F) == sizeof(Fq) ? 128 : 64;     // G2 runs at 255 registers: smaller CTAs fill the SMs better
-    LAUNCH((k_bucket_accum<F, kChunk, AB>), (B->T + AB - 1) / AB, AB, 0, st, keys, vals, count, B->points.as<Affine<F>>(),
+    LAUNCH((k_bucket_accum<F, chunk_of<F>(), AB>), (B->T + AB - 1) / AB, AB, 0, st, keys, vals, count, B->points.as<Affine<F>>(),
            B->buckets.as<X>(), B->pkey.as<uint32_t>(), B->ppt.as<X>());
     uint32_t *pk = B->pkey.as<uint32_t>();
     X *pp = B->ppt.as<X>();
     for (int l = 1; l <= kSegLevels; l++) {
         const size_t threads = (B->lvl_slots[l - 1] + kSeg - 1) / kSeg;
         LAUNCH((k_seg_reduce<F, kSeg>), (unsigned)((threads + 127) / 128), 128, 0, st, pk + B->lvl_off[l - 1],
-               pp + B->lvl_off[l - 1], count, (uint32_t)kChunk, (uint32_t)l, B->buckets.as<X>(), pk + B->lvl_off[l],
+               pp + B->lvl_off[l - 1], count, (uint32_t)chunk_of<F>(), (uint32_t)l, B->buckets.as<X>(), pk + B->lvl_off[l],
                pp + B->lvl_off[l]);
     }
     const size_t fin = B->lvl_slots[kSegLevels];
     LAUNCH((k_partial_merge<F>), (unsigned)((fin + 127) / 128), 128, 0, st, pk + B->lvl_off[kSegLevels],
-           pp + B->lvl_off[kSegLevels], count, (uint32_t)kChunk, (uint32_t)kSeg, (uint32_t)(kSegLevels + 1), B->buckets.as<X>(),
+           pp + B->lvl_off[kSegLevels], count, (uint32_t)chunk_of<F>(), (uint32_t)kSeg, (uint32_t)(kSegLevels + 1), B->buckets.as<X>(),
            B->long_list.as<uint32_t>());
     LAUNCH((k_long_run<F>), (unsigned)(fin / kMergeCap + 1), 128, 128 * sizeof(X), st, pk + B->lvl_off[kSegLevels],
-           pp + B->lvl_off[kSegLevels], count, (uint32_t)kChunk, (uint32_t)kSeg, (uint32_t)(kSegLevels + 1), B->buckets.as<X>(),
+           pp + B->lvl_off[kSegLevels], count, (uint32_t)chunk_of<F>(), (uint32_t)kSeg, (uint32_t)(kSegLevels + 1), B->buckets.as<X>(),
            B->long_list.as<uint32_t>());
     if (B->sets == 1) {
         const uint32_t nb1 = (B->NB + 128 * kRedSer - 1) / (128 * kRedSer);
