@@ -42,6 +42,19 @@ void fq_reduce_wide_host(const uint8_t *t64, uint8_t *o) {
     st(o, Fq::reduce_wide(T));
 }
 int fq_gt(const uint8_t *a, const uint8_t *b) { Fq x, y; ld(x, a); ld(y, b); return Fq::gt_canonical(x, y); }
+// k * P on G1 by ec.cuh's windowed scalar multiplication (host build of the same code): p = x || y canonical (64 B),
+// k canonical (32 B), nbits 128 or 254 picks scalar_mul_u128 / scalar_mul; out = affine x || y canonical, all zero = infinity
+void g1_scalar_mul_host(const uint8_t *p, const uint8_t *k, int nbits, uint8_t *out) {
+    Fq x, y; ld(x, p); ld(y, p + 32);
+    G1XYZZ P = G1XYZZ::from_affine(G1Affine{Fq::from_canonical(x), Fq::from_canonical(y)});
+    Fr s; ld(s, k);
+    G1XYZZ R;
+    if (nbits == 128) { uint32_t k4[4] = {s.l[0], s.l[1], s.l[2], s.l[3]}; R = scalar_mul_u128(P, k4); }
+    else R = scalar_mul(P, s);
+    G1Affine a = R.to_affine();
+    std::memset(out, 0, 64);
+    if (!a.is_inf()) { st(out, a.x.to_canonical()); st(out + 32, a.y.to_canonical()); }
+}
 // GLV split (ec.cuh): out = k1 (16 B) || k2 (16 B); returns neg1 | neg2 << 1 | ok << 2
 int glv_split_host(const uint8_t *k, uint8_t *out) {
     Fr x; ld(x, k);

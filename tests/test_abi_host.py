@@ -148,6 +148,27 @@ def test_lazy_fq2_product_on_host(field_shim, po):
         assert int.from_bytes(bytes(o), "little") == (a * b - c * d) * rinv % q
 
 
+def test_windowed_scalar_mul_on_host(field_shim, po):
+    """ec.cuh's signed 4-bit window scalar multiplication against the oracle's double-and-add."""
+    G = po.G1_GEN
+    rng = po.SplitMix64(321)
+    b32 = lambda v: (C.c_uint8 * 32)(*v.to_bytes(32, "little"))
+    def mul(pt, k, nbits):
+        o = (C.c_uint8 * 64)()
+        field_shim.g1_scalar_mul_host((C.c_uint8 * 64)(*(pt[0].to_bytes(32, "little") + pt[1].to_bytes(32, "little"))), b32(k), nbits, o)
+        x, y = int.from_bytes(bytes(o[:32]), "little"), int.from_bytes(bytes(o[32:]), "little")
+        return None if x == 0 and y == 0 else (x, y)
+    P = po.G1.mul(G, 0x1234567)
+    # digits of every shape: zero, carries running through all windows (0x88.., 0xff..), top-digit carry, r - 1
+    full = [0, 1, 7, 8, 9, 15, 16, po.R_MOD - 1, po.R_MOD - 2, (1 << 253) + 5, int("8" * 63, 16) % po.R_MOD] + \
+           [rng.next_fr() for _ in range(6)]
+    for k in full:
+        assert mul(P, k, 254) == po.G1.mul(P, k), hex(k)
+    half = [0, 1, 8, (1 << 128) - 1, (1 << 127), int("8" * 32, 16), int("7" * 32, 16)] + [rng.next_fr() >> 127 for _ in range(6)]
+    for k in half:
+        assert mul(P, k, 128) == po.G1.mul(P, k), hex(k)
+
+
 def test_glv_split_on_host(field_shim, po):
     """ec.cuh's GLV split: k == +-k1 +- k2 * lambda (mod r) with both halves below 2^128."""
     lam = 0x30644e72e131a029048b6e193fd84104cc37a73fec2bc5e9b8ca0b2d36636f23
