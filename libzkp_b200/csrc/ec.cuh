@@ -141,8 +141,11 @@ LZ_COLD XYZZ<F> scalar_mul_window(const XYZZ<F> &p, const uint32_t (&k)[LIMBS]) 
             const uint32_t cin = i ? (uint32_t)(carries >> (i - 1)) & 1u : 0u, cout = (uint32_t)(carries >> i) & 1u;
             d = (int)(((k[i >> 3] >> ((i & 7) * 4)) & 15u) + cin) - (int)(16u * cout);
         }
-        if (d > 0) acc.add_cold(T[d - 1]);
-        else if (d < 0) acc.add_cold(T[-d - 1].neg());
+        if (d != 0) {                        // one addition for both signs: lanes with opposite signs do not serialise
+            XYZZ<F> q = T[(d < 0 ? -d : d) - 1];
+            if (d < 0) q.y = q.y.neg();
+            acc.add_cold(q);
+        }
     }
     return acc;
 }

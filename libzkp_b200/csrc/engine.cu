@@ -693,7 +693,7 @@ static int run_prove(lzkp_pk *pk, Workspace &ws, uint32_t P, const Fr *d_r, cons
         }
         if (!d_proofs) return LZKP_OK;           // partial sums only (sharded proving): the caller combines
         Region reg(pk, LZKP_REGION_ASSEMBLE, st);
-        LAUNCH(k_assemble, 1, 192, 0, st, res1, ws.res2.as<G2XYZZ>(), pk->consts, d_r, d_s, 1u, d_proofs);
+        LAUNCH(k_assemble, 1, 128, 0, st, res1, ws.res2.as<G2XYZZ>(), pk->consts, d_r, d_s, 1u, d_proofs);
         return LZKP_OK;
     }
     const uint32_t c = pk->c, W = pk->W, gx = (P + 127) / 128;
@@ -727,7 +727,7 @@ static int run_prove(lzkp_pk *pk, Workspace &ws, uint32_t P, const Fr *d_r, cons
     { Region reg(pk, LZKP_REGION_MSM_G1, st); batch_msm_g1(args(pk->g1, fit_variant(pk->g1, item_variant(P)), ws.part1.p, ws.res1.p), st); }
     { Region reg(pk, LZKP_REGION_MSM_G2, st); batch_msm_g2(args(pk->g2, fit_variant(pk->g2, item_variant_g2(P)), ws.part2.p, ws.res2.p), st); }
     Region reg(pk, LZKP_REGION_ASSEMBLE, st);
-    LAUNCH(k_assemble, (P + 31) / 32, 192, 0, st, ws.res1.as<G1XYZZ>(), ws.res2.as<G2XYZZ>(), pk->consts, d_r, d_s, P, d_proofs);
+    LAUNCH(k_assemble, (P + 31) / 32, 128, 0, st, ws.res1.as<G1XYZZ>(), ws.res2.as<G2XYZZ>(), pk->consts, d_r, d_s, P, d_proofs);
     return LZKP_OK;
 }
 
@@ -1269,7 +1269,7 @@ int lzkp_prove_combine_device(lzkp_pk *pk, const void *d_partials, int n_partial
     TRY(ensure_workspace(pk, ws, 1));
     LAUNCH(k_sum_partials, 1, 32, 0, st, (const uint8_t *)d_partials, (uint32_t)n_partials, ws.res1.as<G1XYZZ>(),
            ws.res2.as<G2XYZZ>());
-    LAUNCH(k_assemble, 1, 192, 0, st, ws.res1.as<G1XYZZ>(), ws.res2.as<G2XYZZ>(), pk->consts, (const Fr *)d_r,
+    LAUNCH(k_assemble, 1, 128, 0, st, ws.res1.as<G1XYZZ>(), ws.res2.as<G2XYZZ>(), pk->consts, (const Fr *)d_r,
            (const Fr *)d_s, 1u, (uint8_t *)d_proof);
     CUDA_TRY(cudaGetLastError());
     return LZKP_OK;

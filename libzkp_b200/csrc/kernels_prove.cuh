@@ -364,39 +364,43 @@ __device__ __forceinline__ G1XYZZ glv_half(const G1XYZZ &P, const Fr &k, int hal
     if (half == 0 ? sp.neg1 : sp.neg2) Q.y = Q.y.neg();
     return half == 0 ? scalar_mul_u128(Q, sp.k1) : scalar_mul_u128(Q, sp.k2);
 }
-__global__ void __launch_bounds__(192) k_assemble(const G1XYZZ *g1, const G2XYZZ *g2, ProofConsts K, const Fr *r,
+// Four warps per 32 proofs, one per SM partition: warp w runs GLV strand w of C = s*A + r*B1 + ... (the long serial
+// chain), then warp 0 sums the strands and converts C, while warps 1 and 2 convert A and B (short) beside it.
+__global__ void __launch_bounds__(128) k_assemble(const G1XYZZ *g1, const G2XYZZ *g2, ProofConsts K, const Fr *r,
                                                   const Fr *s, uint32_t P, uint8_t *proofs) {
     __shared__ uint4 sm_raw[3 * 32 * sizeof(G1XYZZ) / 16];
     G1XYZZ *sm = reinterpret_cast<G1XYZZ *>(sm_raw);
     const uint32_t role = threadIdx.x >> 5, lane = threadIdx.x & 31, p = blockIdx.x * 32 + lane;
     const bool live = p < P;
     uint8_t *out = proofs + (size_t)p * 256;
-    G1XYZZ acc = G1XYZZ::inf();
+    G1XYZZ acc = G1XYZZ::inf(), A = G1XYZZ::inf();
     if (live) {
-        if (role <= 1 || role == 4) {
-            G1XYZZ A = ld_vec(g1 + p);
+        if (role <= 1) {
+            A = ld_vec(g1 + p);
             A.madd_cold(K.a0);
-            if (role == 4) write_g1(out, A.to_affine());
-            else if (role == 0) acc = glv_half(A, ld_vec(s + p), 0);
+            if (role == 0) acc = glv_half(A, ld_vec(s + p), 0);
             else st_vec(sm + lane, glv_half(A, ld_vec(s + p), 1));
-        } else if (role <= 3) {
+        } else {
             G1XYZZ B1 = ld_vec(g1 + (size_t)P + p);
             B1.madd_cold(K.b0);
             st_vec(sm + (role - 1) * 32 + lane, glv_half(B1, ld_vec(r + p), role - 2));
-        } else {
-            G2XYZZ B2 = ld_vec(g2 + p);
-            B2.madd_cold(K.b2);
-            write_g2(out + 64, B2.to_affine());
         }
     }
     __syncthreads();
-    if (role == 0 && live) {
+    if (!live) return;
+    if (role == 0) {
         acc.add_cold(ld_vec(sm + lane));
         acc.add_cold(ld_vec(sm + 32 + lane));
         acc.add_cold(ld_vec(sm + 64 + lane));
         acc.add_cold(ld_vec(g1 + 2 * (size_t)P + p));
         acc.add_cold(ld_vec(g1 + 3 * (size_t)P + p));
         write_g1(out + 192, acc.to_affine());
+    } else if (role == 1) {
+        write_g1(out, A.to_affine());
+    } else if (role == 2) {
+        G2XYZZ B2 = ld_vec(g2 + p);
+        B2.madd_cold(K.b2);
+        write_g2(out + 64, B2.to_affine());
     }
 }
 
