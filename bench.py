@@ -147,7 +147,18 @@ def toxic(seed):
 
 
 # ----------------------------------------------------------------------------- reference arm (CPU)
+def host_cores():
+    """Host threads this process may use.  torchrun exports OMP_NUM_THREADS=1 to every rank, which made the OpenMP
+    oracle run single-threaded at N > 1 in round 1; the thread count is therefore always passed explicitly."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def run_reference(args, rank, world):
+    """The reference's CPU prover path (oracle/: restatement of ark-groth16's create_proof, proof-parallel the way
+    src/advanced/batch.rs:123-131 maps a batch over rayon workers) on every host core, rank 0 only."""
     if rank != 0:
         return
     from oracle import c_oracle as co
@@ -155,35 +166,39 @@ def run_reference(args, rank, world):
     circ = co.Circuit("equality")
     pk_bytes, _ = circ.setup(toxic(1))
     opk = co.ProvingKey(pk_bytes)
-    cores = co.num_threads()
-    sample = args.ref_sample or max(cores * 4, 32)
+    cores = host_cores()
+    # a step = a bounded sample of the step's batch: proofs are independent, so proofs/s over the sample is the rate of
+    # the whole batch; sized for ~1 s per step (about 20 proofs/s per core)
+    sample = min(args.batch, args.ref_sample or max(cores * 16, 64))
     a = u64s(3, sample)
     r, s = fr_bytes(4, sample), fr_bytes(40, sample)
-    for _ in range(args.warmup):
-        co.prove_batch(circ, opk, a[:cores], a[:cores], None, None, r[:cores], s[:cores])
+    for _ in range(min(args.warmup, 2)):
+        co.prove_batch(circ, opk, a[:cores], a[:cores], None, None, r[:cores], s[:cores], threads=cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        proofs, status = co.prove_batch(circ, opk, a, a, None, None, r, s)
+        proofs, status = co.prove_batch(circ, opk, a, a, None, None, r, s, threads=cores)
     dt = time.perf_counter() - t0
     assert not status.any()
     v = sample * args.steps / dt
-    desc = f"{sample} of the {args.batch} equality proofs per step, proof-parallel over {cores} OpenMP threads"
+    desc = (f"each step proves the first {sample} of the batch's {args.batch} independent equality proofs, "
+            f"proof-parallel over {cores} OpenMP threads (explicit; OMP_NUM_THREADS is ignored)")
     print(json.dumps({
         "impl": "reference", "metric": "groth16_bn254_proofs_per_sec_batched", "value": v, "unit": "proofs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u256 (4x64-bit Montgomery limbs)",
-        "data": "synthetic", "config": config_dict(args, sample),
+        "data": "synthetic", "config": config_dict(args),
         "cpu_baseline": {"value": v, "unit": "proofs/s", "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": v, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "CPU restatement (C, OpenMP) of the arkworks prover the reference calls; not arkworks itself "
-                "(no Rust toolchain in this image)"}))
+                "(no Rust toolchain in this image). The reference's README quotes ~10 ms per proof per core "
+                "(/root/reference/README.md:327); this port takes ~48 ms, so a real arkworks arm would be ~5x faster."}))
 
 
-def config_dict(args, per_step=None):
+def config_dict(args):
     return {"workload": f"process_batch of {args.batch} prove_equality proofs per GPU (BASELINE.json configs[1]): "
                         "MiMC-5 equality circuit, m=332 constraints, domain n=512, MSM sizes 333/333/333(G2)/332/511",
-            "batch_per_gpu": args.batch, "proofs_per_step_timed": per_step or args.batch,
+            "batch_per_gpu": args.batch,
             "l2": "inputs larger than L2: every step gathers from the resident window tables "
                   "(62 GB at c=16, 116 GB at c=17) and rewrites > 126 MB of workspace"}
 
@@ -337,11 +352,12 @@ def run_ours(args, rank, world, local_rank):
         co.build()
         circ = co.Circuit("equality")
         opk = co.ProvingKey(pk_bytes)
-        cores = co.num_threads()
-        sample = max(cores * 8, 64)
-        co.prove_batch(circ, opk, a_h[:cores], a_h[:cores], None, None, r_h[:cores], s_h[:cores])
+        cores = host_cores()
+        sample = min(P, max(cores * 16, 64))
+        co.prove_batch(circ, opk, a_h[:cores], a_h[:cores], None, None, r_h[:cores], s_h[:cores], threads=cores)
         t0 = time.perf_counter()
-        want, wstat = co.prove_batch(circ, opk, a_h[:sample], a_h[:sample], None, None, r_h[:sample], s_h[:sample])
+        want, wstat = co.prove_batch(circ, opk, a_h[:sample], a_h[:sample], None, None, r_h[:sample], s_h[:sample],
+                                     threads=cores)
         dt = time.perf_counter() - t0
         assert np.array_equal(want, proofs_h[:sample]), "GPU proofs differ from the CPU oracle's"
         cpu = {"value": sample / dt, "unit": "proofs/s", "cores": cores, "kind": "port",

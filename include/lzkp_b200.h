@@ -65,8 +65,20 @@ typedef struct lzkp_pk_options {
 } lzkp_pk_options;
 #define LZKP_PARTIAL_BYTES 768   /* 4 G1 XYZZ sums (a, b1, l, h) + 1 G2 XYZZ sum (b2), opaque device format */
 
-/* Select the CUDA device(s) this process drives (one process per GPU: n_devices == 1). Idempotent. */
+/* Select the CUDA device(s) this process drives.  Idempotent; devices == NULL keeps / picks the default
+ * (LOCAL_RANK, else device 0).
+ *   n_devices == 1: one process per GPU (torchrun).
+ *   n_devices  > 1: ONE process drives several GPUs, the shape of the reference's batch path
+ *     (src/advanced/batch.rs:110-140 maps one batch over the workers of one process).  devices[0] is the primary.
+ *     Every proving key loaded afterwards (resident-table mode, unsharded) is replicated on each listed device -
+ *     tables, matrices, workspaces, two streams and pinned staging per device - and ONE host-buffer batch call
+ *     (lzkp_prove_batch, lzkp_prove_equality_batch / _enveloped, lzkp_prove_membership_batch / _enveloped) of at
+ *     least 512 proofs is cut into one contiguous block per device, each run by its own host thread, results
+ *     written to disjoint slices of the caller's buffers (order preserved, no gather step).  Smaller calls, the
+ *     *_device entry points, lzkp_msm*, lzkp_ntt*, lzkp_setup* and verification run on the primary device. */
 int lzkp_init(const int *devices, int n_devices);
+/* Devices of the list above (1 when lzkp_init was given none). */
+int lzkp_device_count(void);
 int lzkp_shutdown(void);
 const char *lzkp_last_error(void);
 /* Number of engine kernels launched by this process so far (bench.py's gpu_launches). */
@@ -140,7 +152,12 @@ int lzkp_builtin_witness(int kind, uint32_t param, uint64_t value, uint64_t othe
  * n_proofs x 32 B, proofs_out n_proofs x 256 B, status n_proofs ints (0 = ok). */
 int lzkp_prove_batch(lzkp_pk *pk, size_t n_proofs, const uint8_t *z, const uint8_t *r, const uint8_t *s,
                      uint8_t *proofs_out, int32_t *status);
-/* lzkp_prove_batch with every buffer in device memory, asynchronous on `stream`. */
+/* lzkp_prove_batch with every buffer in device memory, asynchronous on `stream`.
+ * Contract of every *_device entry point: the call returns once the work is ENQUEUED on `stream`; caller buffers
+ * must stay valid until `stream` has run it.  The key's internal workspaces are shared by all calls on that key:
+ * the engine records a last-use event per workspace and makes the next user - any stream, any entry point,
+ * host-buffer calls included - wait on it, so calls on one key from different (non-blocking) streams are ordered
+ * on the device in the order they were issued and never overlap inside a workspace. */
 int lzkp_prove_batch_device(lzkp_pk *pk, size_t n_proofs, const void *d_z, const void *d_r, const void *d_s,
                             void *d_proofs, void *d_status, void *stream);
 /* Equality batch (prove_equality_zk x n): a, b u64; commitments n x 32 B or NULL (then MiMC5(a) is

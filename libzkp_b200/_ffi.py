@@ -35,6 +35,7 @@ _vp, _sz, _int = C.c_void_p, C.c_size_t, C.c_int
 _u32, _u64 = C.c_uint32, C.c_uint64
 SIGNATURES = {
     "lzkp_init": (_int, [_vp, _int]),
+    "lzkp_device_count": (_int, []),
     "lzkp_shutdown": (_int, []),
     "lzkp_last_error": (C.c_char_p, []),
     "lzkp_kernel_launches": (_u64, []),

@@ -16,6 +16,16 @@ namespace eng {
 int fail(int code, const std::string &msg);      // records the thread-local message, returns code
 extern std::atomic<uint64_t> g_launches;         // kernels launched by this process (bench.py gpu_launches)
 int ensure_device();                             // LZKP_E_NO_DEVICE when no GPU: there is no CPU fallback
+int current_device();                            // the device ensure_device() binds the calling thread to (-1: none yet)
+// Binds the calling thread to one device of the engine's device list for the scope's lifetime (replica worker
+// threads of a multi-device proving key); ensure_device() inside the scope selects that device.
+struct DeviceScope {
+    int prev;
+    explicit DeviceScope(int dev);
+    ~DeviceScope();
+    DeviceScope(const DeviceScope &) = delete;
+    DeviceScope &operator=(const DeviceScope &) = delete;
+};
 
 struct DBuf {
     void *p = nullptr;

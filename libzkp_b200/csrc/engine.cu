@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <type_traits>
 #include <vector>
 
@@ -27,8 +28,10 @@ using namespace lzkp::eng;
 // ------------------------------------------------------------------------ plumbing
 static thread_local std::string g_err;
 static std::mutex g_mu;
-static int g_device = -1;
-static bool g_mimc_uploaded = false;
+static int g_device = -1;                       // primary device (devices[0] of lzkp_init)
+static std::vector<int> g_devices;               // every device lzkp_init named: a proving key is replicated on each
+static thread_local int t_device = -1;           // DeviceScope: the replica device this worker thread is bound to
+static uint64_t g_mimc_uploaded = 0;             // bit d: c_mimc has been uploaded to device d (constants are per device)
 static std::atomic<int> g_profile{0};
 
 namespace lzkp {
@@ -68,14 +71,25 @@ int ensure_device() {
         if (const char *lr = getenv("LOCAL_RANK")) dev = atoi(lr) % n;
         g_device = dev;
     }
-    CUDA_TRY(cudaSetDevice(g_device));
-    if (!g_mimc_uploaded) {
+    const int dev = t_device >= 0 ? t_device : g_device;
+    CUDA_TRY(cudaSetDevice(dev));
+    if (!(g_mimc_uploaded >> (dev & 63) & 1)) {
         std::vector<Fr> c(110);
         for (uint32_t i = 0; i < 110; i++) c[i] = host::mimc_constant(i);
         CUDA_TRY(cudaMemcpyToSymbol(c_mimc, c.data(), sizeof(Fr) * 110));
-        g_mimc_uploaded = true;
+        g_mimc_uploaded |= 1ull << (dev & 63);
     }
     return LZKP_OK;
+}
+int current_device() { return t_device >= 0 ? t_device : g_device; }
+DeviceScope::DeviceScope(int dev) : prev(t_device) {
+    t_device = dev;
+    cudaSetDevice(dev);
+}
+DeviceScope::~DeviceScope() {
+    t_device = prev;
+    const int back = prev >= 0 ? prev : g_device;
+    if (back >= 0) cudaSetDevice(back);
 }
 }  // namespace eng
 }  // namespace lzkp
@@ -118,13 +132,29 @@ struct Workspace {
     uint32_t chunk = 0;            // proofs the buffers are sized for
     DBuf z, abc, tmp, h, dig, r, s, rs, part1, part2, res1, res2, proofs, status, a, b, commit, sets, setlen, env, envlen;
     HBuf h_proofs, h_status, h_commit, h_env, h_envlen;
+    // Last use of these buffers, on whatever stream it was enqueued (the *_device entry points run on the caller's
+    // stream and return before the work has finished).  Every user waits on it before touching the workspace and
+    // re-records it when its own work is enqueued: ws_acquire / ws_release.  pk->mu only orders the ENQUEUES.
+    cudaEvent_t last_use = nullptr;
+    ~Workspace() { if (last_use) cudaEventDestroy(last_use); }
 };
+static int ws_acquire(Workspace &ws, cudaStream_t st) {
+    if (!ws.last_use) CUDA_TRY(cudaEventCreateWithFlags(&ws.last_use, cudaEventDisableTiming));
+    else CUDA_TRY(cudaStreamWaitEvent(st, ws.last_use, 0));
+    return LZKP_OK;
+}
+static int ws_release(Workspace &ws, cudaStream_t st) {
+    CUDA_TRY(cudaEventRecord(ws.last_use, st));
+    return LZKP_OK;
+}
 
 // pk->stream is a BLOCKING stream on purpose: setup-time uploads use synchronous cudaMemcpy from pageable
 // memory, whose DMA tail is only ordered against the legacy default stream and streams that synchronise
 // with it; a non-blocking stream could run the first kernel before the bytes have landed.
 struct lzkp_pk {
     std::mutex mu;
+    int device = 0;                          // the device every buffer below lives on
+    std::vector<lzkp_pk *> replicas;         // the same key on the other devices of lzkp_init's list (owned)
     uint32_t n_vars = 0, n_inst = 0, n_wit = 0, n = 0, log_n = 0, m = 0;
     bool has_circuit = false;
     int kind = -1;
@@ -164,6 +194,8 @@ struct lzkp_pk {
     double prof_ms[LZKP_PROFILE_REGIONS] = {0};
     uint64_t prof_count[LZKP_PROFILE_REGIONS] = {0};
     ~lzkp_pk() {
+        // (the caller has bound the thread to `device`: lzkp_pk_free / the replica loop below wrap the whole delete)
+        for (lzkp_pk *r : replicas) { DeviceScope ds(r->device); delete r; }
         for (auto &m : marks) { cudaEventDestroy(m.a); cudaEventDestroy(m.b); }
         for (MsmBases *b : {L_a, L_b1, L_b2, L_l, L_h}) if (b) msm_bases_free(b);
         for (auto s_ : L_st) if (s_) cudaStreamDestroy(s_);
@@ -814,6 +846,7 @@ static int run_batch_host(lzkp_pk *pk, size_t n, const uint8_t *r, const uint8_t
         Workspace &ws = pk->ws[w];
         cudaStream_t st = pk->chunk_stream(w);
         TRY(drain(w));                                    // the staging buffers of this workspace are free again
+        TRY(ws_acquire(ws, st));                          // ... and so are its device buffers (a *_device call may still run)
         TRY(ensure_workspace(pk, ws, P));
         TRY(ws.h_proofs.ensure((size_t)ws.chunk * 256)); TRY(ws.h_status.ensure((size_t)ws.chunk * 4));
         TRY(ws.h_commit.ensure((size_t)ws.chunk * 32));
@@ -834,6 +867,7 @@ static int run_batch_host(lzkp_pk *pk, size_t n, const uint8_t *r, const uint8_t
         }
         CUDA_TRY(cudaMemcpyAsync(ws.h_status.p, ws.status.p, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
         if (out.commit) CUDA_TRY(cudaMemcpyAsync(ws.h_commit.p, ws.commit.p, (size_t)P * 32, cudaMemcpyDeviceToHost, st));
+        TRY(ws_release(ws, st));
         pend.push_back({off, P, w});
     }
     TRY(drain(0));
@@ -859,11 +893,13 @@ static int run_batch_device(lzkp_pk *pk, size_t n, const void *d_r, const void *
         const uint32_t P = (uint32_t)std::min<size_t>(C, n - off);
         Workspace &ws = pk->ws[w];
         cudaStream_t st = fork ? pk->chunk_stream(w) : caller;
+        TRY(ws_acquire(ws, st));
         TRY(ensure_workspace(pk, ws, P));
         int32_t *stat = (int32_t *)d_status + off;
         CUDA_TRY(cudaMemsetAsync(stat, 0, (size_t)P * 4, st));
         TRY(prep(ws, off, P, stat, st));
         TRY(run_prove(pk, ws, P, (const Fr *)d_r + off, (const Fr *)d_s + off, (uint8_t *)d_proofs + off * 256, stat, st));
+        TRY(ws_release(ws, st));
     }
     if (fork) {
         for (int w = 0; w < 2; w++) {
@@ -875,20 +911,78 @@ static int run_batch_device(lzkp_pk *pk, size_t n, const void *d_r, const void *
     return LZKP_OK;
 }
 
+// ---- one call, every device: a replicated key cuts a host-buffer batch into one contiguous block per device and
+// runs each block on its own host thread (streams, workspaces and staging buffers are per replica); results land in
+// disjoint slices of the caller's buffers, so order is preserved and there is no gather step.
+static constexpr size_t kFanMinBlock = 256;      // below this a block is latency-bound: fewer devices are used
+static inline bool should_fan(const lzkp_pk *pk, size_t n) { return !pk->replicas.empty() && n >= 2 * kFanMinBlock; }
+static HostOut slice(HostOut o, size_t off) {
+    if (o.proofs) o.proofs += off * 256;
+    o.status += off;
+    if (o.commit) o.commit += off * 32;
+    if (o.env) { o.env += off * o.env_stride; o.env_len += off; }
+    return o;
+}
+template <class Fn>
+static int fan_out(lzkp_pk *pk, size_t n, Fn fn) {
+    const size_t G = std::min<size_t>(1 + pk->replicas.size(), std::max<size_t>(1, n / kFanMinBlock));
+    const size_t base = n / G, rem = n % G;
+    auto begin = [&](size_t g) { return g * base + std::min(g, rem); };
+    std::vector<int> rcs(G, LZKP_OK);
+    std::vector<std::string> errs(G);
+    std::vector<std::thread> th;
+    for (size_t g = 1; g < G; g++)
+        th.emplace_back([&, g] {
+            lzkp_pk *q = pk->replicas[g - 1];
+            DeviceScope ds(q->device);
+            rcs[g] = fn(q, begin(g), begin(g + 1) - begin(g));
+            if (rcs[g] != LZKP_OK) errs[g] = g_err;
+        });
+    rcs[0] = fn(pk, 0, begin(1));
+    if (rcs[0] != LZKP_OK) errs[0] = g_err;
+    for (auto &t : th) t.join();
+    for (size_t g = 0; g < G; g++)
+        if (rcs[g] != LZKP_OK) return fail(rcs[g], errs[g]);
+    return LZKP_OK;
+}
+
 #pragma GCC visibility push(default)
 extern "C" {
 
 int lzkp_init(const int *devices, int n_devices) {
     if (devices && n_devices > 0) {
+        int visible = 0;
+        if (cudaGetDeviceCount(&visible) != cudaSuccess || visible == 0) {
+            cudaGetLastError();
+            return fail(LZKP_E_NO_DEVICE, "no CUDA device: this engine has no CPU fallback");
+        }
+        if (n_devices > 64) return fail(LZKP_E_INVALID, "at most 64 devices");
+        for (int i = 0; i < n_devices; i++) {
+            if (devices[i] < 0 || devices[i] >= visible) return fail(LZKP_E_INVALID, "device index out of range");
+            for (int j = 0; j < i; j++) if (devices[j] == devices[i]) return fail(LZKP_E_INVALID, "device listed twice");
+        }
         std::lock_guard<std::mutex> lk(g_mu);
         if (g_device >= 0 && g_device != devices[0]) return fail(LZKP_E_STATE, "device already selected");
         g_device = devices[0];
+        // the list may grow on a later call (keys loaded before it keep the replicas they were loaded with)
+        if ((size_t)n_devices > g_devices.size()) g_devices.assign(devices, devices + n_devices);
     }
-    return ensure_device();
+    TRY(ensure_device());
+    std::vector<int> devs;
+    { std::lock_guard<std::mutex> lk(g_mu); devs = g_devices; }
+    for (size_t i = 1; i < devs.size(); i++) {           // contexts + constants of the other devices, now rather than mid-batch
+        DeviceScope ds(devs[i]);
+        TRY(ensure_device());
+    }
+    return LZKP_OK;
+}
+int lzkp_device_count(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    return g_devices.empty() ? (g_device >= 0 ? 1 : 0) : (int)g_devices.size();
 }
 int lzkp_shutdown(void) {        // releases the process-wide caches (NTT plans, generator tables); keys are freed by lzkp_pk_free
     if (g_device >= 0) cudaSetDevice(g_device);
-    ntt_plans_free();
+    ntt_plans_free();                  // (plans of every device: each is freed under its own device)
     generator_tables_free();
     return LZKP_OK;
 }
@@ -927,10 +1021,50 @@ int lzkp_pk_load_ex(const uint8_t *pk_bytes, size_t len, int validate, const lzk
     TRY(ensure_device());
     lzkp_pk *pk = new (std::nothrow) lzkp_pk();
     if (!pk) return fail(LZKP_E_NOMEM, "host allocation failed");
+    pk->device = current_device();
     int rc = pk_load_impl(pk_bytes, len, validate, opt, pk);
     if (rc != LZKP_OK) {
         delete pk;
         return rc;
+    }
+    // In-process multi-GPU (SURVEY.md 8e "Batched proving"; the reference's batch path is ONE process,
+    // src/advanced/batch.rs:110-140): the key, its tables and workspaces are replicated on every other device of
+    // lzkp_init's list, each replica loaded by its own host thread with the window size the primary chose.
+    std::vector<int> devs;
+    { std::lock_guard<std::mutex> lk(g_mu); devs = g_devices; }
+    const bool sharded = opt && opt->shard_count > 1;
+    if (devs.size() > 1 && !sharded && !pk->large && pk->device == devs[0]) {
+        lzkp_pk_options ro{};
+        if (opt) ro = *opt;
+        ro.window_bits = pk->c;
+        ro.max_chunk = pk->max_chunk;
+        const size_t R = devs.size() - 1;
+        std::vector<lzkp_pk *> reps(R, nullptr);
+        std::vector<int> rcs(R, LZKP_OK);
+        std::vector<std::string> errs(R);
+        std::vector<std::thread> th;
+        for (size_t i = 0; i < R; i++)
+            th.emplace_back([&, i] {
+                DeviceScope ds(devs[i + 1]);
+                int rc_ = ensure_device();
+                lzkp_pk *r = rc_ == LZKP_OK ? new (std::nothrow) lzkp_pk() : nullptr;
+                if (rc_ == LZKP_OK && !r) rc_ = fail(LZKP_E_NOMEM, "host allocation failed");
+                if (rc_ == LZKP_OK) {
+                    r->device = devs[i + 1];
+                    rc_ = pk_load_impl(pk_bytes, len, 0 /* the primary validated these bytes */, &ro, r);
+                }
+                if (rc_ != LZKP_OK) { errs[i] = g_err; delete r; r = nullptr; }
+                reps[i] = r;
+                rcs[i] = rc_;
+            });
+        for (auto &t : th) t.join();
+        for (size_t i = 0; i < R; i++)
+            if (rcs[i] != LZKP_OK) {
+                for (lzkp_pk *r : reps) if (r) { DeviceScope ds(r->device); delete r; }
+                delete pk;
+                return fail(rcs[i], "replica on device " + std::to_string(devs[i + 1]) + ": " + errs[i]);
+            }
+        pk->replicas = reps;
     }
     *out = pk;
     return LZKP_OK;
@@ -940,7 +1074,7 @@ int lzkp_pk_load(const uint8_t *pk_bytes, size_t len, int validate, lzkp_pk **ou
 }
 void lzkp_pk_free(lzkp_pk *pk) {
     if (!pk) return;
-    if (g_device >= 0) cudaSetDevice(g_device);
+    DeviceScope ds(pk->device);
     delete pk;
 }
 int lzkp_pk_info(const lzkp_pk *pk, uint64_t info[8]) {
@@ -966,7 +1100,15 @@ int lzkp_circuit_load(lzkp_pk *pk, uint32_t m, uint32_t n_inst, uint32_t n_wit, 
     const uint32_t *rp[3] = {a_rowptr, b_rowptr, c_rowptr}, *cl[3] = {a_col, b_col, c_col};
     const uint8_t *vl[3] = {a_val, b_val, c_val};
     pk->kind = -1;
-    return circuit_install(pk, m, n_inst, n_wit, rp, cl, vl);
+    TRY(circuit_install(pk, m, n_inst, n_wit, rp, cl, vl));
+    for (lzkp_pk *q : pk->replicas) {
+        DeviceScope ds(q->device);
+        TRY(ensure_device());
+        std::lock_guard<std::mutex> lq(q->mu);
+        q->kind = -1;
+        TRY(circuit_install(q, m, n_inst, n_wit, rp, cl, vl));
+    }
+    return LZKP_OK;
 }
 static host::R1cs synth(int kind, uint32_t param) {
     return kind == LZKP_CIRCUIT_EQUALITY ? host::synth_equality(param) : host::synth_membership(param);
@@ -987,6 +1129,14 @@ int lzkp_circuit_builtin(lzkp_pk *pk, int kind, uint32_t param) {
     TRY(circuit_install(pk, cs.m, cs.n_inst, cs.n_wit, rp, cl, vl));
     pk->kind = kind;
     pk->kind_param = param;
+    for (lzkp_pk *q : pk->replicas) {
+        DeviceScope ds(q->device);
+        TRY(ensure_device());
+        std::lock_guard<std::mutex> lq(q->mu);
+        TRY(circuit_install(q, cs.m, cs.n_inst, cs.n_wit, rp, cl, vl));
+        q->kind = kind;
+        q->kind_param = param;
+    }
     return LZKP_OK;
 }
 int lzkp_builtin_circuit_csr(int kind, uint32_t param, uint64_t shape[6], uint32_t *rowptr[3], uint32_t *col[3],
@@ -1062,6 +1212,12 @@ int lzkp_generator_mul(int group, const uint8_t *scalars, size_t n, uint8_t *out
 int lzkp_prove_batch(lzkp_pk *pk, size_t n_proofs, const uint8_t *z, const uint8_t *r, const uint8_t *s,
                      uint8_t *proofs_out, int32_t *status) {
     if (!pk || (n_proofs && (!z || !r || !s || !proofs_out || !status))) return fail(LZKP_E_INVALID, "null argument");
+    if (should_fan(pk, n_proofs)) {
+        const size_t zrow = (size_t)pk->n_vars * 32;
+        return fan_out(pk, n_proofs, [&](lzkp_pk *q, size_t off, size_t cnt) {
+            return lzkp_prove_batch(q, cnt, z + off * zrow, r + off * 32, s + off * 32, proofs_out + off * 256, status + off);
+        });
+    }
     TRY(ensure_device());
     std::lock_guard<std::mutex> lk(pk->mu);
     if (!pk->has_circuit) return fail(LZKP_E_STATE, "lzkp_circuit_load has not been called");
@@ -1105,6 +1261,11 @@ int lzkp_builtin_witness(int kind, uint32_t param, uint64_t value, uint64_t othe
 static int equality_batch_impl(lzkp_pk *pk, size_t n_proofs, const uint64_t *a, const uint64_t *b,
                                const uint8_t *commitments, const uint8_t *r, const uint8_t *s, HostOut out) {
     if (!pk || (n_proofs && (!a || !b || !r || !s || !out.status || (!out.proofs && !out.env)))) return fail(LZKP_E_INVALID, "null argument");
+    if (should_fan(pk, n_proofs))
+        return fan_out(pk, n_proofs, [&](lzkp_pk *q, size_t off, size_t cnt) {
+            return equality_batch_impl(q, cnt, a + off, b + off, commitments ? commitments + off * 32 : nullptr, r + off * 32,
+                                       s + off * 32, slice(out, off));
+        });
     TRY(ensure_device());
     std::lock_guard<std::mutex> lk(pk->mu);
     if (!pk->has_circuit || pk->kind != LZKP_CIRCUIT_EQUALITY) return fail(LZKP_E_STATE, "pk is not bound to the builtin equality circuit");
@@ -1142,6 +1303,12 @@ static int membership_batch_impl(lzkp_pk *pk, size_t n_proofs, const uint64_t *v
                                  const uint8_t *r, const uint8_t *s, HostOut out) {
     if (!pk || (n_proofs && (!value || !sets || !set_len || !r || !s || !out.status || (!out.proofs && !out.env))))
         return fail(LZKP_E_INVALID, "null argument");
+    if (n_proofs && set_stride == 0) return fail(LZKP_E_INVALID, "set_stride must be at least 1");
+    if (should_fan(pk, n_proofs))
+        return fan_out(pk, n_proofs, [&](lzkp_pk *q, size_t off, size_t cnt) {
+            return membership_batch_impl(q, cnt, value + off, sets + off * set_stride, set_len + off, set_stride,
+                                         commitments ? commitments + off * 32 : nullptr, r + off * 32, s + off * 32, slice(out, off));
+        });
     TRY(ensure_device());
     std::lock_guard<std::mutex> lk(pk->mu);
     if (!pk->has_circuit || pk->kind != LZKP_CIRCUIT_MEMBERSHIP) return fail(LZKP_E_STATE, "pk is not bound to the builtin membership circuit");
@@ -1176,7 +1343,8 @@ int lzkp_prove_membership_enveloped(lzkp_pk *pk, size_t n_proofs, const uint64_t
                                     int32_t *status) {
     if (n_proofs && (!envelopes_out || !envelope_len)) return fail(LZKP_E_INVALID, "null argument");
     if (!pk) return fail(LZKP_E_INVALID, "null argument");
-    if (envelope_stride < 10 + 4 + 8 * pk->kind_param + 256 + 32 && pk->kind == LZKP_CIRCUIT_MEMBERSHIP)
+    if (pk->kind != LZKP_CIRCUIT_MEMBERSHIP) return fail(LZKP_E_STATE, "pk is not bound to the builtin membership circuit");
+    if (envelope_stride < 10 + 4 + 8 * std::max(pk->kind_param, set_stride) + 256 + 32)
         return fail(LZKP_E_INVALID, "envelope_stride below 302 + 8 * set slots");
     HostOut out{nullptr, status, nullptr};
     out.env = envelopes_out; out.env_len = envelope_len; out.env_stride = envelope_stride; out.scheme = 4;
@@ -1210,10 +1378,12 @@ int lzkp_witness_map(lzkp_pk *pk, size_t n_proofs, const uint8_t *z, uint8_t *h_
     const size_t nv = pk->n_vars, n = pk->n;
     for (size_t off = 0; off < n_proofs; off += pk->max_chunk) {
         uint32_t P = (uint32_t)std::min<size_t>(pk->max_chunk, n_proofs - off);
+        TRY(ws_acquire(ws, st));
         TRY(ensure_workspace(pk, ws, P));
         CUDA_TRY(cudaMemcpyAsync(ws.z.p, z + off * nv * 32, (size_t)P * nv * 32, cudaMemcpyHostToDevice, st));
         TRY(run_witness_map(pk, ws, P, st));
         CUDA_TRY(cudaMemcpyAsync(h_out + off * n * 32, ws.h.p, (size_t)P * n * 32, cudaMemcpyDeviceToHost, st));
+        TRY(ws_release(ws, st));
         CUDA_TRY(cudaStreamSynchronize(st));
         CUDA_TRY(cudaGetLastError());
     }
@@ -1227,10 +1397,12 @@ int lzkp_witness_map_device(lzkp_pk *pk, const void *d_z, void *d_h, void *strea
     if (!pk->has_circuit) return fail(LZKP_E_STATE, "lzkp_circuit_load has not been called");
     cudaStream_t st = (cudaStream_t)stream;
     Workspace &ws = pk->ws[0];
+    TRY(ws_acquire(ws, st));
     TRY(ensure_workspace(pk, ws, 1));
     CUDA_TRY(cudaMemcpyAsync(ws.z.p, d_z, (size_t)pk->n_vars * 32, cudaMemcpyDeviceToDevice, st));
     TRY(run_witness_map(pk, ws, 1, st));
     CUDA_TRY(cudaMemcpyAsync(d_h, ws.h.p, (size_t)pk->n * 32, cudaMemcpyDeviceToDevice, st));
+    TRY(ws_release(ws, st));
     return LZKP_OK;
 }
 
@@ -1244,17 +1416,22 @@ int lzkp_prove_partial_device(lzkp_pk *pk, const void *d_z, const void *d_r, con
     if (!pk->large) return fail(LZKP_E_STATE, "sharded proving needs a large-domain proving key");
     cudaStream_t st = (cudaStream_t)stream;
     Workspace &ws = pk->ws[0];
+    TRY(ws_acquire(ws, st));
     TRY(ensure_workspace(pk, ws, 1));
     if (phase & 1) {
+        // the side streams of the previous proof must have left the scalar vectors (their join events are recorded
+        // in phase 2; waiting on a never-recorded event is a no-op)
+        for (auto ev : pk->L_ev_done) CUDA_TRY(cudaStreamWaitEvent(st, ev, 0));
         CUDA_TRY(cudaMemsetAsync(d_status, 0, 4, st));
         CUDA_TRY(cudaMemcpyAsync(ws.z.p, d_z, (size_t)pk->n_vars * 32, cudaMemcpyDeviceToDevice, st));
     }
     if (phase & 2) CUDA_TRY(cudaMemcpyAsync(ws.h.p, d_h, (size_t)pk->n * 32, cudaMemcpyDeviceToDevice, st));
     TRY(run_prove(pk, ws, 1, (const Fr *)d_r, (const Fr *)d_s, nullptr, (int32_t *)d_status, st, true, phase));
-    if (!(phase & 2)) return LZKP_OK;
+    if (!(phase & 2)) { TRY(ws_release(ws, st)); return LZKP_OK; }
     uint8_t *out = (uint8_t *)d_partial;
     CUDA_TRY(cudaMemcpyAsync(out, ws.res1.p, 4 * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(out + 4 * sizeof(G1XYZZ), ws.res2.p, sizeof(G2XYZZ), cudaMemcpyDeviceToDevice, st));
+    TRY(ws_release(ws, st));
     return LZKP_OK;
 }
 
@@ -1266,11 +1443,13 @@ int lzkp_prove_combine_device(lzkp_pk *pk, const void *d_partials, int n_partial
     if (!pk->large) return fail(LZKP_E_STATE, "sharded proving needs a large-domain proving key");
     cudaStream_t st = (cudaStream_t)stream;
     Workspace &ws = pk->ws[0];
+    TRY(ws_acquire(ws, st));
     TRY(ensure_workspace(pk, ws, 1));
     LAUNCH(k_sum_partials, 1, 32, 0, st, (const uint8_t *)d_partials, (uint32_t)n_partials, ws.res1.as<G1XYZZ>(),
            ws.res2.as<G2XYZZ>());
     LAUNCH(k_assemble, 1, 128, 0, st, ws.res1.as<G1XYZZ>(), ws.res2.as<G2XYZZ>(), pk->consts, (const Fr *)d_r,
            (const Fr *)d_s, 1u, (uint8_t *)d_proof);
+    TRY(ws_release(ws, st));
     CUDA_TRY(cudaGetLastError());
     return LZKP_OK;
 }

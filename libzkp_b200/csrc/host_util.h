@@ -205,7 +205,7 @@ inline R1cs synth_membership(uint32_t S) {
         cs.row({{sel0 + i, one}}, {{value, one}, {set0 + i, mone}}, {{p20 + i, one}}); // sel * (value - set)
     {
         std::vector<std::pair<uint32_t, Fr>> a;
-        for (uint32_t i = 0; i < S; i++) a.push_back({p20 + i, one});
+        for (uint32_t i = 0; i < S; i++) a.push_back({p20 + i, mone});                 // Var == Constant(0): (0 - sum) * 1 = 0
         cs.row(a, {{0, one}}, {});                                                     // sum == 0
     }
     return cs;

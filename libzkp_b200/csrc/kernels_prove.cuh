@@ -99,7 +99,7 @@ __global__ void k_witgen_membership(const uint64_t *value, const uint64_t *sets,
     uint32_t len = set_len[p];
     uint64_t v = value[p];
     uint32_t pos = 0xffffffffu;
-    if (len >= 1 && len <= S)
+    if (len >= 1 && len <= S && len <= set_stride)      // a row is set_stride wide: a longer claimed length is rejected, never read
         for (uint32_t i = 0; i < len; i++)
             if (set[i] == v) { pos = i; break; }
     if (pos == 0xffffffffu) { status[p] = 2; len = 0; }

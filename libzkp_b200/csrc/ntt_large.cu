@@ -184,11 +184,12 @@ __global__ void __launch_bounds__(1024) k_ntt_pass(const Fr *__restrict__ in, Fr
 // ---------------------------------------------------------------- plans (device tables per size/direction)
 struct NttPlan {
     uint32_t log_n = 0, n_pass = 0, bits[3] = {0, 0, 0}, tile_max = 0, lb = 0;
+    int device = 0;                                        // the tables live on this device
     eng::DBuf tile_tw, w_lo, w_hi, g_lo, g_hi, cross[2];   // cross[q]: per-position twiddles after pass q (optional)
     Fr ninv;
 };
 std::mutex g_plan_mu;
-std::map<uint32_t, NttPlan *> g_plans;     // key = log_n * 2 + inverse
+std::map<uint32_t, NttPlan *> g_plans;     // key = device * 256 + log_n * 2 + inverse
 
 Fr host_pow2k(Fr x, uint32_t k) {           // x^(2^k)
     for (uint32_t i = 0; i < k; i++) x = x.sqr();
@@ -201,11 +202,13 @@ namespace eng {
 
 static int get_plan(uint32_t log_n, int inverse, cudaStream_t st, NttPlan **out) {
     std::lock_guard<std::mutex> lk(g_plan_mu);
-    uint32_t key = log_n * 2 + (inverse ? 1 : 0);
+    const int dev = std::max(0, current_device());
+    uint32_t key = (uint32_t)dev * 256u + log_n * 2 + (inverse ? 1 : 0);
     auto it = g_plans.find(key);
     if (it != g_plans.end()) { *out = it->second; return LZKP_OK; }
     NttPlan *P = new NttPlan();
     P->log_n = log_n;
+    P->device = dev;
     // Measured on B200: tiles of <= 2^10 points run at the full 64 G products/s (several CTAs per SM hide the
     // barriers), 2^11-point tiles at ~78 % of it; an extra pass costs one product per element (cross twiddle table).
     static const uint32_t tile_bits = getenv("LZKP_NTT_TILE_BITS") ? (uint32_t)atoi(getenv("LZKP_NTT_TILE_BITS")) : 10u;
@@ -247,10 +250,10 @@ static int get_plan(uint32_t log_n, int inverse, cudaStream_t st, NttPlan **out)
     }
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
-    static bool attr_set = false;
-    if (!attr_set) {
+    static uint64_t attr_set = 0;              // function attributes are per device
+    if (!(attr_set >> (dev & 63) & 1)) {
         CUDA_TRY(cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
+        attr_set |= 1ull << (dev & 63);
     }
     g_plans[key] = P;
     *out = P;
@@ -260,7 +263,7 @@ static int get_plan(uint32_t log_n, int inverse, cudaStream_t st, NttPlan **out)
 // Releases the cached per-size tables (lzkp_shutdown).
 void ntt_plans_free() {
     std::lock_guard<std::mutex> lk(g_plan_mu);
-    for (auto &kv : g_plans) delete kv.second;
+    for (auto &kv : g_plans) { DeviceScope ds(kv.second->device); delete kv.second; }
     g_plans.clear();
 }
 

@@ -28,13 +28,20 @@ def _u8(a, shape_tail: int) -> np.ndarray:
     return a.reshape(-1, shape_tail)
 
 
-def init(device: Optional[int] = None) -> None:
-    """lzkp_init: bind this process to one CUDA device (one process per GPU)."""
+def init(device=None) -> None:
+    """lzkp_init: bind this process to one CUDA device (one process per GPU), or - given a sequence of device
+    indices - to several: proving keys loaded afterwards are replicated on each, and one host-buffer batch call
+    fans out over all of them (the reference's batch path is one process, src/advanced/batch.rs:110-140)."""
     if device is None:
         check(lib().lzkp_init(None, 0))
     else:
-        arr = (C.c_int * 1)(int(device))
-        check(lib().lzkp_init(arr, 1))
+        devs = [int(device)] if isinstance(device, (int, np.integer)) else [int(d) for d in device]
+        arr = (C.c_int * len(devs))(*devs)
+        check(lib().lzkp_init(arr, len(devs)))
+
+
+def device_count() -> int:
+    return int(lib().lzkp_device_count())
 
 
 def profile_enable(on: bool) -> None:

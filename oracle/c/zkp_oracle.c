@@ -562,7 +562,7 @@ static void synth_membership(cs_t *cs, uint32_t slots, uint64_t value, const uin
         lc_acc(&acc, &p.lc, 0);
         lc_free(&diff.lc); lc_free(&p.lc);
     }
-    cs_enforce_equal(cs, &acc, &zero);
+    cs_enforce_equal(cs, &zero, &acc);                    /* Var == Constant(0): ark-r1cs-std enforces (const - var) * 1 = 0 */
     for (uint32_t i = 0; i < slots; i++) { lc_free(&setv[i].lc); lc_free(&real[i].lc); lc_free(&sels[i].lc); }
     free(setv); free(real); free(sels);
     lc_free(&sum); lc_free(&one); lc_free(&acc); lc_free(&vv.lc); lc_free(&hv.lc); lc_free(&cv.lc);

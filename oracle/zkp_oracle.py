@@ -461,7 +461,8 @@ def membership_circuit(value: int, sel: Sequence[int], set_values: Sequence[int]
         diff = FpVar(value_var.val - set_vars[i].val, value_var.lc - set_vars[i].lc)
         p = cs.mul(sels[i], diff)
         acc = FpVar(acc.val + p.val, acc.lc + p.lc)
-    cs.enforce_equal(acc, FpVar(0, LC()))
+    # FpVar::Var == FpVar::Constant takes the branch c.conditional_enforce_equal(v): (c - v) * 1 = 0
+    cs.enforce_equal(FpVar(0, LC()), acc)
     return cs
 
 
