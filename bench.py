@@ -305,16 +305,34 @@ def run_ours(args, rank, world, local_rank):
            "d2h_bytes_per_step": P * (256 + 4 + 32), "steps": e2e_steps,
            "api": "lzkp_prove_equality_batch (C ABI, pinned host buffers)"}
 
+    # ---- N > 1: BASELINE.json configs[3] and configs[4], measured with every rank taking part, then ONE process
+    # driving all N GPUs (rank 0 alone, after the other ranks have left and released their devices)
+    multi = {}
+    work = pk.work()
+    engine_info = {"window_bits": pk.window_bits, "windows": pk.windows, "table_gb": pk.table_bytes / 1e9,
+                   "setup_s": t_setup, "pk_load_s": t_load}
+    if world > 1 and not args.no_extra:
+        pk.close()
+        torch.cuda.empty_cache()
+        dist.barrier()
+        multi["proof_2^20_sharded"] = bench_sharded_proof(torch, dist, dev, rank, world)
+        dist.barrier()
+        multi["mixed_batch_65536"] = bench_mixed_sharded(torch, dist, dev, rank, world)
+        torch.cuda.empty_cache()
+        dist.barrier()
+    if world > 1:
+        dist.destroy_process_group()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return
+    if world > 1 and not args.no_extra:
+        multi["single_process_fanout"] = bench_fanout(torch, world, pk_bytes, engine_info["window_bits"], P, a_p, r_p, s_p,
+                                                      proofs_h, e2e["value"], max(2, e2e_steps))
 
     # ---- roofline of the dominant kernel (G1 table MSM)
     peak, peak_src = imad_peak()
     # mixed additions per proof = (base, window) units the engine actually walks: identity points of the key
     # (variables absent from a matrix) are dropped at load and NOT counted as work
-    g1_units, g2_units, g1_rows, g2_rows = pk.work()
+    g1_units, g2_units, g1_rows, g2_rows = work
     ms_g1, n_g1 = regions["msm_g1"]
     imad_per_launch = P * g1_units * M_MADD_G1 * IMAD_PER_MUL
     achieved = imad_per_launch / (ms_g1 / max(n_g1, 1) * 1e-3) if ms_g1 else 0.0
@@ -384,13 +402,152 @@ def run_ours(args, rank, world, local_rank):
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u256 (8x32-bit Montgomery limbs, integer)",
         "data": "synthetic", "config": config_dict(args), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-        "roofline": roofline, "cpu_baseline": cpu, "extra": extra,
-        "engine": {"window_bits": pk.window_bits, "windows": pk.windows, "table_gb": pk.table_bytes / 1e9,
-                   "setup_s": t_setup, "pk_load_s": t_load},
+        "roofline": roofline, "cpu_baseline": cpu, "extra": {**extra, **multi}, "engine": engine_info,
     }
     print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+
+
+def _np_fr(rng, n):
+    """n canonical Fr scalars (below 2^252 < r), 32 B little-endian each."""
+    w = rng.integers(0, 2**63, size=(n, 4), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=(n, 4), dtype=np.uint64)
+    w[:, 3] &= np.uint64(0x0FFFFFFFFFFFFFFF)
+    return w.view(np.uint8).reshape(n, 32).copy()
+
+
+def bench_sharded_proof(torch, dist, dev, rank, world, rounds=349524, iters=5):
+    """BASELINE.json configs[3]: ONE proof of the 2^20-constraint circuit split across the N ranks (point ranges of the
+    five MSMs per rank, one NCCL gather of partial sums; libzkp_b200/multi.py).  ms per proof = device time, max over
+    ranks; rank 0 then proves the same statement on one GPU from the unsharded key and the bytes must be identical."""
+    from libzkp_b200 import engine
+    from libzkp_b200.multi import ShardedProver
+    pk_bytes, _ = engine.setup_builtin(engine.EQUALITY, rounds, toxic(1))       # deterministic: identical on every rank
+    t0 = time.perf_counter()
+    sp = ShardedProver(pk_bytes, engine.EQUALITY, rounds, rank, world, dev)
+    t_load = time.perf_counter() - t0
+    z = engine.builtin_witness(engine.EQUALITY, rounds, 6, 6) if rank == 0 else None
+    r, s = fr_bytes(4, 1)[0].tobytes(), fr_bytes(40, 1)[0].tobytes()
+    proof = sp.prove(z, r, s)
+    for _ in range(2):
+        sp.prove(resident=True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(iters):
+        sp.prove(resident=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([ev0.elapsed_time(ev1) / iters], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out = {"n_gpus": world, "constraints": 3 * rounds + 2, "domain": sp.n, "ms_per_proof": float(t.item()),
+           "shard_pk_load_s": t_load, "collectives_per_proof": sp.collectives_per_proof,
+           "witness_map_ranks": sp.map_ranks}
+    if rank == 0:
+        full = engine.ProvingKey(pk_bytes)
+        full.circuit_builtin(engine.EQUALITY, rounds)
+        rr, ss = np.frombuffer(r, np.uint8)[None], np.frombuffer(s, np.uint8)[None]
+        want, status = full.prove_batch(z[None], rr, ss)
+        d_z = torch.from_numpy(z).to(dev)
+        d_rs = torch.from_numpy(np.concatenate([rr, ss])).to(dev)
+        d_p, d_st = torch.zeros(256, dtype=torch.uint8, device=dev), torch.zeros(1, dtype=torch.int32, device=dev)
+        st = torch.cuda.current_stream().cuda_stream
+        one = lambda: full.prove_batch_device(1, d_z.data_ptr(), d_rs[0].data_ptr(), d_rs[1].data_ptr(), d_p.data_ptr(),
+                                              d_st.data_ptr(), st)
+        one(); one()
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(iters):
+            one()
+        ev1.record()
+        torch.cuda.synchronize()
+        out["one_gpu_ms_per_proof"] = ev0.elapsed_time(ev1) / iters
+        out["speedup_vs_one_gpu"] = out["one_gpu_ms_per_proof"] / out["ms_per_proof"]
+        out["bytes_identical_to_one_gpu_proof"] = bool(not status.any() and want[0].tobytes() == proof)
+        assert out["bytes_identical_to_one_gpu_proof"], "sharded proof differs from the single-GPU proof"
+        full.close()
+    sp.close()
+    return out
+
+
+def bench_mixed_sharded(torch, dist, dev, rank, world, total=65536, iters=3):
+    """BASELINE.json configs[4]: a 65 536-proof mixed batch (even operations equality, odd ones membership with 64
+    slots) sharded proof-parallel over the N ranks, both keys resident on every GPU; host buffers in, libzkp envelopes
+    out, INCLUDING the gather of all proof bytes to every rank.  Wall clock between barriers, max over ranks."""
+    from libzkp_b200 import engine, parallel
+    pk_e = engine.ProvingKey(engine.setup_builtin(engine.EQUALITY, 110, toxic(1))[0])
+    pk_e.circuit_builtin(engine.EQUALITY, 110)
+    pk_m = engine.ProvingKey(engine.setup_builtin(engine.MEMBERSHIP, 64, toxic(1))[0])
+    pk_m.circuit_builtin(engine.MEMBERSHIP, 64)
+    half = total // 2
+    rng = np.random.default_rng(7)                   # same seed on every rank: every rank holds the whole batch
+    a = rng.integers(0, 2**63, size=half, dtype=np.uint64)
+    sets = rng.integers(0, 2**63, size=(half, 64), dtype=np.uint64)
+    lens = np.full(half, 64, np.uint32)
+    vals = sets[np.arange(half), np.arange(half) % 64].copy()
+    r1, s1, r2, s2 = (_np_fr(rng, half) for _ in range(4))
+
+    def once():
+        return parallel.prove_mixed_enveloped_sharded(pk_e, pk_m, a, vals, sets, lens, r1, s1, r2, s2, rank, world, dev)
+    res = once()
+    best = None
+    for _ in range(iters):
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        res = once()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        best = float(t.item()) if best is None else min(best, float(t.item()))
+    env_e, len_e, st_e, env_m, len_m, st_m = res
+    ok = (not st_e.any() and not st_m.any() and (len_e == 298).all() and (len_m == 302 + 8 * 64).all()
+          and env_e.shape == (half, 298) and env_m.shape[0] == half)
+    # spot check of the gathered bytes: this rank re-proves two operations of ANOTHER rank's block
+    other = (rank + 1) % world
+    lo, _ = parallel.shard_range(half, other, world)
+    chk, _, _ = pk_e.prove_equality_enveloped(a[lo:lo + 2], a[lo:lo + 2], r1[lo:lo + 2], s1[lo:lo + 2])
+    ok = bool(ok and np.array_equal(chk, env_e[lo:lo + 2]))
+    out = {"n_gpus": world, "proofs": total, "ms_per_batch": 1e3 * best, "proofs_per_s_e2e": total / best,
+           "all_ok_and_gather_checked": ok, "tables_gb_per_gpu": (pk_e.table_bytes + pk_m.table_bytes) / 1e9,
+           "window_bits": [pk_e.window_bits, pk_m.window_bits],
+           "what": "host buffers -> envelopes on every rank (two all_gathers of bytes per kind), best of %d" % iters}
+    assert ok, "mixed sharded batch: failed proofs or gathered bytes differ"
+    pk_e.close()
+    pk_m.close()
+    return out
+
+
+def bench_fanout(torch, world, pk_bytes, window_bits, P, a_p, r_p, s_p, proofs_block0, e2e_one_job, steps):
+    """ONE process, N GPUs (the reference's batch path is one process: src/advanced/batch.rs:110-140): lzkp_init with
+    all N devices replicates the key; a single lzkp_prove_equality_batch call of N x P proofs fans out, one host
+    thread per device, results in disjoint slices of the caller's buffer.  Rank 0 runs this alone after the other
+    ranks have exited."""
+    from libzkp_b200 import engine
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < 120:                 # the other ranks' processes release their devices as they exit
+        if all(torch.cuda.mem_get_info(d)[0] > 150e9 for d in range(1, world)):
+            break
+        time.sleep(0.5)
+    engine.init(list(range(world)))
+    t0 = time.perf_counter()
+    pk = engine.ProvingKey(pk_bytes, window_bits=window_bits)
+    pk.circuit_builtin(engine.EQUALITY, 110)
+    t_load = time.perf_counter() - t0
+    n = world * P
+    rep = lambda x: np.ascontiguousarray(np.concatenate([x] * world))
+    a, r, s = rep(a_p), rep(r_p), rep(s_p)
+    proofs, _, status = pk.prove_equality_batch(a, a, r, s)
+    ok = bool(not status.any() and all(np.array_equal(proofs[g * P:(g + 1) * P], proofs_block0) for g in range(world)))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        pk.prove_equality_batch(a, a, r, s)
+    dt = (time.perf_counter() - t0) / steps
+    pk.close()
+    assert ok, "fan-out proofs differ from the one-GPU proofs of the same inputs"
+    return {"devices": world, "proofs_per_call": n, "ms_per_call": 1e3 * dt, "proofs_per_s_e2e": n / dt,
+            "vs_n_processes_e2e": (n / dt) / e2e_one_job, "bytes_equal_one_gpu_proofs": ok, "pk_load_all_devices_s": t_load,
+            "api": "one lzkp_prove_equality_batch call, host buffers, one process"}
 
 
 def bench_python_api(pk_bytes, P):

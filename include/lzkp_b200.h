@@ -193,13 +193,18 @@ int lzkp_prove_equality_batch_device(lzkp_pk *pk, size_t n_proofs, const void *d
 int lzkp_witness_map(lzkp_pk *pk, size_t n_proofs, const uint8_t *z, uint8_t *h_out);
 
 /* Device-resident pieces of ONE large-domain proof, for splitting it across GPUs (one process per GPU):
- *   lzkp_witness_map_device    z -> h on the rank that holds the circuit (then broadcast h, e.g. ncclBroadcast)
+ *   lzkp_witness_map_device    z -> h (for callers that want h itself)
  *   lzkp_prove_partial_device  every rank: the five MSMs over ITS point ranges -> LZKP_PARTIAL_BYTES.  phase 1 starts
- *                              the MSMs that only need z (so they run while rank 0 computes h), phase 2 adds the
- *                              H MSM and writes the partial sums; phase 0 or 3 = both in one call
+ *                              the MSMs that only need z, phase 2 adds the H MSM and writes the partial sums; phase 0
+ *                              or 3 = both in one call.  d_h == NULL: a shard that holds h_query points (the first
+ *                              `map_ranks` shards, lzkp_pk_shard_info) runs the witness map itself from z - h is never
+ *                              sent between GPUs - and needs lzkp_circuit_*; shards without h_query points skip it
  *   lzkp_prove_combine_device  one rank: add the gathered partial sums, assemble and serialize the proof
  * All pointers are device pointers; calls are asynchronous on `stream`. */
 int lzkp_witness_map_device(lzkp_pk *pk, const void *d_z, void *d_h, void *stream);
+/* This shard's point range [first, first + count) of the queries a, b1, l, h, b2 (the +-delta extras included) and the
+ * number of leading shards that run the witness map (and share the H query). */
+int lzkp_pk_shard_info(const lzkp_pk *pk, uint32_t first[5], uint32_t count[5], uint32_t *map_ranks);
 int lzkp_prove_partial_device(lzkp_pk *pk, const void *d_z, const void *d_r, const void *d_s, const void *d_h,
                               void *d_partial, void *d_status, void *stream, int phase);
 int lzkp_prove_combine_device(lzkp_pk *pk, const void *d_partials, int n_partials, const void *d_r, const void *d_s,

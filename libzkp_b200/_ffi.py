@@ -46,6 +46,7 @@ SIGNATURES = {
     "lzkp_pk_free": (None, [_vp]),
     "lzkp_pk_info": (_int, [_vp, C.POINTER(_u64)]),
     "lzkp_pk_work": (_int, [_vp, C.POINTER(_u64)]),
+    "lzkp_pk_shard_info": (_int, [_vp, C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32)]),
     "lzkp_circuit_load": (_int, [_vp, _u32, _u32, _u32] + [_vp] * 9),
     "lzkp_circuit_builtin": (_int, [_vp, _int, _u32]),
     "lzkp_builtin_circuit_csr": (_int, [_int, _u32, C.POINTER(_u64), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),

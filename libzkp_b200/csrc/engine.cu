@@ -6,6 +6,7 @@
 // same objects in process-wide OnceLocks, src/backend/snark.rs:295-339).
 #include <cuda_runtime.h>
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
@@ -183,7 +184,7 @@ struct lzkp_pk {
     cudaEvent_t L_ev_in = nullptr, L_ev_done[3] = {nullptr, nullptr, nullptr};
     // single-proof sharding across GPUs: this rank's point range [lo, lo + cnt) of each query,
     // in the order a, b1, l, h, b2 (extras +-delta included); unsharded = the full ranges
-    uint32_t shard_index = 0, shard_count = 1;
+    uint32_t shard_index = 0, shard_count = 1, map_ranks = 1;
     uint32_t L_lo[5] = {0, 0, 0, 0, 0}, L_cnt[5] = {0, 0, 0, 0, 0};
     cudaStream_t stream = nullptr, stream2 = nullptr;      // chunk i of a batch runs on streams[i & 1]
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
@@ -336,33 +337,44 @@ static int pk_load_impl(const uint8_t *bytes, size_t len, int validate, const lz
         pk->shard_count = opt && opt->shard_count > 1 ? opt->shard_count : 1;
         pk->shard_index = pk->shard_count > 1 ? opt->shard_index : 0;
         if (pk->shard_index >= pk->shard_count) return fail(LZKP_E_INVALID, "shard_index >= shard_count");
-        // cost-weighted split of the concatenation a | b1 | l | h | b2 (a G2 point costs ~2.8 G1 points)
+        // Cost-weighted split (a G2 point costs ~2.8 G1 points).  The witness map is NOT distributed and h is NOT
+        // broadcast: the first k ranks ("map ranks") each run the map themselves and share the H query between them;
+        // the z-only queries a | b1 | l | b2 are cut over all ranks so that every rank ends up with the same load
+        //   T = (W_z + W_h + k M) / G,     map rank: M + W_h / k + z-share,     other ranks: z-share = T
+        // with M the cost of one witness map in MSM weight units (measured at 2^20: 2.6 ms against 23.4 ms of MSMs).
+        // k is the smallest count whose spare capacity k (T - M) covers W_h (1 up to 4 GPUs, 3 at 8).
         const uint64_t sizes[5] = {nv, nv, (uint64_t)pk->n_wit + 1, (uint64_t)n - 1, nv}, wts[5] = {10, 10, 10, 10, 28};
-        uint64_t wtot = 0;
-        for (int q = 0; q < 5; q++) wtot += sizes[q] * wts[q];
-        // rank 0 also runs the witness map (and the final assembly), so it takes a smaller slice: measured at 2^20,
-        // the map costs ~8.5 % of one GPU's MSM time, i.e. a share of (1 - 0.085 G) relative to the other ranks
         const uint32_t G_ = pk->shard_count;
-        const double rho = G_ > 1 ? std::max(0.1, 1.0 - 0.085 * G_) : 1.0, denom = rho + (G_ - 1);
-        auto cut = [&](uint32_t i) -> uint64_t {      // weighted start of shard i
-            if (i == 0) return 0;
-            if (i >= G_) return wtot;
-            return (uint64_t)((rho + (i - 1)) / denom * (double)wtot);
-        };
-        const uint64_t w_lo = cut(pk->shard_index), w_hi = cut(pk->shard_index + 1);
-        uint64_t acc_w = 0;
-        for (int q = 0; q < 5; q++) {
-            // points of query q whose weighted start lies in [w_lo, w_hi)
-            auto first_at = [&](uint64_t w) -> uint64_t {        // smallest i with acc_w + i * wts >= w, clamped
+        const double Wh = (double)sizes[3] * wts[3];
+        double Wz = 0;
+        for (int q : {0, 1, 2, 4}) Wz += (double)sizes[q] * wts[q];
+        static const double map_frac = getenv("LZKP_SHARD_MAP_COST") ? atof(getenv("LZKP_SHARD_MAP_COST")) : 0.11;
+        const double M = G_ > 1 ? map_frac * (Wz + Wh) : 0.0;
+        uint32_t k = 1;
+        while (k < G_ && k * ((Wz + Wh + k * M) / G_ - M) < Wh) k++;
+        const double T = (Wz + Wh + k * M) / G_;
+        std::vector<double> cutz(G_ + 1, 0.0);
+        for (uint32_t i = 0; i < G_; i++) cutz[i + 1] = cutz[i] + (i < k ? std::max(0.0, T - M - Wh / k) : T);
+        for (uint32_t i = 0; i <= G_; i++) cutz[i] *= Wz / cutz[G_];                 // (clamping may leave a remainder)
+        pk->map_ranks = k;
+        const uint32_t me = pk->shard_index;
+        if (me < k) {
+            pk->L_lo[3] = (uint32_t)(sizes[3] * me / k);
+            pk->L_cnt[3] = (uint32_t)(sizes[3] * (me + 1) / k) - pk->L_lo[3];
+        } else {
+            pk->L_lo[3] = 0;
+            pk->L_cnt[3] = 0;
+        }
+        double acc_w = 0;
+        for (int q : {0, 1, 2, 4}) {
+            auto first_at = [&](double w) -> uint64_t {          // first point of query q at or after weighted position w
                 if (w <= acc_w) return 0;
-                uint64_t i = (w - acc_w + wts[q] - 1) / wts[q];
-                return std::min<uint64_t>(i, sizes[q]);
+                return std::min<uint64_t>((uint64_t)std::ceil((w - acc_w) / wts[q]), sizes[q]);
             };
-            uint64_t lo = first_at(w_lo), hi = first_at(w_hi);
-            if (pk->shard_index + 1 == pk->shard_count) hi = sizes[q];
+            uint64_t lo = first_at(cutz[me]), hi = me + 1 == G_ ? sizes[q] : first_at(cutz[me + 1]);
             pk->L_lo[q] = (uint32_t)lo;
             pk->L_cnt[q] = (uint32_t)(hi - lo);
-            acc_w += sizes[q] * wts[q];
+            acc_w += (double)sizes[q] * wts[q];
         }
         auto load1 = [&](std::vector<host::G1Canon> v, size_t skip, const host::G1Canon *extra, int q, MsmBases **out) {
             v.erase(v.begin(), v.begin() + skip);
@@ -394,6 +406,23 @@ static int pk_load_impl(const uint8_t *bytes, size_t len, int validate, const lz
         TRY(upload(d_misc1, misc1)); TRY(upload(d_misc2, misc2));
         LAUNCH(k_fq_to_mont, 1, 128, 0, st, d_misc1.as<Fq>(), misc1.size() * 2);
         LAUNCH(k_fq_to_mont, 1, 128, 0, st, d_misc2.as<Fq>(), misc2.size() * 4);
+        if (validate) {
+            // the queries were checked by msm_bases_load; here the remaining points deserialize_uncompressed validates
+            std::vector<host::G1Canon> v1 = gamma_abc;
+            v1.push_back(alpha_g1); v1.push_back(beta_g1); v1.push_back(delta_g1); v1.push_back(a_q[0]); v1.push_back(b1_q[0]);
+            std::vector<host::G2Canon> v2 = {beta_g2, gamma_g2, delta_g2, b2_q[0]};
+            DBuf d_v1, d_v2, d_bad;
+            TRY(upload(d_v1, v1)); TRY(upload(d_v2, v2)); TRY(d_bad.alloc(sizeof(int)));
+            CUDA_TRY(cudaMemsetAsync(d_bad.p, 0, sizeof(int), st));
+            LAUNCH(k_fq_to_mont, (unsigned)((v1.size() * 2 + 127) / 128), 128, 0, st, d_v1.as<Fq>(), v1.size() * 2);
+            LAUNCH(k_fq_to_mont, 1, 128, 0, st, d_v2.as<Fq>(), v2.size() * 4);
+            LAUNCH(k_check_g1, (unsigned)((v1.size() + 63) / 64), 64, 0, st, d_v1.as<G1Affine>(), (uint32_t)v1.size(), d_bad.as<int>());
+            LAUNCH(k_check_g2, 1, 64, 0, st, d_v2.as<G2Affine>(), (uint32_t)v2.size(), d_bad.as<int>());
+            int bad = 0;
+            CUDA_TRY(cudaMemcpyAsync(&bad, d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            if (bad) return fail(LZKP_E_INVALID, "proving key: " + std::to_string(bad) + " point(s) off-curve or outside the subgroup");
+        }
         TRY(d_out1.alloc(2 * sizeof(G1Affine))); TRY(d_out2.alloc(sizeof(G2Affine)));
         LAUNCH((k_affine_add<Fq>), 1, 1, 0, st, d_misc1.as<G1Affine>() + 0, d_misc1.as<G1Affine>() + 2, d_out1.as<G1Affine>() + 0, 0);
         LAUNCH((k_affine_add<Fq>), 1, 1, 0, st, d_misc1.as<G1Affine>() + 1, d_misc1.as<G1Affine>() + 3, d_out1.as<G1Affine>() + 1, 0);
@@ -717,7 +746,7 @@ static int run_prove(lzkp_pk *pk, Workspace &ws, uint32_t P, const Fr *d_r, cons
         }
         }
         if (!(phase & 2)) return LZKP_OK;
-        if (!have_h) TRY(run_witness_map(pk, ws, P, st));
+        if (!have_h && cnt[3]) TRY(run_witness_map(pk, ws, P, st));      // a shard without h_query points skips the map
         TRY(msm_device_raw(pk->L_h, ws.h.as<uint8_t>() + (size_t)lo[3] * 32, cnt[3], res1 + 3, st));
         for (int i = 0; i < 3; i++) {
             CUDA_TRY(cudaEventRecord(pk->L_ev_done[i], pk->L_st[i]));
@@ -1085,6 +1114,14 @@ int lzkp_pk_info(const lzkp_pk *pk, uint64_t info[8]) {
     return LZKP_OK;
 }
 
+int lzkp_pk_shard_info(const lzkp_pk *pk, uint32_t first[5], uint32_t count[5], uint32_t *map_ranks) {
+    if (!pk || !first || !count) return fail(LZKP_E_INVALID, "null argument");
+    if (!pk->large) return fail(LZKP_E_STATE, "not a large-domain proving key");
+    for (int q = 0; q < 5; q++) { first[q] = pk->L_lo[q]; count[q] = pk->L_cnt[q]; }
+    if (map_ranks) *map_ranks = pk->map_ranks;
+    return LZKP_OK;
+}
+
 int lzkp_pk_work(const lzkp_pk *pk, uint64_t work[4]) {
     if (!pk || !work) return fail(LZKP_E_INVALID, "null argument");
     work[0] = pk->g1.n_units; work[1] = pk->g2.n_units; work[2] = pk->g1.n_rows; work[3] = pk->g2.n_rows;
@@ -1409,11 +1446,13 @@ int lzkp_witness_map_device(lzkp_pk *pk, const void *d_z, void *d_h, void *strea
 int lzkp_prove_partial_device(lzkp_pk *pk, const void *d_z, const void *d_r, const void *d_s, const void *d_h,
                               void *d_partial, void *d_status, void *stream, int phase) {
     if (phase == 0) phase = 3;
-    if (!pk || !d_r || !d_s || !d_status || ((phase & 1) && !d_z) || ((phase & 2) && (!d_h || !d_partial)))
+    if (!pk || !d_r || !d_s || !d_status || ((phase & 1) && !d_z) || ((phase & 2) && !d_partial))
         return fail(LZKP_E_INVALID, "null argument");
     TRY(ensure_device());
     std::lock_guard<std::mutex> lk(pk->mu);
     if (!pk->large) return fail(LZKP_E_STATE, "sharded proving needs a large-domain proving key");
+    if ((phase & 2) && !d_h && pk->L_cnt[3] && !pk->has_circuit)
+        return fail(LZKP_E_STATE, "this shard holds h_query points: pass h, or bind the circuit so that it runs the witness map itself");
     cudaStream_t st = (cudaStream_t)stream;
     Workspace &ws = pk->ws[0];
     TRY(ws_acquire(ws, st));
@@ -1425,8 +1464,8 @@ int lzkp_prove_partial_device(lzkp_pk *pk, const void *d_z, const void *d_r, con
         CUDA_TRY(cudaMemsetAsync(d_status, 0, 4, st));
         CUDA_TRY(cudaMemcpyAsync(ws.z.p, d_z, (size_t)pk->n_vars * 32, cudaMemcpyDeviceToDevice, st));
     }
-    if (phase & 2) CUDA_TRY(cudaMemcpyAsync(ws.h.p, d_h, (size_t)pk->n * 32, cudaMemcpyDeviceToDevice, st));
-    TRY(run_prove(pk, ws, 1, (const Fr *)d_r, (const Fr *)d_s, nullptr, (int32_t *)d_status, st, true, phase));
+    if ((phase & 2) && d_h) CUDA_TRY(cudaMemcpyAsync(ws.h.p, d_h, (size_t)pk->n * 32, cudaMemcpyDeviceToDevice, st));
+    TRY(run_prove(pk, ws, 1, (const Fr *)d_r, (const Fr *)d_s, nullptr, (int32_t *)d_status, st, d_h != nullptr, phase));
     if (!(phase & 2)) { TRY(ws_release(ws, st)); return LZKP_OK; }
     uint8_t *out = (uint8_t *)d_partial;
     CUDA_TRY(cudaMemcpyAsync(out, ws.res1.p, 4 * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, st));
@@ -1445,7 +1484,7 @@ int lzkp_prove_combine_device(lzkp_pk *pk, const void *d_partials, int n_partial
     Workspace &ws = pk->ws[0];
     TRY(ws_acquire(ws, st));
     TRY(ensure_workspace(pk, ws, 1));
-    LAUNCH(k_sum_partials, 1, 32, 0, st, (const uint8_t *)d_partials, (uint32_t)n_partials, ws.res1.as<G1XYZZ>(),
+    LAUNCH(k_sum_partials, 1, 160, 0, st, (const uint8_t *)d_partials, (uint32_t)n_partials, ws.res1.as<G1XYZZ>(),
            ws.res2.as<G2XYZZ>());
     LAUNCH(k_assemble, 1, 128, 0, st, ws.res1.as<G1XYZZ>(), ws.res2.as<G2XYZZ>(), pk->consts, (const Fr *)d_r,
            (const Fr *)d_s, 1u, (uint8_t *)d_proof);

@@ -436,10 +436,11 @@ __global__ void __launch_bounds__(128) k_envelope(const uint8_t *proofs, const u
 }
 
 // Sharded single proof: partial[i] = 4 G1 XYZZ sums (a, b1, l, h) then 1 G2 XYZZ sum (b2) of rank i's point ranges.
-// Thread q < 4 adds up slot q over the ranks, thread 4 the G2 slot.
+// Warp q < 4 adds up G1 slot q over the ranks, warp 4 the G2 slot (one lane each: five independent chains side by side).
 constexpr uint32_t kPartialBytes = 4 * sizeof(G1XYZZ) + sizeof(G2XYZZ);
 __global__ void k_sum_partials(const uint8_t *partials, uint32_t n, G1XYZZ *g1, G2XYZZ *g2) {
-    const uint32_t q = threadIdx.x;
+    const uint32_t q = threadIdx.x >> 5;
+    if (threadIdx.x & 31) return;
     if (q < 4) {
         G1XYZZ acc = G1XYZZ::inf();
         for (uint32_t i = 0; i < n; i++)

@@ -409,8 +409,17 @@ __global__ void k_check_on_curve(const Affine<F> *pts, uint32_t n, int *bad) {
     if (i >= n) return;
     Affine<F> p = ld_vec(pts + i);
     bool ok;
-    if constexpr (sizeof(F) == sizeof(Fq)) ok = g1_on_curve(p);
-    else ok = g2_on_curve(p);
+    if constexpr (sizeof(F) == sizeof(Fq)) ok = g1_on_curve(p);       // G1 has cofactor 1: on the curve = in the group
+    else {
+        ok = g2_on_curve(p);
+        if (ok && !p.is_inf()) {       // r-torsion test, as deserialize_uncompressed does: (r - 1) P == -P
+            Fr rm1 = Fr::modulus();
+            rm1.l[0] -= 1;
+            XYZZ<F> t = scalar_mul(XYZZ<F>::from_affine(p), rm1);
+            t.madd_cold(p);
+            ok = t.is_inf();
+        }
+    }
     if (!ok) atomicAdd(bad, 1);
 }
 
@@ -476,7 +485,7 @@ static int bases_prepare(MsmBases *B, const uint8_t *bases_bytes, size_t n, int 
         LAUNCH((k_check_on_curve<F>), (B->n + 127) / 128, 128, 0, 0, B->points.as<Affine<F>>(), B->n, B->bad.as<int>());
         int bad = 0;
         CUDA_TRY(cudaMemcpy(&bad, B->bad.p, sizeof(int), cudaMemcpyDeviceToHost));
-        if (bad) return fail(LZKP_E_INVALID, "MSM bases: " + std::to_string(bad) + " point(s) not on the curve");
+        if (bad) return fail(LZKP_E_INVALID, "MSM bases: " + std::to_string(bad) + " point(s) off-curve or outside the subgroup");
     }
     if (B->resident && n)
         LAUNCH((k_precompute_windows<F>), (B->n + 127) / 128, 128, 0, 0, B->points.as<Affine<F>>(), B->n, B->c, B->W);

@@ -68,6 +68,17 @@ __device__ __noinline__ bool read_g2_checked(const uint8_t *b, G2Affine &p) {
 }
 
 // e(alpha, beta) once per key (what process_vk precomputes)
+// What VerifyingKey::deserialize_uncompressed (Validate::Yes, snark.rs:66) checks: every point of the key is on its
+// curve and, in G2, in the r-torsion.  One thread per point of the raw ark-serialize bytes.
+__global__ void k_vk_validate(const uint8_t *vk_bytes, uint32_t n_abc, int *bad) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool ok = true;
+    if (i == 0) { G1Affine p; ok = read_g1_checked(vk_bytes, p); }
+    else if (i < 4) { G2Affine q; ok = read_g2_checked(vk_bytes + 64 + 128 * (i - 1), q); }
+    else if (i < 4 + n_abc) { G1Affine p; ok = read_g1_checked(vk_bytes + 456 + 64 * (size_t)(i - 4), p); }
+    if (!ok) atomicAdd(bad, 1);
+}
+
 __global__ void k_vk_prepare(VkDev *vk) {
     G1Affine P[1] = {vk->alpha};
     G2Affine Q[1] = {vk->beta};
@@ -181,6 +192,16 @@ int vk_load(const uint8_t *bytes, size_t len, VerifyingKeyDev **out) {
         if (!q.y1.is_zero()) sub8(r.y1.l, m.l, q.y1.l);
         return r;
     };
+    {
+        DBuf d_raw, d_bad;
+        TRY(d_raw.alloc(len)); TRY(d_bad.alloc(sizeof(int)));
+        CUDA_TRY(cudaMemcpy(d_raw.p, bytes, len, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemset(d_bad.p, 0, sizeof(int)));
+        LAUNCH(k_vk_validate, (unsigned)((cnt + 4 + 63) / 64), 64, 0, 0, d_raw.as<uint8_t>(), (uint32_t)cnt, d_bad.as<int>());
+        int bad = 0;
+        CUDA_TRY(cudaMemcpy(&bad, d_bad.p, sizeof(int), cudaMemcpyDeviceToHost));
+        if (bad) return fail(LZKP_E_INVALID, "verifying key: " + std::to_string(bad) + " point(s) off-curve or outside the subgroup");
+    }
     VerifyingKeyDev *V = new (std::nothrow) VerifyingKeyDev();
     if (!V) return fail(LZKP_E_NOMEM, "host allocation failed");
     V->n_pub = (uint32_t)cnt - 1;

@@ -146,6 +146,12 @@ class ProvingKey:
         check(lib().lzkp_pk_work(self._h, w))
         return tuple(int(x) for x in w)
 
+    def shard_info(self):
+        """(first[5], count[5], map_ranks): this shard's point ranges of a, b1, l, h, b2 (large-domain keys)."""
+        first, count, k = (C.c_uint32 * 5)(), (C.c_uint32 * 5)(), C.c_uint32()
+        check(lib().lzkp_pk_shard_info(self._h, first, count, C.byref(k)))
+        return list(first), list(count), int(k.value)
+
     def close(self):
         if self._h:
             lib().lzkp_pk_free(self._h)

@@ -31,7 +31,9 @@ _key_dir_override: Optional[str] = None
 _setups: Dict[str, object] = {}      # prefix -> Setup | Exception text (OnceLock<Result<..>>)
 # Test / deployment hook: a callable(prefix) -> (pk_bytes, vk_bytes) used when no key files exist.
 _generator: Optional[Callable[[str], Tuple[bytes, bytes]]] = None
-_pk_options = {"window_bits": 0, "table_budget_bytes": 0, "max_chunk": 0, "validate": False}
+# validate None = the reference's behaviour: keys READ FROM FILES are validated (deserialize_uncompressed checks curve and
+# subgroup membership, snark.rs:64-66), keys this process just generated are not
+_pk_options = {"window_bits": 0, "table_budget_bytes": 0, "max_chunk": 0, "validate": None}
 
 
 class OsRng:
@@ -73,7 +75,7 @@ class Setup:
         return self._vk
 
 
-def configure(window_bits: int = 0, table_budget_bytes: int = 0, max_chunk: int = 0, validate: bool = False,
+def configure(window_bits: int = 0, table_budget_bytes: int = 0, max_chunk: int = 0, validate: Optional[bool] = None,
               generator: Optional[Callable[[str], Tuple[bytes, bytes]]] = None) -> None:
     """Engine options used when a setup is first loaded (window size of the resident tables, ...)."""
     global _generator
@@ -135,7 +137,7 @@ def _generate(prefix: str) -> Tuple[bytes, bytes]:
     return _setup.generate(prefix)
 
 
-def _load_or_generate(prefix: str) -> Tuple[bytes, bytes]:   # snark.rs:122-139
+def _load_or_generate(prefix: str) -> Tuple[bytes, bytes, bool]:   # snark.rs:122-139; third item: read from files
     paths = _key_paths(prefix)
     if paths is not None:
         pk_path, vk_path = paths
@@ -144,7 +146,7 @@ def _load_or_generate(prefix: str) -> Tuple[bytes, bytes]:   # snark.rs:122-139
                 pk = f.read()
             with open(vk_path, "rb") as f:
                 vk = f.read()
-            return pk, vk
+            return pk, vk, True
         pk, vk = _generate(prefix)
         try:                                       # best effort, errors ignored (snark.rs:130-132)
             os.makedirs(os.path.dirname(pk_path) or ".", exist_ok=True)
@@ -154,8 +156,9 @@ def _load_or_generate(prefix: str) -> Tuple[bytes, bytes]:   # snark.rs:122-139
                 f.write(vk)
         except OSError:
             pass
-        return pk, vk
-    return _generate(prefix)
+        return pk, vk, False
+    pk, vk = _generate(prefix)
+    return pk, vk, False
 
 
 _CIRCUITS = {"equality_mimc": (engine.EQUALITY, MIMC_ROUNDS), "membership_mimc": (engine.MEMBERSHIP, MAX_SET_SIZE)}
@@ -167,9 +170,10 @@ def _get_setup(prefix: str):
         got = _setups.get(prefix)
         if got is None:
             try:
-                pk_bytes, vk_bytes = _load_or_generate(prefix)
+                pk_bytes, vk_bytes, from_file = _load_or_generate(prefix)
                 o = _pk_options
-                pk = engine.ProvingKey(pk_bytes, validate=o["validate"], window_bits=o["window_bits"],
+                validate = from_file if o["validate"] is None else bool(o["validate"])
+                pk = engine.ProvingKey(pk_bytes, validate=validate, window_bits=o["window_bits"],
                                        table_budget_bytes=o["table_budget_bytes"], max_chunk=o["max_chunk"])
                 kind, param = _CIRCUITS[prefix]
                 pk.circuit_builtin(kind, param)

@@ -80,6 +80,18 @@ def _worker(rank, world, port, q):
             raise AssertionError("batch id must be consumed")
         except InvalidInput:
             pass
+        # byte gather of per-rank blocks (the proof bytes of a sharded batch): uneven blocks, operation order
+        import numpy as np
+        for n_total in (11, 4, 1, 0):
+            lo, hi = parallel.shard_range(n_total, rank, world)
+            full = (np.arange(n_total * 5, dtype=np.int64) % 251).astype(np.uint8).reshape(n_total, 5)
+            got = parallel.gather_rows(full[lo:hi], n_total)
+            assert got.shape == (n_total, 5) and np.array_equal(got, full), (n_total, got)
+        try:
+            parallel.gather_rows(np.zeros((3, 5), np.uint8), 11)
+            raise AssertionError("wrong block size must be rejected")
+        except ValueError:
+            pass
         q.put((rank, "ok"))
     except Exception as e:                          # noqa: BLE001
         q.put((rank, repr(e)))

@@ -42,6 +42,8 @@ if rank == 0:
     full = engine.ProvingKey(pk_bytes)
     full.circuit_builtin(engine.EQUALITY, rounds)
     want, status = full.prove_batch(z[None], np.frombuffer(r, np.uint8)[None], np.frombuffer(s, np.uint8)[None])
-    print({"world": world, "n": sp.n, "ms_per_proof": 1e3 * dt, "matches_single_gpu": want[0].tobytes() == proof})
+    import json
+    print(json.dumps({"world": world, "n": sp.n, "ms_per_proof": 1e3 * dt, "map_ranks": sp.map_ranks,
+                      "matches_single_gpu": bool(not status.any() and want[0].tobytes() == proof)}))
 if world > 1:
     dist.destroy_process_group()
