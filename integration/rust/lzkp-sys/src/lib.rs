@@ -27,6 +27,7 @@ pub const LZKP_CIRCUIT_MEMBERSHIP: c_int = 1;
 
 extern "C" {
     pub fn lzkp_init(devices: *const c_int, n_devices: c_int) -> c_int;
+    pub fn lzkp_device_count() -> c_int;
     pub fn lzkp_last_error() -> *const c_char;
     pub fn lzkp_pk_load_ex(pk: *const u8, len: usize, validate: c_int, opt: *const lzkp_pk_options,
                            out: *mut *mut lzkp_pk) -> c_int;
@@ -94,6 +95,11 @@ impl DevicePk {
     pub fn prove_equality(&self, a: &[u64], b: &[u64], commitments: &[[u8; 32]], r: &[[u8; 32]],
                           s: &[[u8; 32]]) -> Result<Vec<Option<[u8; 256]>>, String> {
         let n = a.len();
+        // the C side reads n entries from every slice: a shorter one would be an out-of-bounds read from safe code
+        if b.len() != n || commitments.len() != n || r.len() != n || s.len() != n {
+            return Err(format!("prove_equality: slice lengths differ (a {}, b {}, commitments {}, r {}, s {})",
+                               n, b.len(), commitments.len(), r.len(), s.len()));
+        }
         let mut proofs = vec![0u8; 256 * n];
         let mut status = vec![0i32; n];
         let rc = unsafe {

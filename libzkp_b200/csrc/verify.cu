@@ -72,10 +72,15 @@ __device__ __noinline__ bool read_g2_checked(const uint8_t *b, G2Affine &p) {
 // curve and, in G2, in the r-torsion.  One thread per point of the raw ark-serialize bytes.
 __global__ void k_vk_validate(const uint8_t *vk_bytes, uint32_t n_abc, int *bad) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool ok = true;
-    if (i == 0) { G1Affine p; ok = read_g1_checked(vk_bytes, p); }
-    else if (i < 4) { G2Affine q; ok = read_g2_checked(vk_bytes + 64 + 128 * (i - 1), q); }
-    else if (i < 4 + n_abc) { G1Affine p; ok = read_g1_checked(vk_bytes + 456 + 64 * (size_t)(i - 4), p); }
+    if (i >= 4 + n_abc) return;
+    // the readers use 128-bit loads; offsets inside a key (456 + 64 i) are only 8-byte aligned: stage the point
+    __align__(16) uint8_t buf[128];
+    const uint8_t *src = i == 0 ? vk_bytes : i < 4 ? vk_bytes + 64 + 128 * (i - 1) : vk_bytes + 456 + 64 * (size_t)(i - 4);
+    const uint32_t len = (i >= 1 && i < 4) ? 128 : 64;
+    for (uint32_t b = 0; b < len; b++) buf[b] = src[b];
+    bool ok;
+    if (len == 128) { G2Affine q; ok = read_g2_checked(buf, q); }
+    else { G1Affine p; ok = read_g1_checked(buf, p); }
     if (!ok) atomicAdd(bad, 1);
 }
 
