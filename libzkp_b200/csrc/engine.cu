@@ -944,7 +944,10 @@ static int run_batch_device(lzkp_pk *pk, size_t n, const void *d_r, const void *
 // runs each block on its own host thread (streams, workspaces and staging buffers are per replica); results land in
 // disjoint slices of the caller's buffers, so order is preserved and there is no gather step.
 static constexpr size_t kFanMinBlock = 256;      // below this a block is latency-bound: fewer devices are used
-static inline bool should_fan(const lzkp_pk *pk, size_t n) { return !pk->replicas.empty() && n >= 2 * kFanMinBlock; }
+static thread_local bool t_in_fan = false;       // set while a thread runs ONE block of a fan-out (the primary's block must not fan out again)
+static inline bool should_fan(const lzkp_pk *pk, size_t n) {
+    return !t_in_fan && !pk->replicas.empty() && n >= 2 * kFanMinBlock;
+}
 static HostOut slice(HostOut o, size_t off) {
     if (o.proofs) o.proofs += off * 256;
     o.status += off;
@@ -964,10 +967,13 @@ static int fan_out(lzkp_pk *pk, size_t n, Fn fn) {
         th.emplace_back([&, g] {
             lzkp_pk *q = pk->replicas[g - 1];
             DeviceScope ds(q->device);
+            t_in_fan = true;
             rcs[g] = fn(q, begin(g), begin(g + 1) - begin(g));
             if (rcs[g] != LZKP_OK) errs[g] = g_err;
         });
+    t_in_fan = true;
     rcs[0] = fn(pk, 0, begin(1));
+    t_in_fan = false;
     if (rcs[0] != LZKP_OK) errs[0] = g_err;
     for (auto &t : th) t.join();
     for (size_t g = 0; g < G; g++)

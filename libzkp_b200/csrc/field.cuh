@@ -185,6 +185,26 @@ LZ_HD uint32_t sub8(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b
     return bw;
 }
 
+// Column accumulator (t0, t1, t2) += a * b: the 64-bit product joins (t0, t1) and the carry out joins t2.  ptxas emits
+// IMAD.WIDE.U32 with a carry-OUT predicate and folds the carries of two consecutive products into one IADD3.X.
+// (Measured on B200, tools/microbench/imadrate.cu: every 32x32->64 multiply-add form - plain, carry-out, carry-in
+// .X, IMAD.HI - issues at the same ~31.7 lanes per SM per clock, so product and column scanning cost the same per
+// limb product; column scanning is used where it needs FEWER limb products: squaring.)
+LZ_HD void mac3(uint32_t &t0, uint32_t &t1, uint32_t &t2, uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+        "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+        "addc.u32 %2, %2, 0;" : "+r"(t0), "+r"(t1), "+r"(t2) : "r"(a), "r"(b));
+#else
+    uint64_t p = (uint64_t)a * b;
+    uint64_t lo = (uint64_t)t0 + (uint32_t)p;
+    uint64_t hi = (uint64_t)t1 + (uint32_t)(p >> 32) + (lo >> 32);
+    t0 = (uint32_t)lo;
+    t1 = (uint32_t)hi;
+    t2 += (uint32_t)(hi >> 32);
+#endif
+}
+
 // --------------------------------------------------------------------------
 // Double-width arithmetic (lazy reduction in Fq2): a 16-limb product without reduction, and the Montgomery reduction
 // of a 16-limb value, so that c0 = a0 b0 - a1 b1 and c1 = (a0+a1)(b0+b1) - a0 b0 - a1 b1 take three multiplications
@@ -496,7 +516,45 @@ struct alignas(16) Fp {
         add8(s, X, hi);
         return reduce_once(s);
     }
-    LZ_HD Fp sqr() const { return *this * *this; }
+    // a^2 * R^-1 by column scanning with the reduction interleaved (FIPS): 36 + 64 limb products instead of 64 + 64.
+    //   a^2 = sum_i a_i B^i * (a_i B^i + 2 * (a div B^(i+1)) * B^(i+1)):  row i multiplies a_i by a_i, by
+    //   e_(i+1) = 2 a_(i+1) mod 2^32 (bit 0 clear) and by d_j = limb j of 2a (j > i + 1); 2a < 2^256 because a < 2^255.
+    // Measured 79 G squarings/s against 64 G products/s (tools/microbench/mulcs.cu), bit-exact against operator*.
+    LZ_HD Fp sqr() const {
+#ifdef LZKP_SQR_AS_MUL           // A/B switch: the round-1 behaviour (a full product)
+        return *this * *this;
+#endif
+        uint32_t d[8], e[8];
+        d[0] = l[0] << 1;
+        e[0] = 0;
+#pragma unroll
+        for (int i = 1; i < 8; i++) { d[i] = (l[i] << 1) | (l[i - 1] >> 31); e[i] = l[i] << 1; }
+        uint32_t t0 = 0, t1 = 0, t2 = 0, m[8], r[8];
+#pragma unroll
+        for (int k = 0; k < 15; k++) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int j = k - i;
+                if (j < i || j > 7) continue;
+                if (j == i) mac3(t0, t1, t2, l[i], l[i]);
+                else if (j == i + 1) mac3(t0, t1, t2, l[i], e[j]);
+                else mac3(t0, t1, t2, l[i], d[j]);
+            }
+            if (k < 8) {
+#pragma unroll
+                for (int i = 0; i < k; i++) mac3(t0, t1, t2, m[i], P::MOD(k - i));
+                m[k] = t0 * P::INV;
+                mac3(t0, t1, t2, m[k], P::MOD(0));
+            } else {
+#pragma unroll
+                for (int i = k - 7; i < 8; i++) mac3(t0, t1, t2, m[i], P::MOD(k - i));
+                r[k - 8] = t0;
+            }
+            t0 = t1; t1 = t2; t2 = 0;
+        }
+        r[7] = t0;
+        return reduce_once(r);
+    }
     // Montgomery reduction of a 16-limb T < p * 2^256: T * R^-1 mod p = (T_lo + M p) / R + T_hi, where the eight
     // rounds run on the lower half alone (U = (T_lo + M p) / R <= p) in the product's aligned / offset accumulators,
     // and T_hi < p joins at the end: U + T_hi < 2p.
