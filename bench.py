@@ -535,8 +535,8 @@ def bench_fanout(torch, world, pk_bytes, window_bits, P, a_p, r_p, s_p, proofs_b
     pk.circuit_builtin(engine.EQUALITY, 110)
     t_load = time.perf_counter() - t0
     n = world * P
-    rep = lambda x: np.ascontiguousarray(np.concatenate([x] * world))
-    a, r, s = rep(a_p), rep(r_p), rep(s_p)
+    rep = lambda x: torch.from_numpy(np.ascontiguousarray(np.concatenate([x] * world)).view(np.uint8)).pin_memory().numpy()
+    a, r, s = rep(a_p).view(np.uint64), rep(r_p).reshape(n, 32), rep(s_p).reshape(n, 32)
     proofs, _, status = pk.prove_equality_batch(a, a, r, s)
     ok = bool(not status.any() and all(np.array_equal(proofs[g * P:(g + 1) * P], proofs_block0) for g in range(world)))
     t0 = time.perf_counter()

@@ -166,6 +166,12 @@ struct lzkp_pk {
     uint32_t max_chunk = 8192;
     uint32_t n_dig_rows = 0, nz = 0;
     MsmPlan g1, g2;
+    // Latency form for small calls (P <= latency_limit()): s*A and r*B1 of the assembly become two more fixed-base table
+    // MSMs over the a / b1 rows with the scalars s*z_i / r*z_i (digit rows row_sz / row_rz), so the proof's tail is
+    // a handful of additions and three inversions instead of two 254-bit variable-base scalar multiplications.
+    MsmPlan g1_lat;                 // six MSMs: a, b1, l, h, s*A, r*B1 (shares g1.table)
+    uint32_t row_sz = 0, row_rz = 0;
+    bool has_lat = false;
     ProofConsts consts;
     // circuit
     DBuf csr_rowptr[3], csr_col[3], csr_val[3];
@@ -452,6 +458,30 @@ static int pk_load_impl(const uint8_t *bytes, size_t len, int validate, const lz
         msm1[1].push_back({ROW_S, rd1});      // B1 += s * delta_g1
         msm1[2].push_back({ROW_RS, rnd1});    // C  -= rs * delta_g1 (folded into the L sum)
     }
+    // latency form: C = s*(alpha + a0) + r*(beta + b0) + sum (s z_i) a_i + sum (r z_i) b_i + 2 rs delta + [L - rs delta] + H
+    std::vector<std::vector<BaseRef>> msm1_lat;
+    {
+        pk->row_sz = pk->n_dig_rows;
+        pk->row_rz = pk->n_dig_rows + pk->nz;
+        msm1_lat = msm1;
+        msm1_lat.resize(6);
+        for (auto &b : msm1[0]) if (b.dig_row < pk->nz) msm1_lat[4].push_back({pk->row_sz + b.dig_row, b.tbl_row});
+        for (auto &b : msm1[1]) if (b.dig_row < pk->nz) msm1_lat[5].push_back({pk->row_rz + b.dig_row, b.tbl_row});
+        // the three constant points, computed with the host build of the same field / curve code
+        auto mont = [](const host::G1Canon &c) { return G1Affine{Fq::from_canonical(c.x), Fq::from_canonical(c.y)}; };
+        auto canon = [](const G1Affine &m) { host::G1Canon c; c.x = m.x.to_canonical(); c.y = m.y.to_canonical(); return c; };
+        auto sum2 = [&](const host::G1Canon &u, const host::G1Canon &v) {
+            G1XYZZ t = host::is_inf(u) ? G1XYZZ::inf() : G1XYZZ::from_affine(mont(u));
+            if (!host::is_inf(v)) t.madd(mont(v));
+            return t.is_inf() ? host::G1Canon{Fq::zero(), Fq::zero()} : canon(t.to_affine());
+        };
+        const host::G1Canon a0c = sum2(alpha_g1, a_q[0]), b0c = sum2(beta_g1, b1_q[0]), d2c = sum2(delta_g1, delta_g1);
+        if (!host::is_inf(a0c)) msm1_lat[4].push_back({ROW_S, add1(a0c)});
+        if (!host::is_inf(b0c)) msm1_lat[5].push_back({ROW_R, add1(b0c)});
+        if (!host::is_inf(d2c)) msm1_lat[5].push_back({ROW_RS, add1(d2c)});
+        pk->n_dig_rows += 2 * pk->nz;
+        pk->has_lat = true;
+    }
     for (uint32_t j = 1; j < nv; j++)
         if (!host::is_inf(b2_q[j])) { rows2.push_back(b2_q[j]); msm2[0].push_back({j - 1, (uint32_t)rows2.size() - 1}); }
     if (!host::is_inf(delta_g2)) { rows2.push_back(delta_g2); msm2[0].push_back({ROW_S, (uint32_t)rows2.size() - 1}); }
@@ -485,6 +515,10 @@ static int pk_load_impl(const uint8_t *bytes, size_t len, int validate, const lz
     CUDA_TRY(cudaStreamCreate(&pk->stream2));
     CUDA_TRY(cudaEventCreateWithFlags(&pk->ev_fork, cudaEventDisableTiming));
     for (auto &ev : pk->ev_join) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    // side stream of the latency form (small calls: the G2 MSM beside the witness map and the G1 MSMs)
+    CUDA_TRY(cudaStreamCreateWithFlags(&pk->L_st[0], cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&pk->L_ev_in, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&pk->L_ev_done[0], cudaEventDisableTiming));
     cudaStream_t st = pk->stream;
 
     // --- upload points, to Montgomery, optional validation ---
@@ -539,6 +573,7 @@ static int pk_load_impl(const uint8_t *bytes, size_t len, int validate, const lz
     if (!rows2.empty())
         TRY(build_table_g2(d_rows2.p, (uint32_t)rows2.size(), c, pk->W, pk->N, pk->g2.table.p, st));
     TRY(finish_plan(pk->g1, msm1, pk->W));
+    TRY(finish_plan(pk->g1_lat, msm1_lat, pk->W));
     TRY(finish_plan(pk->g2, msm2, pk->W));
     // proofs per device pass: two workspaces must fit beside the tables
     {
@@ -626,6 +661,13 @@ static inline int fit_variant(const MsmPlan &pl, int v) {
     while (v < 3 && pl.n_items[v] > 65535u) v++;
     return v;
 }
+// Calls of at most this many proofs take the latency form (fixed-base s*A + r*B1, k_assemble_sums): +47 % G1 MSM work,
+// which is free while the call is latency-bound.  LZKP_LATENCY_BATCH overrides (0 disables).
+static inline uint32_t latency_limit() {
+    static const uint32_t v = getenv("LZKP_LATENCY_BATCH") ? (uint32_t)atoi(getenv("LZKP_LATENCY_BATCH")) : 128u;
+    return v;
+}
+static inline bool use_lat(const lzkp_pk *pk, uint32_t P) { return pk->has_lat && P <= latency_limit() && P <= small_batch_limit(); }
 static inline int item_variant_g2(uint32_t P) {
     // 32-unit items at every batch size: the G2 grid then is several waves of its 148 x 6 resident CTAs (with 128-unit
     // items a 4096-proof batch was 1.87 waves and paid for 2: measured 7.59 -> 7.06 ms; lengths 24..37 are within 2 %)
@@ -636,6 +678,7 @@ static int ensure_workspace(lzkp_pk *pk, Workspace &ws, uint32_t P) {
     size_t part1 = 0, part2 = 0;       // worst case over the batch sizes <= P
     for (uint32_t pp : {std::min(P, small_batch_limit()), std::min(P, 255u), std::min(P, 2047u), P}) {
         part1 = std::max(part1, (size_t)pk->g1.n_items[fit_variant(pk->g1, item_variant(pp))] * pp);
+        if (use_lat(pk, pp)) part1 = std::max(part1, (size_t)pk->g1_lat.n_items[fit_variant(pk->g1_lat, item_variant(pp))] * pp);
         part2 = std::max(part2, (size_t)pk->g2.n_items[fit_variant(pk->g2, item_variant_g2(pp))] * pp);
     }
     const size_t nv = pk->n_vars, n = pk->n;
@@ -651,7 +694,7 @@ static int ensure_workspace(lzkp_pk *pk, Workspace &ws, uint32_t P) {
     TRY(ws.r.ensure(P * 32)); TRY(ws.s.ensure(P * 32)); TRY(ws.rs.ensure(P * 32));
     TRY(ws.part1.ensure(part1 * sizeof(G1XYZZ)));
     TRY(ws.part2.ensure(part2 * sizeof(G2XYZZ)));
-    TRY(ws.res1.ensure((size_t)4 * P * sizeof(G1XYZZ)));
+    TRY(ws.res1.ensure((size_t)6 * P * sizeof(G1XYZZ)));
     TRY(ws.res2.ensure((size_t)P * sizeof(G2XYZZ)));
     TRY(ws.proofs.ensure((size_t)P * 256));
     TRY(ws.status.ensure((size_t)P * sizeof(int32_t)));
@@ -760,34 +803,72 @@ static int run_prove(lzkp_pk *pk, Workspace &ws, uint32_t P, const Fr *d_r, cons
     const uint32_t c = pk->c, W = pk->W, gx = (P + 127) / 128;
     void *dig = ws.dig.p;
     const uint32_t dig_bytes = pk->c > 16 ? 4u : 2u;      // signed c-bit digits: int16 up to c = 16
-    // One stream, stage after stage.  (Measured on B200: running the witness map and the G1 half of the assembly on
-    // a side stream underneath the MSM kernels gains < 2 % without stream priority - their CTAs only get SMs in the
-    // MSM kernel's last wave - and LOSES 2 % with priority, because a latency-bound CTA that holds 17k registers
-    // displaces a quarter of an SM's MSM warps while issuing almost nothing.  Overlap happens across chunks instead.)
-    if (!have_h) TRY(run_witness_map(pk, ws, P, st));
-    {
-    Region reg(pk, LZKP_REGION_DIGITS, st);
-    LAUNCH(k_fr_mul_canonical, gx, 128, 0, st, d_r, d_s, ws.rs.as<Fr>(), P);
+    const bool lat = use_lat(pk, P);
     const uint32_t ymax = 32768u;
-    auto digits = [&](auto *dg) -> int {
+    // digits of z, r, s, rs (everything but h); the latency form adds the rows s * z_i and r * z_i
+    auto digits_z = [&](auto *dg) -> int {
         using DigT = std::remove_pointer_t<decltype(dg)>;
         LAUNCH(k_digits<DigT>, dim3(gx, std::min(pk->nz, ymax)), 128, 0, st, ws.z.as<Fr>(), pk->n_vars, 1u, dg, 0u, P, c, W, d_status, pk->nz);
         LAUNCH(k_digits<DigT>, dim3(gx, 1), 128, 0, st, d_r, 1u, 0u, dg, pk->nz, P, c, W, d_status, 1u);
         LAUNCH(k_digits<DigT>, dim3(gx, 1), 128, 0, st, d_s, 1u, 0u, dg, pk->nz + 1, P, c, W, d_status, 1u);
         LAUNCH(k_digits<DigT>, dim3(gx, 1), 128, 0, st, ws.rs.as<Fr>(), 1u, 0u, dg, pk->nz + 2, P, c, W, d_status, 1u);
+        if (lat) {
+            LAUNCH(k_digits_scaled<DigT>, dim3(gx, std::min(pk->nz, ymax)), 128, 0, st, ws.z.as<Fr>(), pk->n_vars, 1u, d_s, dg, pk->row_sz, P, c, W, pk->nz);
+            LAUNCH(k_digits_scaled<DigT>, dim3(gx, std::min(pk->nz, ymax)), 128, 0, st, ws.z.as<Fr>(), pk->n_vars, 1u, d_r, dg, pk->row_rz, P, c, W, pk->nz);
+        }
+        return LZKP_OK;
+    };
+    auto digits_h = [&](auto *dg) -> int {
+        using DigT = std::remove_pointer_t<decltype(dg)>;
         LAUNCH(k_digits<DigT>, dim3(gx, std::min(pk->n - 1, ymax)), 128, 0, st, ws.h.as<Fr>(), pk->n, 0u, dg, pk->nz + 3, P, c, W, d_status,
                pk->n - 1);
         return LZKP_OK;
     };
-    if (dig_bytes == 2) TRY(digits((int16_t *)dig)); else TRY(digits((int32_t *)dig));
-    }
     auto args = [&](MsmPlan &pl, int iv, void *partial, void *out) {
         return BatchMsmArgs{pl.table.p, pk->N, pl.unit_dig.as<uint32_t>(), pl.unit_tbl.as<uint32_t>(), pl.items[iv].p,
                             pl.n_items[iv], pl.msm_items[iv].p, pl.n_msm, dig, dig_bytes, P, partial, out};
     };
-    { Region reg(pk, LZKP_REGION_MSM_G1, st); batch_msm_g1(args(pk->g1, fit_variant(pk->g1, item_variant(P)), ws.part1.p, ws.res1.p), st); }
-    { Region reg(pk, LZKP_REGION_MSM_G2, st); batch_msm_g2(args(pk->g2, fit_variant(pk->g2, item_variant_g2(P)), ws.part2.p, ws.res2.p), st); }
+    // Latency form: the G2 MSM only needs the digits of z and s, so it runs on a side stream beside the witness map, the
+    // digits of h and the G1 MSMs (all of them latency-bound at these sizes) and joins before the assembly.
+    cudaStream_t st_g2 = st;
+    if (lat) {
+        {
+            Region reg(pk, LZKP_REGION_DIGITS, st);
+            LAUNCH(k_fr_mul_canonical, gx, 128, 0, st, d_r, d_s, ws.rs.as<Fr>(), P);
+            if (dig_bytes == 2) TRY(digits_z((int16_t *)dig)); else TRY(digits_z((int32_t *)dig));
+        }
+        st_g2 = pk->L_st[0];
+        CUDA_TRY(cudaEventRecord(pk->L_ev_in, st));
+        CUDA_TRY(cudaStreamWaitEvent(st_g2, pk->L_ev_in, 0));
+        { Region reg(pk, LZKP_REGION_MSM_G2, st_g2); batch_msm_g2(args(pk->g2, fit_variant(pk->g2, item_variant_g2(P)), ws.part2.p, ws.res2.p), st_g2); }
+        CUDA_TRY(cudaEventRecord(pk->L_ev_done[0], st_g2));
+        if (!have_h) TRY(run_witness_map(pk, ws, P, st));
+        { Region reg(pk, LZKP_REGION_DIGITS, st); if (dig_bytes == 2) TRY(digits_h((int16_t *)dig)); else TRY(digits_h((int32_t *)dig)); }
+    } else {
+        // One stream, stage after stage.  (Measured on B200: running the witness map and the G1 half of the assembly on
+        // a side stream underneath the MSM kernels gains < 2 % without stream priority - their CTAs only get SMs in the
+        // MSM kernel's last wave - and LOSES 2 % with priority, because a latency-bound CTA that holds 17k registers
+        // displaces a quarter of an SM's MSM warps while issuing almost nothing.  Overlap happens across chunks instead.)
+        if (!have_h) TRY(run_witness_map(pk, ws, P, st));
+        Region reg(pk, LZKP_REGION_DIGITS, st);
+        LAUNCH(k_fr_mul_canonical, gx, 128, 0, st, d_r, d_s, ws.rs.as<Fr>(), P);
+        if (dig_bytes == 2) { TRY(digits_z((int16_t *)dig)); TRY(digits_h((int16_t *)dig)); }
+        else { TRY(digits_z((int32_t *)dig)); TRY(digits_h((int32_t *)dig)); }
+    }
+    MsmPlan &pl1 = lat ? pk->g1_lat : pk->g1;
+    {
+        Region reg(pk, LZKP_REGION_MSM_G1, st);
+        BatchMsmArgs a1 = args(pl1, fit_variant(pl1, item_variant(P)), ws.part1.p, ws.res1.p);
+        a1.table = pk->g1.table.p;                        // the latency plan walks the same tables
+        batch_msm_g1(a1, st);
+    }
+    if (lat) CUDA_TRY(cudaStreamWaitEvent(st, pk->L_ev_done[0], 0));
+    else { Region reg(pk, LZKP_REGION_MSM_G2, st); batch_msm_g2(args(pk->g2, fit_variant(pk->g2, item_variant_g2(P)), ws.part2.p, ws.res2.p), st); }
     Region reg(pk, LZKP_REGION_ASSEMBLE, st);
+    if (lat) {
+        LAUNCH(k_assemble_sums, (P + 31) / 32, 96, 0, st, ws.res1.as<G1XYZZ>(), ws.res2.as<G2XYZZ>(), pk->consts, P, d_proofs);
+        return LZKP_OK;
+    }
     LAUNCH(k_assemble, (P + 31) / 32, 128, 0, st, ws.res1.as<G1XYZZ>(), ws.res2.as<G2XYZZ>(), pk->consts, d_r, d_s, P, d_proofs);
     return LZKP_OK;
 }

@@ -331,6 +331,26 @@ __global__ void __launch_bounds__(128) k_digits(const Fr *scalars, uint32_t stri
         for (uint32_t w = 0; w < W; w++) dig[base + (size_t)w * P] = (DigT)recoded_digit(v, c, w);
     }
 }
+// Digits of scalars[p][first + j] * mult[p] mod r (canonical in): the rows s * z_i and r * z_i of the latency form.
+template <class DigT>
+__global__ void __launch_bounds__(128) k_digits_scaled(const Fr *scalars, uint32_t stride, uint32_t first, const Fr *mult,
+                                                       DigT *dig, uint32_t row0, uint32_t P, uint32_t c, uint32_t W,
+                                                       uint32_t count) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    Fr m = ld_vec(mult + p);
+    if (!fr_is_canonical(m)) m = Fr::zero();               // (k_digits flags the proof; here only keep the arithmetic defined)
+    const Fr mr2 = m * Fr::r2();                            // Montgomery form of mult: (z * mR) R^-1 = z * mult, canonical
+    for (uint32_t j = blockIdx.y; j < count; j += gridDim.y) {
+        Fr z = ld_vec(scalars + (size_t)p * stride + first + j);
+        if (!fr_is_canonical(z)) z = Fr::zero();
+        const Fr s = z * mr2;
+        uint32_t v[10];
+        recode_offset(s, c, W, v);
+        const size_t base = ((size_t)(row0 + j) * W) * P + p;
+        for (uint32_t w = 0; w < W; w++) dig[base + (size_t)w * P] = (DigT)recoded_digit(v, c, w);
+    }
+}
 // rs[p] = r[p] * s[p] mod r, canonical in / out
 __global__ void k_fr_mul_canonical(const Fr *r, const Fr *s, Fr *rs, uint32_t P) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -398,6 +418,31 @@ __global__ void __launch_bounds__(128) k_assemble(const G1XYZZ *g1, const G2XYZZ
     } else if (role == 1) {
         write_g1(out, A.to_affine());
     } else if (role == 2) {
+        G2XYZZ B2 = ld_vec(g2 + p);
+        B2.madd_cold(K.b2);
+        write_g2(out + 64, B2.to_affine());
+    }
+}
+
+// Latency form (small calls): g1[q * P + p] additionally holds q = 4: s*(alpha + a0) + sum (s z_i) a_i and
+// q = 5: r*(beta + b0) + sum (r z_i) b_i + 2 rs delta, so C is a sum of four MSM results and the tail of a proof is
+// three conversions to affine on three warps (no scalar multiplication).
+__global__ void __launch_bounds__(96) k_assemble_sums(const G1XYZZ *g1, const G2XYZZ *g2, ProofConsts K, uint32_t P,
+                                                      uint8_t *proofs) {
+    const uint32_t role = threadIdx.x >> 5, lane = threadIdx.x & 31, p = blockIdx.x * 32 + lane;
+    if (p >= P) return;
+    uint8_t *out = proofs + (size_t)p * 256;
+    if (role == 0) {
+        G1XYZZ acc = ld_vec(g1 + 4 * (size_t)P + p);
+        acc.add_cold(ld_vec(g1 + 5 * (size_t)P + p));
+        acc.add_cold(ld_vec(g1 + 2 * (size_t)P + p));
+        acc.add_cold(ld_vec(g1 + 3 * (size_t)P + p));
+        write_g1(out + 192, acc.to_affine());
+    } else if (role == 1) {
+        G1XYZZ A = ld_vec(g1 + p);
+        A.madd_cold(K.a0);
+        write_g1(out, A.to_affine());
+    } else {
         G2XYZZ B2 = ld_vec(g2 + p);
         B2.madd_cold(K.b2);
         write_g2(out + 64, B2.to_affine());
