@@ -11,9 +11,13 @@ LOCAL_RANK / WORLD_SIZE); proofs are independent, so ranks shard the batch with 
   e2e     the same through the C-ABI call lzkp_prove_equality_batch with HOST buffers
           (H2D of inputs and D2H of proofs/status/commitments inside the timed region)
   roofline  the dominant kernel (G1 table MSM): algorithmic IMADs / its CUDA-event time vs the
-          measured IMAD peak of this pool's B200 (profiles/r1_microbench.jsonl)
+          measured peak of the 32x32->64 multiplier on this pool's B200 (profiles/r2_imadrate.jsonl)
   cpu_baseline  the CPU restatement (oracle/, C, OpenMP) on a bounded sample of the same workload
   extra   G1 MSM points/s @2^20 and NTT elements/s @2^22 (BASELINE.json's other two metrics)
+
+`--gpus N` (torchrun) adds, in `extra`: BASELINE.json configs[3] (one 2^20-constraint proof split over the N ranks, bytes
+asserted equal to the one-GPU proof), configs[4] (65 536-proof mixed batch sharded over the ranks, gather included) and
+the same 4096-per-GPU batch through ONE process driving all N GPUs (lzkp_init with N devices).
 
 `--impl reference` times the CPU restatement of the reference's prover (oracle/: the reference is
 Rust + un-vendored arkworks crates and cannot be built here, DESIGN.md "Oracle") on the same config.
@@ -37,9 +41,16 @@ M_MADD_G1 = 10                # XYZZ mixed add: 8M + 2S
 M_MADD_G2 = 28                # over Fq2: 8 * 3 + 2 * 2 base-field products
 # What the kernels execute per mixed add since lazy reduction went in (field.cuh): G1 = 8 products + one a*b - c*d with
 # a shared reduction (2 * 128 + 144); G2 = 8 Fq2 products of 3 * 128 + 2 * 144 and 2 Fq2 squares of 2 * 272.
-IMAD_EXEC_MADD_G1 = 8 * 272 + 400
+# (round 2: the two squarings of a G1 mixed add are dedicated 36 + 64 + 4 limb-product squarings = 208 issues each)
+IMAD_EXEC_MADD_G1 = 6 * 272 + 2 * 208 + 400
 IMAD_EXEC_MADD_G2 = 8 * 672 + 2 * 544
-IMAD_PEAK_FALLBACK = 17.25e12  # measured: tools/microbench on this pool (profiles/r1_microbench.jsonl)
+# Peak of the 32x32->64 multiplier, in SURVEY units (mad.lo and mad.hi counted separately = 2 per IMAD.WIDE):
+# tools/microbench/imadrate.cu on this pool's B200 measures 31.8 IMAD.WIDE lanes per SM per clock for EVERY form of the
+# instruction a big-integer product can use (carry-in .X rows, carry-out only, IMAD.HI; vector or uniform operands),
+# i.e. 9.25 T wide/s = 18.49 T IMAD/s at 148 SMs x 1965 MHz.  Round 1's 17.25 T/s "independent IMAD.WIDE" figure was an
+# artefact: ptxas had strength-reduced that microbenchmark's loop-invariant products into IADD3 pairs (its SASS holds
+# 9 IMAD.WIDE and 128 IADD3), so it measured the ALU pipe.  There is no 2x-faster flag-free form to move to.
+IMAD_PEAK_FALLBACK = 18.49e12
 
 
 class SplitMix64:
@@ -74,22 +85,23 @@ def u64s(seed, n):
 
 
 def imad_peak():
-    p = os.path.join(ROOT, "profiles", "r1_microbench.jsonl")
+    p = os.path.join(ROOT, "profiles", "r2_imadrate.jsonl")
     best = 0.0
     try:
         for line in open(p):
             d = json.loads(line)
-            if d.get("bench") == "imad_wide_independent":
-                best = max(best, d["Tops_per_s"] * 1e12)
+            if d.get("bench") in ("imad_wide_x_rows", "imad_wide_carry_out", "imad_hi"):
+                best = max(best, 2 * d["Tops_per_s"] * 1e12)
     except OSError:
         pass
-    return (best, "measured (profiles/r1_microbench.jsonl, mad.wide.u32 issue rate x 1 = 32-bit IMAD pairs)") if best \
+    return (best, "measured (profiles/r2_imadrate.jsonl: IMAD.WIDE.U32[.X] / IMAD.HI lanes per second x 2 mad.lo/hi "
+                  "issues; the 32x32->64 multiplier runs at 31.8 lanes per SM per clock in every form)") if best \
         else (IMAD_PEAK_FALLBACK, "fallback")
 
 
 def ncu_traffic(kernel_substr):
     """dram__bytes_read + dram__bytes_write per launch of a kernel, from the committed ncu --set full summary."""
-    path = os.path.join(ROOT, "profiles", "r1_ncu_msm_batch.txt")
+    path = os.path.join(ROOT, "profiles", "r2_ncu_msm_batch.txt")
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     try:
         lines = open(path).read().splitlines()
@@ -341,7 +353,8 @@ def run_ours(args, rank, world, local_rank):
         "bound": "imad", "kernel": "k_msm_batch<Fq> + k_msm_reduce<Fq> (G1 fixed-base table MSM)",
         "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "T IMAD/s", "frac": achieved / peak,
         "peak_source": peak_src, "traffic": ncu_traffic("k_msm_batch<Fp<FqParams>"),
-        "traffic_note": "DRAM bytes per launch from profiles/r1_ncu_msm_batch.txt (ncu --set full); algorithmic bytes "
+        "traffic_note": "DRAM bytes per launch from profiles/r2_ncu_msm_batch.txt (ncu --set full of the shipped kernel: 128 "
+                        "registers, 4 CTAs per SM, 5312-CTA grid); algorithmic bytes "
                         "are in hbm.algorithmic_bytes_per_launch - 64 B table entries are fetched as 128 B lines",
         "algorithmic_imad_per_launch": imad_per_launch, "avg_launch_ms": ms_g1 / max(n_g1, 1),
         "algorithmic_note": "SURVEY.md 8d unit: a mixed add = 10 Montgomery products of 272 IMAD; the kernel executes "

@@ -42,25 +42,16 @@ namespace lzkp {
 
 // D = (s0,s1,s2,s3) * k
 LZ_HD void row_mul(uint32_t (&D)[8], uint32_t s0, uint32_t s1, uint32_t s2, uint32_t s3, uint32_t k) {
-#ifdef __CUDA_ARCH__
-    asm("mul.lo.u32 %0, %8, %12;\n\t"
-        "mul.hi.u32 %1, %8, %12;\n\t"
-        "mul.lo.u32 %2, %9, %12;\n\t"
-        "mul.hi.u32 %3, %9, %12;\n\t"
-        "mul.lo.u32 %4, %10, %12;\n\t"
-        "mul.hi.u32 %5, %10, %12;\n\t"
-        "mul.lo.u32 %6, %11, %12;\n\t"
-        "mul.hi.u32 %7, %11, %12;"
-        : "=r"(D[0]), "=r"(D[1]), "=r"(D[2]), "=r"(D[3]), "=r"(D[4]), "=r"(D[5]), "=r"(D[6]), "=r"(D[7])
-        : "r"(s0), "r"(s1), "r"(s2), "r"(s3), "r"(k));
-#else
+    // 64-bit products: ptxas emits one IMAD.WIDE.U32 each.  (Written as mul.lo / mul.hi pairs it kept them apart as
+    // IMAD + IMAD.HI.U32 - 6 multiplier-pipe cycles per product instead of 4; ncu round 2: 3 % of the G1 kernel's
+    // executed instructions were IMAD.HI.)
     const uint32_t s[4] = {s0, s1, s2, s3};
+#pragma unroll
     for (int t = 0; t < 4; t++) {
         uint64_t p = (uint64_t)s[t] * k;
         D[2 * t] = (uint32_t)p;
         D[2 * t + 1] = (uint32_t)(p >> 32);
     }
-#endif
 }
 
 // D += (s0,s1,s2,s3) * k as one carry chain; returns the carry out of D[7].

@@ -15,7 +15,7 @@
 //                        (runs longer than a cap go to k_long_run: one CTA per run, tree reduction)
 //   5. k_red_*           sum_b (b+1) * B[b]: per-thread running sums over groups of 16 buckets, then
 //                        bit-plane tree sums over the group index (log depth, no long serial chain)
-//   6. k_horner / k_finish   combine windows (generic mode only), to affine, ark-serialize bytes
+//   6. k_horner_* / k_finish combine windows (generic mode only), to affine, ark-serialize bytes
 //
 // Two modes.  "Resident" bases (the proving key's queries: loaded once, kept in HBM) also hold
 // 2^(c*w) * P for every window w, so all windows share ONE bucket set, there is no Horner tail, and
@@ -364,16 +364,36 @@ __global__ void __launch_bounds__(32) k_red_direct3(const XYZZ<F> *__restrict__ 
 
 // ---------------------------------------------------------------- 6. window combination, output
 // generic mode: result = sum_w 2^(c*w) R[w]
+// Window w is shifted by its own CTA (one thread: c*w doublings of R[w], in place), all windows side by side on
+// different SMs; k_horner_sum then adds the W shifted sums in log depth.  The serial chain is the top window's
+// c*(W-1) doublings - nothing else: the Horner form (c doublings and one addition, W - 1 times on ONE thread)
+// took 1.12 ms at c = 16, W = 16.
 template <class F>
-__global__ void k_horner(XYZZ<F> *R, uint32_t W, uint32_t c) {
-    XYZZ<F> acc = ld_vec(R + (W - 1));
+__global__ void k_horner_shift(XYZZ<F> *R, uint32_t c) {
+    if (threadIdx.x) return;
+    const uint32_t w = blockIdx.x;
+    if (w == 0) return;
+    XYZZ<F> acc = ld_vec(R + w);
 #pragma unroll 1
-    for (int w = (int)W - 2; w >= 0; w--) {
-#pragma unroll 1
-        for (uint32_t d = 0; d < c; d++) acc.dbl_cold();
-        acc.add_cold(ld_vec(R + w));
+    for (uint32_t d = 0; d < c * w; d++) acc.dbl_cold();
+    st_vec(R + w, acc);
+}
+template <class F>
+__global__ void __launch_bounds__(32) k_horner_sum(XYZZ<F> *R, uint32_t W) {      // W <= 32: lane w owns window w
+    __shared__ uint4 raw[32 * sizeof(XYZZ<F>) / 16];
+    XYZZ<F> *sm = reinterpret_cast<XYZZ<F> *>(raw);
+    const uint32_t w = threadIdx.x;
+    if (w < W) st_vec(sm + w, ld_vec(R + w));
+    __syncwarp();
+    for (uint32_t s = 1; s < W; s <<= 1) {
+        if (w < W && (w & (2 * s - 1)) == 0 && w + s < W) {
+            XYZZ<F> a = ld_vec(sm + w);
+            a.add_cold(ld_vec(sm + w + s));
+            st_vec(sm + w, a);
+        }
+        __syncwarp();
     }
-    st_vec(R, acc);
+    if (w == 0) st_vec(R, ld_vec(sm));
 }
 template <class F, int BYTES>
 __global__ void k_finish(const XYZZ<F> *R, uint8_t *out) {
@@ -589,7 +609,8 @@ static int msm_run(MsmBases *B, const Fr *d_scalars, uint32_t n_used, uint8_t *d
     LAUNCH((k_red_planes<F>), dim3(B->nblk, B->LP + 1, B->sets), 128, 128 * sizeof(X), st, B->Sg.as<X>(), B->Ag.as<X>(), B->NG,
            B->LP, B->out1.as<X>());
     LAUNCH((k_red_finish<F>), B->sets, 32, 32 * sizeof(X), st, B->out1.as<X>(), B->nblk, B->LP, B->R.as<X>());
-    LAUNCH((k_horner<F>), 1, 1, 0, st, B->R.as<X>(), B->sets, B->c);
+    LAUNCH((k_horner_shift<F>), B->sets, 32, 0, st, B->R.as<X>(), B->c);
+    LAUNCH((k_horner_sum<F>), 1, 32, 0, st, B->R.as<X>(), B->sets);
     }
     if (raw) CUDA_TRY(cudaMemcpyAsync(d_out, B->R.p, sizeof(X), cudaMemcpyDeviceToDevice, st));
     else LAUNCH((k_finish<F, BYTES>), 1, 1, 0, st, B->R.as<X>(), d_out);

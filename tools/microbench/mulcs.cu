@@ -18,11 +18,6 @@
 using namespace lzkp;
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1); } } while (0)
 
-__device__ __forceinline__ void mac3(uint32_t &lo, uint32_t &hi, uint32_t &c, uint32_t a, uint32_t b) {
-    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
-        "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
-        "addc.u32 %2, %2, 0;" : "+r"(lo), "+r"(hi), "+r"(c) : "r"(a), "r"(b));
-}
 // (lo, hi) += a*b, no carry out wanted (caller knows it cannot overflow)
 __device__ __forceinline__ void mac2(uint32_t &lo, uint32_t &hi, uint32_t a, uint32_t b) {
     asm("mad.lo.cc.u32 %0, %2, %3, %0;\n\t"
