@@ -342,6 +342,132 @@ LZ_HD uint32_t sub16(uint32_t (&r)[16], const uint32_t (&a)[16], const uint32_t 
     return bw;
 }
 
+// ---- Karatsuba for the 256 x 256 -> 512-bit product: three 128 x 128-bit products instead of four, i.e. 48 limb
+// products instead of 64, paid for with ~70 add / xor instructions on the ALU pipe (which the product kernels leave
+// two thirds idle: ncu round 2, sm__inst_executed_pipe_alu 36 % against a multiplier pipe at > 80 %).
+//   a b = L + (L + H -+ M) B^4 + H B^8,   L = a0 b0,  H = a1 b1,  M = |a1 - a0| |b1 - b0|  (subtractive form: the middle
+//   term a0 b1 + a1 b0 = L + H - (a1 - a0)(b1 - b0) needs no 129-bit operands; M is subtracted when the two
+//   differences have the same sign and added otherwise).
+// T[0..7] = x[0..3] * y[0..3] by column scanning (16 limb products)
+LZ_HD void mul4x4(uint32_t (&T)[8], const uint32_t *x, const uint32_t *y) {
+    uint32_t t0 = 0, t1 = 0, t2 = 0;
+#pragma unroll
+    for (int k = 0; k < 7; k++) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int j = k - i;
+            if (j >= 0 && j < 4) mac3(t0, t1, t2, x[i], y[j]);
+        }
+        T[k] = t0; t0 = t1; t1 = t2; t2 = 0;
+    }
+    T[7] = t0;
+}
+// d = |x - y| over four limbs; returns an all-ones mask when x < y, else 0
+LZ_HD uint32_t absdiff4(uint32_t (&d)[4], const uint32_t *x, const uint32_t *y) {
+    uint32_t m;
+#ifdef __CUDA_ARCH__
+    asm("sub.cc.u32 %0, %5, %9;\n\t"
+        "subc.cc.u32 %1, %6, %10;\n\t"
+        "subc.cc.u32 %2, %7, %11;\n\t"
+        "subc.cc.u32 %3, %8, %12;\n\t"
+        "subc.u32 %4, 0, 0;\n\t"                 // 0 or 0xffffffff
+        "xor.b32 %0, %0, %4;\n\t"
+        "xor.b32 %1, %1, %4;\n\t"
+        "xor.b32 %2, %2, %4;\n\t"
+        "xor.b32 %3, %3, %4;\n\t"
+        "sub.cc.u32 %0, %0, %4;\n\t"             // (d ^ m) - m: two's complement negation when m is all ones
+        "subc.cc.u32 %1, %1, %4;\n\t"
+        "subc.cc.u32 %2, %2, %4;\n\t"
+        "subc.u32 %3, %3, %4;"
+        : "=&r"(d[0]), "=&r"(d[1]), "=&r"(d[2]), "=&r"(d[3]), "=&r"(m)
+        : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(y[0]), "r"(y[1]), "r"(y[2]), "r"(y[3]));
+#else
+    uint64_t c = 0;
+    for (int i = 0; i < 4; i++) {
+        uint64_t v = (uint64_t)x[i] - y[i] - c;
+        d[i] = (uint32_t)v;
+        c = (v >> 32) & 1;
+    }
+    m = c ? 0xffffffffu : 0u;
+    uint64_t cy = c;
+    for (int i = 0; i < 4; i++) {
+        uint64_t v = (uint64_t)(d[i] ^ m) + cy;
+        d[i] = (uint32_t)v;
+        cy = v >> 32;
+    }
+#endif
+    return m;
+}
+// T = a * b (16 limbs), a, b < 2^256
+LZ_HD void mul_wide_k(uint32_t (&T)[16], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+    uint32_t L[8], H[8], M[8], da[4], db[4], m8[8], mid[9];
+    mul4x4(L, a, b);
+    mul4x4(H, a + 4, b + 4);
+    const uint32_t sa = absdiff4(da, a + 4, a), sb = absdiff4(db, b + 4, b);
+    mul4x4(M, da, db);
+    const uint32_t n = ~(sa ^ sb);                 // all ones: subtract M (same signs); 0: add M
+    const uint32_t c = add8(m8, L, H);             // mid = L + H, 9 limbs (the ninth is the carry)
+#pragma unroll
+    for (int i = 0; i < 8; i++) mid[i] = m8[i];
+#ifdef __CUDA_ARCH__
+    // mid += (M ^ n) + (n & 1), with M ^ n sign-extended by n: mid -+ M in two's complement
+    uint32_t x[8], junk;
+#pragma unroll
+    for (int i = 0; i < 8; i++) x[i] = M[i] ^ n;
+    asm("add.cc.u32 %9, %19, 0xffffffff;\n\t"     // carry out = n & 1
+        "addc.cc.u32 %0, %0, %10;\n\t"
+        "addc.cc.u32 %1, %1, %11;\n\t"
+        "addc.cc.u32 %2, %2, %12;\n\t"
+        "addc.cc.u32 %3, %3, %13;\n\t"
+        "addc.cc.u32 %4, %4, %14;\n\t"
+        "addc.cc.u32 %5, %5, %15;\n\t"
+        "addc.cc.u32 %6, %6, %16;\n\t"
+        "addc.cc.u32 %7, %7, %17;\n\t"
+        "addc.u32 %8, %18, %20;"
+        : "+r"(mid[0]), "+r"(mid[1]), "+r"(mid[2]), "+r"(mid[3]), "+r"(mid[4]), "+r"(mid[5]), "+r"(mid[6]), "+r"(mid[7]),
+          "=r"(mid[8]), "=&r"(junk)
+        : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]), "r"(c), "r"(n & 1u), "r"(n));
+    // T = L | H, then T[4..12] += mid with the carry running to the top
+    asm("add.cc.u32 %0, %12, %24;\n\t"
+        "addc.cc.u32 %1, %13, %25;\n\t"
+        "addc.cc.u32 %2, %14, %26;\n\t"
+        "addc.cc.u32 %3, %15, %27;\n\t"
+        "addc.cc.u32 %4, %16, %28;\n\t"
+        "addc.cc.u32 %5, %17, %29;\n\t"
+        "addc.cc.u32 %6, %18, %30;\n\t"
+        "addc.cc.u32 %7, %19, %31;\n\t"
+        "addc.cc.u32 %8, %20, %32;\n\t"
+        "addc.cc.u32 %9, %21, 0;\n\t"
+        "addc.cc.u32 %10, %22, 0;\n\t"
+        "addc.u32 %11, %23, 0;"
+        : "=r"(T[4]), "=r"(T[5]), "=r"(T[6]), "=r"(T[7]), "=r"(T[8]), "=r"(T[9]), "=r"(T[10]), "=r"(T[11]), "=r"(T[12]),
+          "=r"(T[13]), "=r"(T[14]), "=r"(T[15])
+        : "r"(L[4]), "r"(L[5]), "r"(L[6]), "r"(L[7]), "r"(H[0]), "r"(H[1]), "r"(H[2]), "r"(H[3]), "r"(H[4]), "r"(H[5]),
+          "r"(H[6]), "r"(H[7]),
+          "r"(mid[0]), "r"(mid[1]), "r"(mid[2]), "r"(mid[3]), "r"(mid[4]), "r"(mid[5]), "r"(mid[6]), "r"(mid[7]), "r"(mid[8]));
+#pragma unroll
+    for (int i = 0; i < 4; i++) T[i] = L[i];
+#else
+    {
+        uint64_t cy = n & 1u;
+        for (int i = 0; i < 8; i++) {
+            cy += (uint64_t)mid[i] + (M[i] ^ n);
+            mid[i] = (uint32_t)cy;
+            cy >>= 32;
+        }
+        mid[8] = (uint32_t)(c + n + cy);
+        for (int i = 0; i < 4; i++) T[i] = L[i];
+        cy = 0;
+        for (int i = 4; i < 16; i++) {
+            const uint32_t base = i < 8 ? L[i] : H[i - 8];
+            cy += (uint64_t)base + (i - 4 < 9 ? mid[i - 4] : 0u);
+            T[i] = (uint32_t)cy;
+            cy >>= 32;
+        }
+    }
+#endif
+}
+
 // One round of reduce_wide, fused the way row_mad_shift fuses a product row: the limb that drops to column 0 joins
 // the aligned array (A0 += D[1]), the Montgomery factor m = A0 * inv follows from it, and D moves down two limbs while
 // taking the row (p1, p3, p5, p7) * m:  D[j] = p*m + D[j+2] + carry.  mul.lo leaves the carry flag alone.

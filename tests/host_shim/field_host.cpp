@@ -36,6 +36,12 @@ void fq_mul_wide_host(const uint8_t *a, const uint8_t *b, uint8_t *o64) {
     mul_wide(T, x.l, y.l);
     std::memcpy(o64, T, 64);
 }
+void fq_mul_wide_k_host(const uint8_t *a, const uint8_t *b, uint8_t *o64) {      // Karatsuba form
+    Fq x, y; ld(x, a); ld(y, b);
+    uint32_t T[16];
+    mul_wide_k(T, x.l, y.l);
+    std::memcpy(o64, T, 64);
+}
 void fq_reduce_wide_host(const uint8_t *t64, uint8_t *o) {
     uint32_t T[16];
     std::memcpy(T, t64, 64);

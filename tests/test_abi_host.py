@@ -119,12 +119,18 @@ def test_lazy_fq2_product_on_host(field_shim, po):
     b32 = lambda v: (C.c_uint8 * 32)(*v.to_bytes(32, "little"))
     b64 = lambda v: (C.c_uint8 * 64)(*v.to_bytes(64, "little"))
     edge = [0, 1, q - 1, q - 2, R % q, (1 << 254) % q, 0xffffffff, q >> 1]
+    # operands that stress the Karatsuba halves (any 256-bit value is a legal input of the wide products)
+    halves = [(1 << 128) - 1, 1 << 128, ((1 << 128) - 1) << 128, (1 << 128) + 1, ((1 << 127) << 128) | 1,
+              (0xffffffff << 128) | 0xfffffffe, (1 << 256) - 1, ((1 << 128) - 1) << 128 | 1]
     vals = edge + [rng.next_fr() % q for _ in range(300)]
-    for i, a in enumerate(vals):                       # 16-limb product, also of unreduced operands (sums < 2^256)
-        for b in (vals[(i * 5 + 1) % len(vals)], (1 << 256) - 1, 2 * q - 2):
+    wv = vals + halves
+    for i, a in enumerate(wv):                         # 16-limb product, also of unreduced operands (sums < 2^256)
+        for b in (wv[(i * 5 + 1) % len(wv)], (1 << 256) - 1, 2 * q - 2, halves[i % len(halves)]):
             o = (C.c_uint8 * 64)()
             field_shim.fq_mul_wide_host(b32(a), b32(b), o)
             assert int.from_bytes(bytes(o), "little") == a * b
+            field_shim.fq_mul_wide_k_host(b32(a), b32(b), o)            # Karatsuba (three 128-bit products)
+            assert int.from_bytes(bytes(o), "little") == a * b, (hex(a), hex(b))
     wide = [0, 1, q * R - 1, q * R - q, (q - 1) * (q - 1), 2 * (q - 1) * (q - 1), R - 1, R, q] + \
            [rng.next_fr() * rng.next_fr() % (q * R) for _ in range(300)]
     for t in wide:                                     # reduction of any T < q * 2^256

@@ -124,6 +124,8 @@ __device__ __forceinline__ Fq mulv(const Fq &a, const Fq &b) {
     if (V == 0) return a * b;
     if (V == 1) return cs_mul1<FqParams>(a, b);
     if (V == 2) return cs_mul2<FqParams>(a, b);
+    if (V == 4) { uint32_t T[16]; mul_wide_k(T, a.l, b.l); return Fq::reduce_wide(T); }      // Karatsuba + reduction
+    if (V == 5) { uint32_t T[16]; mul_wide(T, a.l, b.l); return Fq::reduce_wide(T); }        // schoolbook + reduction
     return cs_sqr<FqParams>(a);
 }
 
@@ -152,6 +154,7 @@ __global__ void k_check(const Fq *in, int n, int *bad) {
         if (cs_mul1<FqParams>(a, b) != w) atomicAdd(bad, 1);
         if (cs_mul2<FqParams>(a, b) != w) atomicAdd(bad + 1, 1);
         if (cs_sqr<FqParams>(a) != a * a) atomicAdd(bad + 2, 1);
+        if (mulv<4>(a, b) != w) atomicAdd(bad + 3, 1);
         a = w; b = b + a;
     }
 }
@@ -171,6 +174,15 @@ __global__ void __launch_bounds__(256) k_rate(uint32_t *out, uint32_t a, uint32_
 #pragma unroll
     for (int j = 0; j < 4; j++) s ^= lo[j] ^ hi[j] ^ c[j];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// Field inversions per second (binary extended GCD, field.cuh): what ONE shared inversion of a batch-affine addition
+// scheme costs, in units of Montgomery products.
+__global__ void __launch_bounds__(128) k_inv(Fq *out, const Fq *in, int iters) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    Fq x = in[t], y = in[t + 1];
+    for (int i = 0; i < iters; i++) x = x.inverse() + y;
+    out[t] = x;
 }
 
 static float time_ms(cudaEvent_t a, cudaEvent_t b) { float ms; cudaEventElapsedTime(&ms, a, b); return ms; }
@@ -212,8 +224,8 @@ int main() {
     }
     int *bad; CK(cudaMalloc(&bad, 16)); CK(cudaMemset(bad, 0, 16));
     k_check<<<1024, 256>>>((const Fq *)buf, 1024 * 256, bad);
-    int hb[3]; CK(cudaMemcpy(hb, bad, 12, cudaMemcpyDeviceToHost));
-    printf("{\"check\": \"vs operator*\", \"cs1_bad\": %d, \"cs2_bad\": %d, \"sqr_bad\": %d}\n", hb[0], hb[1], hb[2]);
+    int hb[4]; CK(cudaMemcpy(hb, bad, 16, cudaMemcpyDeviceToHost));
+    printf("{\"check\": \"vs operator*\", \"cs1_bad\": %d, \"cs2_bad\": %d, \"sqr_bad\": %d, \"karatsuba_bad\": %d}\n", hb[0], hb[1], hb[2], hb[3]);
     {
         const int blocks = sms * 8, iters = 2000;
         for (int rep = 0; rep < 3; rep++) {
@@ -224,7 +236,17 @@ int main() {
                    time_ms(e0, e1), ops / time_ms(e0, e1) / 1e9, ops / (time_ms(e0, e1) * 1e-3) / sms / 1.965e9);
         }
     }
+    for (int bl : {4, 16}) {
+        k_inv<<<sms * bl, 128>>>((Fq *)buf, (const Fq *)buf, 1);
+        cudaEventRecord(e0); k_inv<<<sms * bl, 128>>>((Fq *)buf, (const Fq *)buf, 20); cudaEventRecord(e1);
+        CK(cudaEventSynchronize(e1));
+        double ops = (double)sms * bl * 128 * 20;
+        printf("{\"bench\": \"fq_inverse_binary_gcd\", \"warps_per_sm\": %d, \"ms\": %.3f, \"Ginv_per_s\": %.4f}\n", bl * 4, time_ms(e0, e1), ops / time_ms(e0, e1) / 1e6);
+    }
     run<0, 1>("cios_shipped", sms, buf, e0, e1);
+    run<4, 1>("karatsuba_wide_plus_reduce", sms, buf, e0, e1);
+    run<5, 1>("schoolbook_wide_plus_reduce", sms, buf, e0, e1);
+    run<4, 2>("karatsuba_wide_plus_reduce", sms, buf, e0, e1);
     run<1, 1>("cs1", sms, buf, e0, e1);
     run<2, 1>("cs2", sms, buf, e0, e1);
     run<3, 1>("cs_sqr", sms, buf, e0, e1);
