@@ -343,18 +343,23 @@ static int pk_load_impl(const uint8_t *bytes, size_t len, int validate, const lz
         pk->shard_count = opt && opt->shard_count > 1 ? opt->shard_count : 1;
         pk->shard_index = pk->shard_count > 1 ? opt->shard_index : 0;
         if (pk->shard_index >= pk->shard_count) return fail(LZKP_E_INVALID, "shard_index >= shard_count");
-        // Cost-weighted split (a G2 point costs ~2.8 G1 points).  The witness map is NOT distributed and h is NOT
+        // Cost-weighted split (a G2 point costs ~3.2 G1 points in the sort-based MSM, fixed costs included; weights and
+        // the map cost below were fitted with tools/shard_balance.py: slowest shard of 8 at 2^20 5.02 -> 4.5 ms).  The witness map is NOT distributed and h is NOT
         // broadcast: the first k ranks ("map ranks") each run the map themselves and share the H query between them;
         // the z-only queries a | b1 | l | b2 are cut over all ranks so that every rank ends up with the same load
         //   T = (W_z + W_h + k M) / G,     map rank: M + W_h / k + z-share,     other ranks: z-share = T
-        // with M the cost of one witness map in MSM weight units (measured at 2^20: 2.6 ms against 23.4 ms of MSMs).
+        // with M the cost of one witness map in MSM weight units (2.6 ms against 23.4 ms of MSMs at 2^20, less what
+        // overlaps with the z-only MSMs on the side streams).
         // k is the smallest count whose spare capacity k (T - M) covers W_h (1 up to 4 GPUs, 3 at 8).
-        const uint64_t sizes[5] = {nv, nv, (uint64_t)pk->n_wit + 1, (uint64_t)n - 1, nv}, wts[5] = {10, 10, 10, 10, 28};
+        // (every MSM call also carries ~0.55 ms (G1) / ~1 ms (G2) that does not scale with its range, so the best
+        // weights drift with the shard count: fitted at 2, 4 and 8 shards)
         const uint32_t G_ = pk->shard_count;
+        const uint64_t w_g2 = getenv("LZKP_SHARD_G2_WEIGHT") ? (uint64_t)atoi(getenv("LZKP_SHARD_G2_WEIGHT")) : (G_ > 4 ? 32 : 28);
+        const uint64_t sizes[5] = {nv, nv, (uint64_t)pk->n_wit + 1, (uint64_t)n - 1, nv}, wts[5] = {10, 10, 10, 10, w_g2};
         const double Wh = (double)sizes[3] * wts[3];
         double Wz = 0;
         for (int q : {0, 1, 2, 4}) Wz += (double)sizes[q] * wts[q];
-        static const double map_frac = getenv("LZKP_SHARD_MAP_COST") ? atof(getenv("LZKP_SHARD_MAP_COST")) : 0.11;
+        const double map_frac = getenv("LZKP_SHARD_MAP_COST") ? atof(getenv("LZKP_SHARD_MAP_COST")) : (G_ > 4 ? 0.085 : 0.11);
         const double M = G_ > 1 ? map_frac * (Wz + Wh) : 0.0;
         uint32_t k = 1;
         while (k < G_ && k * ((Wz + Wh + k * M) / G_ - M) < Wh) k++;
