@@ -300,11 +300,13 @@ def run_ours(args, rank, world, local_rank):
     pin = lambda x: torch.from_numpy(x).pin_memory().numpy()
     a_p, r_p, s_p = as_i64(a_h).pin_memory().numpy().view(np.uint64), pin(r_h), pin(s_h)
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    pk.prove_equality_batch(a_p, a_p, r_p, s_p)
+    zp = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory().numpy()
+    out_p = (zp((P, 256), torch.uint8), zp((P, 32), torch.uint8), zp((P,), torch.int32))     # caller-owned pinned result buffers
+    pk.prove_equality_batch(a_p, a_p, r_p, s_p, out=out_p)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        proofs_h, cms_h, status_h = pk.prove_equality_batch(a_p, a_p, r_p, s_p)
+        proofs_h, cms_h, status_h = pk.prove_equality_batch(a_p, a_p, r_p, s_p, out=out_p)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -550,11 +552,13 @@ def bench_fanout(torch, world, pk_bytes, window_bits, P, a_p, r_p, s_p, proofs_b
     n = world * P
     rep = lambda x: torch.from_numpy(np.ascontiguousarray(np.concatenate([x] * world)).view(np.uint8)).pin_memory().numpy()
     a, r, s = rep(a_p).view(np.uint64), rep(r_p).reshape(n, 32), rep(s_p).reshape(n, 32)
-    proofs, _, status = pk.prove_equality_batch(a, a, r, s)
+    pinned = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory().numpy()
+    out = (pinned((n, 256), torch.uint8), pinned((n, 32), torch.uint8), pinned((n,), torch.int32))    # caller-owned result buffers
+    proofs, _, status = pk.prove_equality_batch(a, a, r, s, out=out)
     ok = bool(not status.any() and all(np.array_equal(proofs[g * P:(g + 1) * P], proofs_block0) for g in range(world)))
     t0 = time.perf_counter()
     for _ in range(steps):
-        pk.prove_equality_batch(a, a, r, s)
+        pk.prove_equality_batch(a, a, r, s, out=out)
     dt = (time.perf_counter() - t0) / steps
     pk.close()
     assert ok, "fan-out proofs differ from the one-GPU proofs of the same inputs"

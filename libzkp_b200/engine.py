@@ -217,15 +217,23 @@ class ProvingKey:
                              stream: int = 0) -> None:
         check(lib().lzkp_prove_combine_device(self._h, d_partials, n_partials, d_r, d_s, d_proof, stream))
 
-    def prove_equality_batch(self, a, b, r, s, commitments=None):
+    def prove_equality_batch(self, a, b, r, s, commitments=None, out=None):
+        """out = (proofs[n, 256] uint8, commitments[n, 32] uint8, status[n] int32) reuses caller-owned result buffers
+        (a server proving batch after batch keeps them, e.g. pinned); by default fresh arrays are returned."""
         a = np.ascontiguousarray(a, np.uint64)
         b = np.ascontiguousarray(b, np.uint64)
         n = a.shape[0]
         r, s = _u8(r, 32), _u8(s, 32)
         cm = None if commitments is None else _u8(commitments, 32)
-        proofs = np.zeros((n, 256), np.uint8)
-        cm_out = np.zeros((n, 32), np.uint8)
-        status = np.zeros(n, np.int32)
+        if out is not None:
+            proofs, cm_out, status = out
+            if (proofs.shape, cm_out.shape, status.shape) != ((n, 256), (n, 32), (n,)) or proofs.dtype != np.uint8 \
+                    or cm_out.dtype != np.uint8 or status.dtype != np.int32 or not (proofs.flags.c_contiguous and cm_out.flags.c_contiguous):
+                raise ValueError("out buffers must be C-contiguous (n, 256) uint8, (n, 32) uint8, (n,) int32")
+        else:
+            proofs = np.zeros((n, 256), np.uint8)
+            cm_out = np.zeros((n, 32), np.uint8)
+            status = np.zeros(n, np.int32)
         check(lib().lzkp_prove_equality_batch(self._h, n, _p(a), _p(b), _p(cm), _p(r), _p(s), _p(proofs), _p(cm_out),
                                               _p(status)))
         return proofs, cm_out, status
