@@ -78,11 +78,14 @@ def process_batch_sharded(batch_id: int, rng=None) -> List[bytes]:
     return process_operations_sharded(ops, lambda blk: _batch.prove_operations(blk, rng))
 
 
-def gather_rows(local, n_total: int, rank: Optional[int] = None, world: Optional[int] = None, device=None):
+def gather_rows(local, n_total: int, rank: Optional[int] = None, world: Optional[int] = None, device=None,
+                dst: Optional[int] = None):
     """All ranks hold the rows [shard_range(n_total, rank, world)) of a 2-D uint8 / int32 array; returns the full array
-    (n_total rows, operation order) on every rank.  One all_gather of equal-sized, zero-padded blocks (NCCL wants equal
-    sizes; block sizes differ by at most one row) - bytes only, no pickling, so a 65 536-proof batch gathers in
-    milliseconds.  `device` = the CUDA device of this rank for NCCL, None for gloo (CPU tensors)."""
+    (n_total rows, operation order) on every rank - or, with `dst`, only on that rank (None elsewhere: the reference
+    hands a batch's results to ONE caller, so the other ranks need not pay for the copy back).  One collective of
+    equal-sized, zero-padded blocks (NCCL wants equal sizes; block sizes differ by at most one row) - bytes only, no
+    pickling, so a 65 536-proof batch gathers in milliseconds.  `device` = the CUDA device of this rank for NCCL, None
+    for gloo (CPU tensors)."""
     import numpy as np
     import torch
     dist = _dist()
@@ -97,33 +100,54 @@ def gather_rows(local, n_total: int, rank: Optional[int] = None, world: Optional
     if world == 1:
         return local
     rows = -(-n_total // world)                                  # largest block
-    pad = np.zeros((rows,) + local.shape[1:], local.dtype)
-    pad[:hi - lo] = local
-    t = torch.from_numpy(pad)
+    if hi - lo == rows:
+        t = torch.from_numpy(local)
+    else:
+        pad = np.zeros((rows,) + local.shape[1:], local.dtype)
+        pad[:hi - lo] = local
+        t = torch.from_numpy(pad)
     if device is not None:
-        t = t.to(device)
-    out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
-    dist.all_gather_into_tensor(out.view(-1), t.view(-1))
+        t = t.to(device, non_blocking=True)
+    if dst is None:
+        out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out.view(-1), t.view(-1))
+    else:
+        out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device) if rank == dst else None
+        dist.gather(t, list(out.unbind(0)) if rank == dst else None, dst=dst)
+        if rank != dst:
+            return None
     out = out.cpu().numpy()
+    if n_total == rows * world:                                  # even split: the gathered buffer IS the result
+        return out.reshape((n_total,) + local.shape[1:])
     return np.concatenate([out[g, :shard_range(n_total, g, world)[1] - shard_range(n_total, g, world)[0]] for g in range(world)])
 
 
 def prove_mixed_enveloped_sharded(pk_eq, pk_mb, eq_vals, mb_vals, mb_sets, mb_lens, r_eq, s_eq, r_mb, s_mb,
-                                  rank: int, world: int, device=None):
+                                  rank: int, world: int, device=None, dst: Optional[int] = None):
     """BASELINE.json configs[4]: one mixed batch (the caller's even operations are equality proofs, the odd ones
     membership proofs, as process_batch groups them per circuit - src/advanced/batch.rs:123-131) sharded
     proof-parallel: rank g proves block g of each kind on its own GPU (both keys resident), libzkp envelopes are
-    written on the device, and the finished bytes are gathered on every rank in operation order.
-    All array arguments are the FULL batch on every rank.  Returns (eq_env, eq_len, eq_status, mb_env, mb_len, mb_status)."""
+    written on the device, and the finished bytes are gathered in operation order on every rank (dst=None) or on rank
+    `dst` only (the other ranks return None).  Lengths and status words travel inside the same rows as the envelopes:
+    two collectives per batch.  All array arguments are the FULL batch on every rank.
+    Returns (eq_env, eq_len, eq_status, mb_env, mb_len, mb_status)."""
     ne, nm = len(eq_vals), len(mb_vals)
     elo, ehi = shard_range(ne, rank, world)
     mlo, mhi = shard_range(nm, rank, world)
     env_e, len_e, st_e = pk_eq.prove_equality_enveloped(eq_vals[elo:ehi], eq_vals[elo:ehi], r_eq[elo:ehi], s_eq[elo:ehi])
     env_m, len_m, st_m = pk_mb.prove_membership_enveloped(mb_vals[mlo:mhi], mb_sets[mlo:mhi], mb_lens[mlo:mhi],
                                                           r_mb[mlo:mhi], s_mb[mlo:mhi])
-    g = lambda a, n: gather_rows(a, n, rank, world, device)
     import numpy as np
-    meta_e = np.stack([len_e.astype(np.int32), st_e.astype(np.int32)], 1)
-    meta_m = np.stack([len_m.astype(np.int32), st_m.astype(np.int32)], 1)
-    env_e, meta_e, env_m, meta_m = g(env_e, ne), g(meta_e, ne), g(env_m, nm), g(meta_m, nm)
-    return env_e, meta_e[:, 0], meta_e[:, 1], env_m, meta_m[:, 0], meta_m[:, 1]
+
+    def pack(env, lens, st):                       # [envelope bytes | len u32 | status i32] per row: one collective per kind
+        meta = np.stack([lens.astype(np.uint32).view(np.int32), st.astype(np.int32)], 1).view(np.uint8).reshape(len(lens), 8)
+        return np.concatenate([env, meta], 1)
+
+    def unpack(rows, width):
+        meta = np.ascontiguousarray(rows[:, width:]).view(np.int32).reshape(-1, 2)
+        return rows[:, :width], meta[:, 0].view(np.uint32), meta[:, 1]
+    ge = gather_rows(pack(env_e, len_e, st_e), ne, rank, world, device, dst)
+    gm = gather_rows(pack(env_m, len_m, st_m), nm, rank, world, device, dst)
+    if ge is None:
+        return None
+    return unpack(ge, env_e.shape[1]) + unpack(gm, env_m.shape[1])

@@ -87,6 +87,8 @@ def _worker(rank, world, port, q):
             full = (np.arange(n_total * 5, dtype=np.int64) % 251).astype(np.uint8).reshape(n_total, 5)
             got = parallel.gather_rows(full[lo:hi], n_total)
             assert got.shape == (n_total, 5) and np.array_equal(got, full), (n_total, got)
+            one = parallel.gather_rows(full[lo:hi], n_total, dst=1)          # results on one rank only
+            assert (one is None) == (rank != 1) and (one is None or np.array_equal(one, full))
         try:
             parallel.gather_rows(np.zeros((3, 5), np.uint8), 11)
             raise AssertionError("wrong block size must be rejected")
