@@ -79,6 +79,96 @@ __global__ void __launch_bounds__(256) k_msm_digits(const Fr *__restrict__ scala
     }
 }
 
+// GLV form of the generic (one bucket set per window) G1 MSM: k P = (+-k1) P + (+-k2) phi(P) with phi(x, y) = (beta x, y)
+// and |k1|, |k2| < 2^128, so the 2n "virtual" points (P_i at i, phi(P_i) at n + i) carry 128-bit scalars: half as many
+// windows - the window combination's chain of dependent doublings drops from c (W - 1) = 240 to 128 and the number of
+// bucket sets to reduce from 16 to 9 - for the same number of (point, window) pairs.
+// Magnitudes of the lattice split stay below ~2^128 (ec.cuh glv_split: never above 2^127 over 2 * 10^5 scalars);
+// the W = ceil(129 / c) + ... windows used here hold anything below 2^(c W - 1), and a split beyond that is counted in
+// `bad` like a non-canonical scalar rather than silently mis-added.
+__device__ __forceinline__ void glv_split_wide(const Fr &k, Fr &m1, bool &neg1, Fr &m2, bool &neg2) {
+    const uint32_t G1C[5] = {0x00ff6565u, 0x5398fd03u, 0xa773d2d2u, 0x4ccef014u, 0x00000002u};
+    const uint32_t G2C[3] = {0xc7e0b3d7u, 0xd91d232eu, 0x00000002u};
+    const uint32_t A1[4] = {0x7d4f1128u, 0x8211bbebu, 0xeeb859fcu, 0x6f4d8248u};
+    const uint32_t A2[2] = {0x94d213e3u, 0x89d32568u};          // a2 = -b1
+    const uint32_t B2[4] = {0x1221250bu, 0x0be4e154u, 0xeeb859fdu, 0x6f4d8248u};
+    uint32_t t13[13], t11[11], c1[5], c2[3];
+    mul_limbs<13, 8, 5>(t13, k.l, G1C);
+#pragma unroll
+    for (int i = 0; i < 5; i++) c1[i] = t13[8 + i];
+    mul_limbs<11, 8, 3>(t11, k.l, G2C);
+#pragma unroll
+    for (int i = 0; i < 3; i++) c2[i] = t11[8 + i];
+    uint32_t p1[8], p2[8], p3[8], p4[8], t[8];
+    mul_limbs<8, 5, 4>(p1, c1, A1);
+    mul_limbs<8, 3, 2>(p2, c2, A2);
+    mul_limbs<8, 5, 2>(p3, c1, A2);
+    mul_limbs<8, 3, 4>(p4, c2, B2);
+    sub8(t, k.l, p1);
+    sub8(m1.l, t, p2);
+    sub8(m2.l, p3, p4);
+    neg1 = (m1.l[7] >> 31) != 0;
+    neg2 = (m2.l[7] >> 31) != 0;
+    const uint32_t zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (neg1) { sub8(t, zero, m1.l);
+#pragma unroll
+        for (int i = 0; i < 8; i++) m1.l[i] = t[i]; }
+    if (neg2) { sub8(t, zero, m2.l);
+#pragma unroll
+        for (int i = 0; i < 8; i++) m2.l[i] = t[i]; }
+}
+__global__ void __launch_bounds__(256) k_msm_digits_glv(const Fr *__restrict__ scalars, uint32_t n_used, uint32_t n,
+                                                        uint32_t c, uint32_t W, uint32_t NB, uint32_t *__restrict__ keys,
+                                                        uint32_t *__restrict__ vals, int *__restrict__ bad) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_used) return;
+    Fr s = ld_vec(scalars + i);
+    if (!fr_is_canonical(s)) {
+        atomicAdd(bad, 1);
+        s = Fr::zero();
+    }
+    Fr m[2];
+    bool neg[2];
+    glv_split_wide(s, m[0], neg[0], m[1], neg[1]);
+    const uint32_t top = c * W - 1;                       // magnitudes must stay below 2^top for the offset recoding
+    for (int h = 0; h < 2; h++) {
+        uint32_t over = 0;
+        for (uint32_t b = top >> 5; b < 8; b++) over |= b == (top >> 5) ? (m[h].l[b] >> (top & 31)) : m[h].l[b];
+        if (over) {
+            atomicAdd(bad, 1);
+            m[h] = Fr::zero();
+        }
+    }
+    const size_t nv = (size_t)2 * n;
+    for (int h = 0; h < 2; h++) {
+        uint32_t v[10];
+        recode_offset(m[h], c, W, v);
+        for (uint32_t w = 0; w < W; w++) {
+            int d = recoded_digit(v, c, w);
+            if (neg[h]) d = -d;
+            uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+            uint32_t key = SENT, val = 0;
+            if (d) {
+                key = w * NB + mag - 1u;
+                val = ((uint32_t)h * n + i) | (d < 0 ? 0x80000000u : 0u);
+            }
+            keys[(size_t)w * nv + (size_t)h * n + i] = key;
+            vals[(size_t)w * nv + (size_t)h * n + i] = val;
+        }
+    }
+}
+// pts[n + i] = phi(pts[i]) = (beta * x, y); infinity (0, 0) stays infinity
+__global__ void k_phi_points(G1Affine *pts, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    G1Affine p = ld_vec(pts + i);
+    Fq beta;
+#pragma unroll
+    for (int j = 0; j < 8; j++) beta.l[j] = FqParams::BETA(j);
+    p.x = p.x * beta;
+    st_vec(pts + n + i, p);
+}
+
 // count[0] = number of sorted pairs with a real key (sentinels sort last)
 __global__ void k_find_count(const uint32_t *keys, uint32_t total, uint32_t *count) {
     uint32_t lo = 0, hi = total;
@@ -455,6 +545,8 @@ struct MsmBases {
     int group = 1;                 // 1 = G1, 2 = G2
     uint32_t n = 0, c = 16, W = 16, NB = 32768;
     bool resident = false;
+    bool glv = false;              // generic G1 mode: 2n virtual points (P, phi(P)) with 128-bit scalars
+    uint32_t nv = 0;               // points the pipeline walks per window: n, or 2n with glv
     uint32_t sets = 16;            // bucket sets: 1 (resident) or W (generic)
     DBuf points;                   // Affine<F>[n] or [W * n]
     // workspace
@@ -478,8 +570,11 @@ static int bases_prepare(MsmBases *B, const uint8_t *bases_bytes, size_t n, int 
     B->W = (255 + B->c - 1) / B->c;
     B->NB = 1u << (B->c - 1);
     B->resident = resident != 0;
+    B->glv = !B->resident && BYTES == 64 && getenv("LZKP_MSM_NO_GLV") == nullptr;
+    if (B->glv) B->W = (130 + B->c - 1) / B->c;          // s + K < 2^(cW) with |s| < 2^129: 9 windows at c = 16
     B->sets = B->resident ? 1u : B->W;
-    if ((uint64_t)B->n * B->W >= (1ull << 31)) return fail(LZKP_E_UNSUPPORTED, "MSM: n * windows must stay below 2^31");
+    B->nv = B->glv ? 2 * B->n : B->n;
+    if ((uint64_t)B->nv * B->W >= (1ull << 31)) return fail(LZKP_E_UNSUPPORTED, "MSM: n * windows must stay below 2^31");
     const uint32_t n1 = std::max<uint32_t>(B->n, 1);
     // ---- parse ark-serialize points on the host (canonical limbs, flags stripped), upload, to Montgomery
     std::vector<uint8_t> canon;
@@ -490,7 +585,7 @@ static int bases_prepare(MsmBases *B, const uint8_t *bases_bytes, size_t n, int 
         else ok = host::read_g2(bases_bytes + i * 128, *reinterpret_cast<host::G2Canon *>(canon.data() + i * 128));
         if (!ok) return fail(LZKP_E_INVALID, "MSM base " + std::to_string(i) + ": non-canonical coordinate");
     }
-    TRY(B->points.alloc((size_t)n1 * (B->resident ? B->W : 1) * BYTES));
+    TRY(B->points.alloc((size_t)n1 * (B->resident ? B->W : (B->glv ? 2 : 1)) * BYTES));
     if (canon_input) {      // already parsed: canonical limbs, (0,0) = infinity
         CUDA_TRY(cudaMemset(B->points.p, 0, (size_t)n1 * BYTES));
         if (n) CUDA_TRY(cudaMemcpy(B->points.p, bases_bytes, n * BYTES, cudaMemcpyHostToDevice));
@@ -509,8 +604,11 @@ static int bases_prepare(MsmBases *B, const uint8_t *bases_bytes, size_t n, int 
     }
     if (B->resident && n)
         LAUNCH((k_precompute_windows<F>), (B->n + 127) / 128, 128, 0, 0, B->points.as<Affine<F>>(), B->n, B->c, B->W);
+    if constexpr (BYTES == 64) {
+        if (B->glv && n) LAUNCH(k_phi_points, (B->n + 127) / 128, 128, 0, 0, B->points.as<G1Affine>(), B->n);
+    }
     // ---- workspace
-    const size_t total = (size_t)n1 * B->W;
+    const size_t total = (size_t)std::max<uint32_t>(B->nv, 1) * B->W;
     B->key_bits = 1;
     while ((1ull << B->key_bits) < (uint64_t)B->sets * B->NB) B->key_bits++;
     B->T = (uint32_t)((total + chunk_of<F>() - 1) / chunk_of<F>());
@@ -563,10 +661,13 @@ static int msm_run(MsmBases *B, const Fr *d_scalars, uint32_t n_used, uint8_t *d
         return LZKP_OK;
     }
     CUDA_TRY(cudaMemsetAsync(B->buckets.p, 0, (size_t)B->sets * B->NB * sizeof(X), st));
-    const size_t total = (size_t)n * B->W;
+    const size_t total = (size_t)B->nv * B->W;
     if (n_used < n)      // unused tail of the digit arrays: sentinels
         CUDA_TRY(cudaMemsetAsync(B->keys_a.p, 0xFF, total * 4, st));
-    if (n_used) {
+    if (n_used && B->glv) {
+        LAUNCH(k_msm_digits_glv, (n_used + 255) / 256, 256, 0, st, d_scalars, n_used, n, B->c, B->W, B->NB,
+               B->keys_a.as<uint32_t>(), B->vals_a.as<uint32_t>(), B->bad.as<int>());
+    } else if (n_used) {
         // digits are laid out with the resident stride n so that point refs w * n + i stay valid
         LAUNCH(k_msm_digits, (n_used + 255) / 256, 256, 0, st, d_scalars, n_used, n, B->c, B->W, B->NB, (int)B->resident,
                B->keys_a.as<uint32_t>(), B->vals_a.as<uint32_t>(), B->bad.as<int>());

@@ -71,7 +71,8 @@ def bench_msm(torch, dev, imad_peak, log_n=20, group=1, c=16, iters=10, resident
             "points_per_s": n / (ms * 1e-3), "algorithmic_imad": muls * IMAD_PER_MUL,
             "imad_achieved_T": muls * IMAD_PER_MUL / (ms * 1e-3) / 1e12,
             "imad_frac_of_measured_peak": muls * IMAD_PER_MUL / (ms * 1e-3) / imad_peak,
-            "mode": "bases resident in HBM with all window multiples" if resident else "one bucket set per window",
+            "mode": "bases resident in HBM with all window multiples" if resident else
+            ("one bucket set per window, GLV split: 2n points x 128-bit scalars" if group == 1 else "one bucket set per window"),
             "scalars": "50% zero/one, 50% uniform" if witness_like else "uniform in [0, r)",
             "mixed_adds_counted": madds, "result_hex": bytes(out.cpu().numpy()).hex()[:32],
             "result_equals_sum_k_s_times_G": checked}
