@@ -230,15 +230,22 @@ def bench_verify(torch, dev, n=4096, iters=3):
 
 
 def bench(torch, dev, imad_peak, hbm_gbs):
-    return {"msm_g1_2^20": bench_msm(torch, dev, imad_peak, 20, 1),
-            "msm_g1_2^20_witness_like": bench_msm(torch, dev, imad_peak, 20, 1, witness_like=True),
-            "msm_g1_2^20_one_shot_bases": bench_msm(torch, dev, imad_peak, 20, 1, resident=False),
-            "msm_g2_2^18": bench_msm(torch, dev, imad_peak, 18, 2, iters=5),
-            "ntt_2^22": bench_ntt(torch, dev, imad_peak, hbm_gbs, 22),
-            "ntt_2^22_coset_inverse": bench_ntt(torch, dev, imad_peak, hbm_gbs, 22, inverse=True, coset=True),
-            "ntt_2^20": bench_ntt(torch, dev, imad_peak, hbm_gbs, 20),
-            "membership_batch_1024": bench_membership(torch, dev),
-            "membership_1024_slots_batch_1024": bench_membership(torch, dev, iters=2, slots=1024),
-            "mixed_batch_8192": bench_mixed(torch, dev),
-            "verify_batch": bench_verify(torch, dev),
-            "proof_2^20_constraints": bench_large_proof(torch, dev)}
+    jobs = {"msm_g1_2^20": lambda: bench_msm(torch, dev, imad_peak, 20, 1),
+            "msm_g1_2^20_witness_like": lambda: bench_msm(torch, dev, imad_peak, 20, 1, witness_like=True),
+            "msm_g1_2^20_one_shot_bases": lambda: bench_msm(torch, dev, imad_peak, 20, 1, resident=False),
+            "msm_g2_2^18": lambda: bench_msm(torch, dev, imad_peak, 18, 2, iters=5),
+            "ntt_2^22": lambda: bench_ntt(torch, dev, imad_peak, hbm_gbs, 22),
+            "ntt_2^22_coset_inverse": lambda: bench_ntt(torch, dev, imad_peak, hbm_gbs, 22, inverse=True, coset=True),
+            "ntt_2^20": lambda: bench_ntt(torch, dev, imad_peak, hbm_gbs, 20),
+            "membership_batch_1024": lambda: bench_membership(torch, dev),
+            "membership_1024_slots_batch_1024": lambda: bench_membership(torch, dev, iters=2, slots=1024),
+            "mixed_batch_8192": lambda: bench_mixed(torch, dev),
+            "verify_batch": lambda: bench_verify(torch, dev),
+            "proof_2^20_constraints": lambda: bench_large_proof(torch, dev)}
+    out = {}
+    for name, fn in jobs.items():           # one failing workload is recorded under its key, the others still run
+        try:
+            out[name] = fn()
+        except Exception as e:              # noqa: BLE001
+            out[name] = {"error": repr(e)}
+    return out
