@@ -241,6 +241,7 @@ def bench(torch, dev, imad_peak, hbm_gbs):
             "membership_1024_slots_batch_1024": lambda: bench_membership(torch, dev, iters=2, slots=1024),
             "mixed_batch_8192": lambda: bench_mixed(torch, dev),
             "verify_batch": lambda: bench_verify(torch, dev),
+            "verify_batch_65536_rlc": lambda: bench_verify(torch, dev, n=65536, iters=2),
             "proof_2^20_constraints": lambda: bench_large_proof(torch, dev)}
     out = {}
     for name, fn in jobs.items():           # one failing workload is recorded under its key, the others still run

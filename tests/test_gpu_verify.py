@@ -128,3 +128,65 @@ def test_batch_then_verify_proofs_parallel(api):
     broken[50] ^= 4
     res = api.verify_proofs_parallel([(bytes(broken), "equality"), (proofs[1], "membership"), (proofs[0], "membership")])
     assert res == [False, True, False]
+
+
+def test_rlc_batched_verification_equals_independent_verification(eq_keys, mb_keys, co, po, frs, monkeypatch):
+    # Large batches take the random-linear-combination path (one Miller loop per proof, one final exponentiation per
+    # group of 64); forced here at a small size.  Decisions must be those of proof-by-proof verification: malformed
+    # proofs are reported individually, a group holding a false proof falls back to k_verify4, clean groups pass.
+    pk = engine.ProvingKey(eq_keys.pk_bytes, window_bits=WINDOW_BITS)
+    pk.circuit_builtin(engine.EQUALITY, 110)
+    n = 64 * 4 + 21                                                      # five groups, the last one partial
+    rng = po.SplitMix64(77)
+    a = np.array([rng.next_u64() for _ in range(n)], np.uint64)
+    proofs, cms, st = pk.prove_equality_batch(a, a, frs(78, n), frs(79, n))
+    pk.close()
+    assert not st.any()
+    vk = engine.VerifyingKey(eq_keys.vk_bytes)
+    bad = proofs.copy()
+    x = cms.copy()
+    bad[3, 5] ^= 1                                                       # off-curve A                      (group 0)
+    bad[70, 192:256] = proofs[71, 192:256]                               # a valid curve point, wrong C      (group 1)
+    x[200] = cms[201]                                                    # wrong public input                (group 3)
+    bad[270, 64:192] = np.frombuffer(po.g2_to_bytes(po.G2.mul(po.G2_GEN, 5)), np.uint8)   # wrong B            (group 4)
+    want = np.ones(n, bool)
+    want[[3, 70, 200, 270]] = False
+    monkeypatch.setenv("LZKP_VERIFY_RLC_MIN", "1000000000")
+    independent = vk.verify_batch(bad, x)
+    assert np.array_equal(independent, want)
+    monkeypatch.setenv("LZKP_VERIFY_RLC_MIN", "64")
+    assert np.array_equal(vk.verify_batch(bad, x), want)                 # groups 0, 1, 3, 4 re-verified; group 2 by the combined check
+    assert vk.verify_batch(proofs, cms).all()                            # all valid: no fallback at all
+    assert not vk.verify_batch(proofs, np.roll(cms, 1, axis=0)).any()    # all false
+    bad2 = proofs.copy()
+    bad2[130:140, 0] ^= 1                                                # only malformed proofs in group 2: excluded, the rest of the group still passes combined
+    w2 = np.ones(n, bool)
+    w2[130:140] = False
+    assert np.array_equal(vk.verify_batch(bad2, cms), w2)
+    vk.close()
+    # membership (129 public inputs: the vk_x combination is where the combined form saves most)
+    pkm = engine.ProvingKey(mb_keys.pk_bytes, window_bits=8)
+    pkm.circuit_builtin(engine.MEMBERSHIP, 64)
+    m = 70
+    sets = np.zeros((m, 64), np.uint64)
+    lens = np.zeros(m, np.uint32)
+    vals = np.zeros(m, np.uint64)
+    for i in range(m):
+        L = 1 + (i * 5) % 64
+        lens[i] = L
+        sets[i, :L] = [rng.next_u64() for _ in range(L)]
+        vals[i] = sets[i, i % L]
+    mp, mcm, mst = pkm.prove_membership_batch(vals, sets, lens, frs(80, m), frs(81, m))
+    pkm.close()
+    assert not mst.any()
+    xs = np.zeros((m, 129, 32), np.uint8)
+    for i in range(m):
+        pub = po.membership_public_inputs(int.from_bytes(mcm[i].tobytes(), "little"), [int(v) for v in sets[i, :lens[i]]])
+        xs[i] = co.fr_array(pub)
+    vkm = engine.VerifyingKey(mb_keys.vk_bytes)
+    assert vkm.verify_batch(mp, xs).all()
+    xs[66, 3, 0] ^= 1                                                    # one set element changed (group 1)
+    wm = np.ones(m, bool)
+    wm[66] = False
+    assert np.array_equal(vkm.verify_batch(mp, xs), wm)
+    vkm.close()
