@@ -239,7 +239,12 @@ int lzkp_ntt_device(void *d_in, void *d_out, uint32_t log_n, int inverse, int co
  * Proof::deserialize_uncompressed + Groth16::verify_with_processed_vk decide (snark.rs:378-400, 463-494):
  * proofs n x 256 B, public_inputs n x n_pub x 32 B canonical (equality: [commitment]; membership: [commitment,
  * set[64], is_real[64]], snark.rs:398,482-492); ok_out[i] = 1 accept, 0 reject (malformed, off-curve, outside the
- * subgroup, non-canonical, wrong input count, or failing the pairing equation). */
+ * subgroup, non-canonical, wrong input count, or failing the pairing equation).  lzkp_vk_load validates every point
+ * of the key (curve and subgroup), as deserialize_uncompressed does.
+ * Calls of at least 16384 proofs (LZKP_VERIFY_RLC_MIN) check groups of 64 proofs with one random linear combination
+ * each (128-bit coefficients from the OS CSPRNG: one Miller loop per proof, one final exponentiation per group);
+ * malformed proofs are reported individually and a failing group is re-verified proof by proof, so the decisions are
+ * those of independent verification up to a soundness error of 2^-128 per group. */
 typedef struct lzkp_vk lzkp_vk;
 int lzkp_vk_load(const uint8_t *vk_bytes, size_t len, lzkp_vk **out);
 void lzkp_vk_free(lzkp_vk *vk);
