@@ -190,3 +190,86 @@ def test_rlc_batched_verification_equals_independent_verification(eq_keys, mb_ke
     wm[66] = False
     assert np.array_equal(vkm.verify_batch(mp, xs), wm)
     vkm.close()
+
+
+def test_latency_form_equals_lane_per_proof_form(eq_keys, mb_keys, co, po, frs, monkeypatch):
+    # Calls of up to 512 proofs give every proof a CTA whose lanes share each Fq12 product (coop.cuh: prepared lines for
+    # -gamma / -delta, byte-window tables for vk_x, lane-parallel subgroup ladder); larger calls run one proof per lane
+    # (k_verify4).  Both must decide what the oracle's pairing verifier decides (snark.rs:377-401), case by case.
+    pk = engine.ProvingKey(eq_keys.pk_bytes, window_bits=WINDOW_BITS)
+    pk.circuit_builtin(engine.EQUALITY, 110)
+    n = 40
+    rng = po.SplitMix64(91)
+    a = np.array([rng.next_u64() for _ in range(n)], np.uint64)
+    proofs, cms, st = pk.prove_equality_batch(a, a, frs(92, n), frs(93, n))
+    pk.close()
+    assert not st.any()
+    bad, x = proofs.copy(), cms.copy()
+    bad[1, 5] ^= 1                                                       # A off the curve
+    bad[2, 70] ^= 1                                                      # B off the twist
+    bad[3, 200] ^= 1                                                     # C off the curve
+    bad[4, 255] ^= 0x20                                                  # stray flag bit
+    bad[5, 0:64] = proofs[6, 0:64]                                       # valid points, wrong proof
+    bad[7, 192:256] = proofs[8, 192:256]
+    bad[9, 64:192] = np.frombuffer(po.g2_to_bytes(po.G2.mul(po.G2_GEN, 77)), np.uint8)
+    bad[10, :64] = 0
+    bad[10, 63] = 0x40                                                   # A = infinity
+    bad[11, 64:192] = 0
+    bad[11, 191] = 0x40                                                  # B = infinity
+    bad[12, 192:256] = 0
+    bad[12, 255] = 0x40                                                  # C = infinity
+    bad[13, :] = 0
+    bad[14, 31] |= 0x3F                                                  # x >= q
+    offsub = bytes.fromhex("02000000000000000000000000000000000000000000000000000000000000000100000000000000000000000000000000000000000000000000000000000000ce0141067f1657f01323d6d1264d1f38c5e0ce2da0ec9950b908934178721f10de5f8f80b5b618595db7a7f6137c7f775a006a5485ac3d962ab99b5979c176ab")
+    bad[15, 64:192] = np.frombuffer(offsub, np.uint8)                    # on the twist, outside the r-torsion
+    x[16] = cms[17]                                                      # wrong public input
+    x[18] = 0xFF                                                         # non-canonical public input
+    x[19] = 0                                                            # zero public input
+    want = np.ones(n, bool)
+    want[[1, 2, 3, 4, 5, 7, 9, 10, 11, 12, 13, 14, 15, 16, 18, 19]] = False
+    ovk = po.vk_from_bytes(eq_keys.vk_bytes)
+    for k in (0, 5, 10, 11, 16, 19):                                     # the oracle's verdicts on a sample (it is slow)
+        try:
+            o = po.verify(ovk, [int.from_bytes(x[k].tobytes(), "little")], po.proof_from_bytes(bad[k].tobytes()))
+        except Exception:
+            o = False
+        assert bool(o) == bool(want[k]), k
+    vk = engine.VerifyingKey(eq_keys.vk_bytes)
+    monkeypatch.setenv("LZKP_VERIFY_COOP_MAX", "512")
+    coop = vk.verify_batch(bad, x)
+    one_by_one = np.array([vk.verify_batch(bad[k:k + 1], x[k:k + 1])[0] for k in range(n)])
+    monkeypatch.setenv("LZKP_VERIFY_COOP_MAX", "0")
+    lanes = vk.verify_batch(bad, x)
+    vk.close()
+    assert np.array_equal(coop, want) and np.array_equal(lanes, want) and np.array_equal(one_by_one, want)
+    # membership: 129 public inputs through the byte-window tables (64-bit set elements and a full-size commitment)
+    pkm = engine.ProvingKey(mb_keys.pk_bytes, window_bits=8)
+    pkm.circuit_builtin(engine.MEMBERSHIP, 64)
+    m = 12
+    sets = np.zeros((m, 64), np.uint64)
+    lens = np.zeros(m, np.uint32)
+    vals = np.zeros(m, np.uint64)
+    for i in range(m):
+        L = [1, 2, 63, 64][i % 4]
+        lens[i] = L
+        sets[i, :L] = [rng.next_u64() for _ in range(L)]
+        vals[i] = sets[i, i % L]
+    mp, mcm, mst = pkm.prove_membership_batch(vals, sets, lens, frs(94, m), frs(95, m))
+    pkm.close()
+    assert not mst.any()
+    xs = np.zeros((m, 129, 32), np.uint8)
+    for i in range(m):
+        pub = po.membership_public_inputs(int.from_bytes(mcm[i].tobytes(), "little"), [int(v) for v in sets[i, :lens[i]]])
+        xs[i] = co.fr_array(pub)
+    xs[3, 1, 0] ^= 1                                                     # first set element changed
+    xs[5, 128, 7] ^= 0x80                                                # last input changed
+    xs[7, 0, 31] ^= 1                                                    # top byte of the commitment changed
+    wm = np.ones(m, bool)
+    wm[[3, 5, 7]] = False
+    vkm = engine.VerifyingKey(mb_keys.vk_bytes)
+    monkeypatch.setenv("LZKP_VERIFY_COOP_MAX", "512")
+    coop_m = vkm.verify_batch(mp, xs)
+    monkeypatch.setenv("LZKP_VERIFY_COOP_MAX", "0")
+    lanes_m = vkm.verify_batch(mp, xs)
+    vkm.close()
+    assert np.array_equal(coop_m, wm) and np.array_equal(lanes_m, wm)

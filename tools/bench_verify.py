@@ -16,9 +16,11 @@ proofs, cms, st = pk.prove_equality_batch(a, a, r, s)
 if not os.environ.get("KEEP_PK"):
     pk.close()
 vk = engine.VerifyingKey(vk_bytes)
-for nb in (1, 64, 4096, 4096):
+for nb in [int(v) for v in os.environ.get('BATCHES', '1,8,64,256,512,1024,2048,4096').split(',')]:
     ok = vk.verify_batch(proofs[:nb], cms[:nb])
     assert ok.all()
+    bad = proofs[:nb].copy(); bad[nb // 2, 200] ^= 1
+    assert not vk.verify_batch(bad, cms[:nb])[nb // 2]
     K = 3
     ts = []
     for _ in range(K):
