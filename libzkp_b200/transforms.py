@@ -215,7 +215,7 @@ def bench_verify(torch, dev, n=4096, iters=3):
     pk.close()
     vk = engine.VerifyingKey(vk_bytes)
     out = {}
-    for nb in (1, n):
+    for nb in ((1, 64, 512, n) if n <= 4096 else (1, n)):
         ok = vk.verify_batch(proofs[:nb], cms[:nb])
         t0 = time.perf_counter()
         for _ in range(iters):
