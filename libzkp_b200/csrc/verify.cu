@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(kCoopThreads) k_verify_coop(const VkDev *__res
 
 // LZKP_COOP_SELFTEST=1 at key load: the cooperative Miller loop (both line sources), final exponentiation and subgroup
 // test against the serial code of pairing.cuh on the key's own points.  result: bit per failing stage.
-__global__ void __launch_bounds__(kCoopThreads) k_coop_selftest(const VkDev *__restrict__ vk, const Fq2 *__restrict__ lines_gamma, int *result, long long *stamps) {
+__global__ void __launch_bounds__(kCoopThreads) k_coop_selftest(const VkDev *__restrict__ vk, const Fq2 *__restrict__ lines_gamma, int *result, long long *stamps, int solo) {
     extern __shared__ uint4 smem_raw[];
     CoopSmem &sm = *reinterpret_cast<CoopSmem *>(smem_raw);
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -486,6 +486,16 @@ __global__ void __launch_bounds__(kCoopThreads) k_coop_selftest(const VkDev *__r
     const G2Affine B = vk->beta;
     const long long t_start = clock64();
     auto stamp = [&](int k) { if (lane == 0) stamps[k] = clock64() - t_start; };
+    if (solo) {              // timing only: the (A, B) Miller loop's two warps with nothing beside them (solo = 2: line chain alone first)
+        if (warp == 3) { coop::line_chain(&sm.ls, A, B, sm.lines, &sm.ready); stamp(11); }
+        if (warp == 0) {
+            if (solo == 2) coop::flag_wait(&sm.ready, coop::kLines);
+            const long long t0 = clock64();
+            coop::miller_f<true>(sm.fc[0].f, sm.lines, &sm.ready, nullptr, nullptr, &sm.fc[0].s);
+            if (lane == 0) { stamps[10] = clock64() - t_start; stamps[9] = clock64() - t0; }
+        }
+        return;
+    }
     if (warp == 0) {
         FChain &c = sm.fc[0];
         coop::miller_f<true>(c.f, sm.lines, &sm.ready, nullptr, nullptr, &c.s);
@@ -589,10 +599,10 @@ static int coop_prepare(VerifyingKeyDev *V) {
     CUDA_TRY(cudaDeviceSynchronize());
     if (getenv("LZKP_COOP_SELFTEST")) {
         DBuf d_res;
-        TRY(d_res.alloc(sizeof(int) + 12 * sizeof(long long)));
+        TRY(d_res.alloc(sizeof(int) + 16 * sizeof(long long)));
         CUDA_TRY(cudaMemset(d_res.p, 0, d_res.bytes));
         long long *d_st = reinterpret_cast<long long *>(d_res.as<char>() + 8);
-        LAUNCH(k_coop_selftest, 1, kCoopThreads, sizeof(CoopSmem), 0, V->vk.as<VkDev>(), V->lines_gamma.as<Fq2>(), d_res.as<int>(), d_st);
+        LAUNCH(k_coop_selftest, 1, kCoopThreads, sizeof(CoopSmem), 0, V->vk.as<VkDev>(), V->lines_gamma.as<Fq2>(), d_res.as<int>(), d_st, 0);
         int res = -1;
         long long st[10];
         CUDA_TRY(cudaMemcpy(&res, d_res.p, sizeof(int), cudaMemcpyDeviceToHost));
@@ -600,6 +610,13 @@ static int coop_prepare(VerifyingKeyDev *V) {
         fprintf(stderr, "lzkp coop selftest cycles: Miller(A,B) f chain done %lld, line chain done %lld, f chain alone %lld, prepared-line Miller %lld, "
                         "64 products %lld, final exponentiation %lld, subgroup test %lld, serial f6_inv %lld, Fq inverse %lld, 16 serial Fq2 products %lld\n",
                 st[0], st[3], st[5], st[2], st[6], st[1], st[4], st[7], st[8], st[9]);
+        for (int solo = 1; solo <= 2; solo++) {
+            long long s2[12];
+            LAUNCH(k_coop_selftest, 1, kCoopThreads, sizeof(CoopSmem), 0, V->vk.as<VkDev>(), V->lines_gamma.as<Fq2>(), d_res.as<int>(), d_st, solo);
+            CUDA_TRY(cudaMemcpy(s2, d_st, sizeof(s2), cudaMemcpyDeviceToHost));
+            fprintf(stderr, "lzkp coop selftest cycles, two warps only (%s): line chain done %lld, f chain done %lld (its own span %lld)\n",
+                    solo == 1 ? "side by side" : "line chain first", s2[11], s2[10], s2[9]);
+        }
         fprintf(stderr, "lzkp coop selftest: %s (mask %d: 1 Miller(A,B), 2 final exponentiation, 4 Miller on prepared lines, 8 subgroup)\n",
                 res == 0 ? "ok" : "MISMATCH", res);
         if (res != 0) return fail(LZKP_E_CUDA, "cooperative verifier self-test failed");
