@@ -199,8 +199,10 @@ int lzkp_witness_map(lzkp_pk *pk, size_t n_proofs, const uint8_t *z, uint8_t *h_
  *                              or 3 = both in one call.  d_h == NULL: a shard that holds h_query points (the first
  *                              `map_ranks` shards, lzkp_pk_shard_info) runs the witness map itself from z - h is never
  *                              sent between GPUs - and needs lzkp_circuit_*; shards without h_query points skip it
- *   lzkp_prove_combine_device  one rank: add the gathered partial sums, assemble and serialize the proof
- * All pointers are device pointers; calls are asynchronous on `stream`. */
+ *   lzkp_prove_combine_device  one rank: add the gathered partial sums, convert A, B, C to affine and serialize
+ * A partial is four G1 XYZZ sums and one G2 sum: A-range, s * A-range + r * B1-range (every shard scales its own sums
+ * beside its remaining MSMs, shard 0 including alpha + a_0 and beta + b_0, so the combining rank runs no scalar
+ * multiplication), L-range, H-range, B2-range.  All pointers are device pointers; calls are asynchronous on `stream`. */
 int lzkp_witness_map_device(lzkp_pk *pk, const void *d_z, void *d_h, void *stream);
 /* This shard's point range [first, first + count) of the queries a, b1, l, h, b2 (the +-delta extras included) and the
  * number of leading shards that run the witness map (and share the H query). */

@@ -187,7 +187,7 @@ struct lzkp_pk {
     // the five MSMs of one large proof run on side streams (each MsmBases has its own workspace), so the
     // latency-bound tail of one (bucket reduction, a few CTAs) runs under the accumulation of another
     cudaStream_t L_st[3] = {nullptr, nullptr, nullptr};
-    cudaEvent_t L_ev_in = nullptr, L_ev_done[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t L_ev_in = nullptr, L_ev_done[3] = {nullptr, nullptr, nullptr}, L_ev_a = nullptr;
     // single-proof sharding across GPUs: this rank's point range [lo, lo + cnt) of each query,
     // in the order a, b1, l, h, b2 (extras +-delta included); unsharded = the full ranges
     uint32_t shard_index = 0, shard_count = 1, map_ranks = 1;
@@ -207,6 +207,7 @@ struct lzkp_pk {
         for (MsmBases *b : {L_a, L_b1, L_b2, L_l, L_h}) if (b) msm_bases_free(b);
         for (auto s_ : L_st) if (s_) cudaStreamDestroy(s_);
         if (L_ev_in) cudaEventDestroy(L_ev_in);
+        if (L_ev_a) cudaEventDestroy(L_ev_a);
         for (auto ev : L_ev_done) if (ev) cudaEventDestroy(ev);
         if (ev_fork) cudaEventDestroy(ev_fork);
         for (auto ev : ev_join) if (ev) cudaEventDestroy(ev);
@@ -404,6 +405,7 @@ static int pk_load_impl(const uint8_t *bytes, size_t len, int validate, const lz
         }
         for (auto &s_ : pk->L_st) CUDA_TRY(cudaStreamCreateWithFlags(&s_, cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreateWithFlags(&pk->L_ev_in, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&pk->L_ev_a, cudaEventDisableTiming));
         for (auto &ev : pk->L_ev_done) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         pk->c = wb ? wb : 16;
         pk->W = (255 + pk->c - 1) / pk->c;
@@ -785,9 +787,15 @@ static int run_prove(lzkp_pk *pk, Workspace &ws, uint32_t P, const Fr *d_r, cons
         {
             Region reg(pk, LZKP_REGION_MSM_G1, pk->L_st[0]);
             TRY(msm_device_raw(pk->L_a, sa + (size_t)lo[0] * 32, cnt[0], res1 + 0, pk->L_st[0]));
+            CUDA_TRY(cudaEventRecord(pk->L_ev_a, pk->L_st[0]));
             TRY(msm_device_raw(pk->L_l, sl + (size_t)lo[2] * 32, cnt[2], res1 + 2, pk->L_st[0]));
         }
         TRY(msm_device_raw(pk->L_b1, sb + (size_t)lo[1] * 32, cnt[1], res1 + 1, pk->L_st[1]));
+        // slot 1 <- s * A-sum + r * B1-sum as soon as both exist, beside the remaining MSMs (k_scale_ab).  Shard 0 is the
+        // one whose sums carry the key's constant terms; a shard without points of either query has nothing to scale.
+        CUDA_TRY(cudaStreamWaitEvent(pk->L_st[1], pk->L_ev_a, 0));
+        if (cnt[0] || cnt[1] || pk->shard_index == 0)
+            LAUNCH(k_scale_ab, 1, 128, 0, pk->L_st[1], res1, pk->consts, d_r, d_s, pk->shard_index == 0 ? 1 : 0);
         {
             Region reg(pk, LZKP_REGION_MSM_G2, pk->L_st[2]);
             TRY(msm_device_raw(pk->L_b2, sb + (size_t)lo[4] * 32, cnt[4], ws.res2.p, pk->L_st[2]));
@@ -802,7 +810,7 @@ static int run_prove(lzkp_pk *pk, Workspace &ws, uint32_t P, const Fr *d_r, cons
         }
         if (!d_proofs) return LZKP_OK;           // partial sums only (sharded proving): the caller combines
         Region reg(pk, LZKP_REGION_ASSEMBLE, st);
-        LAUNCH(k_assemble, 1, 128, 0, st, res1, ws.res2.as<G2XYZZ>(), pk->consts, d_r, d_s, 1u, d_proofs);
+        LAUNCH(k_assemble_sums, 1, 96, 0, st, res1, ws.res2.as<G2XYZZ>(), pk->consts, 1u, d_proofs, 1, -1);
         return LZKP_OK;
     }
     const uint32_t c = pk->c, W = pk->W, gx = (P + 127) / 128;
@@ -882,7 +890,7 @@ static int run_prove(lzkp_pk *pk, Workspace &ws, uint32_t P, const Fr *d_r, cons
     else { Region reg(pk, LZKP_REGION_MSM_G2, st); batch_msm_g2(args(pk->g2, fit_variant(pk->g2, item_variant_g2(P)), ws.part2.p, ws.res2.p), st); }
     Region reg(pk, LZKP_REGION_ASSEMBLE, st);
     if (lat) {
-        LAUNCH(k_assemble_sums, (P + 31) / 32, 96, 0, st, ws.res1.as<G1XYZZ>(), ws.res2.as<G2XYZZ>(), pk->consts, P, d_proofs);
+        LAUNCH(k_assemble_sums, (P + 31) / 32, 96, 0, st, ws.res1.as<G1XYZZ>(), ws.res2.as<G2XYZZ>(), pk->consts, P, d_proofs, 4, 5);
         return LZKP_OK;
     }
     LAUNCH(k_assemble, (P + 31) / 32, 128, 0, st, ws.res1.as<G1XYZZ>(), ws.res2.as<G2XYZZ>(), pk->consts, d_r, d_s, P, d_proofs);
@@ -1589,8 +1597,8 @@ int lzkp_prove_combine_device(lzkp_pk *pk, const void *d_partials, int n_partial
     TRY(ensure_workspace(pk, ws, 1));
     LAUNCH(k_sum_partials, 1, 160, 0, st, (const uint8_t *)d_partials, (uint32_t)n_partials, ws.res1.as<G1XYZZ>(),
            ws.res2.as<G2XYZZ>());
-    LAUNCH(k_assemble, 1, 128, 0, st, ws.res1.as<G1XYZZ>(), ws.res2.as<G2XYZZ>(), pk->consts, (const Fr *)d_r,
-           (const Fr *)d_s, 1u, (uint8_t *)d_proof);
+    // slot 1 of every partial already holds the shard's s * A + r * B1 share (k_scale_ab): the tail is three conversions
+    LAUNCH(k_assemble_sums, 1, 96, 0, st, ws.res1.as<G1XYZZ>(), ws.res2.as<G2XYZZ>(), pk->consts, 1u, (uint8_t *)d_proof, 1, -1);
     TRY(ws_release(ws, st));
     CUDA_TRY(cudaGetLastError());
     return LZKP_OK;

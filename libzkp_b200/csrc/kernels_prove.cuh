@@ -424,17 +424,43 @@ __global__ void __launch_bounds__(128) k_assemble(const G1XYZZ *g1, const G2XYZZ
     }
 }
 
+// One large proof (P = 1): slot 1 <- s * (slot 0 [+ a0]) + r * (slot 1 [+ b0]), the four GLV strands on four warps.  The
+// two variable-base multiplications of the assembly (0.83 ms as a serial chain) leave the proof's tail: they only need
+// the A and B1 sums, so they run on a side stream beside the L, H and B2 MSMs; a shard scales ITS partial sums before
+// the gather (with_consts: the shard that also carries alpha + a_0 and beta + b_0), and C = sum of slots 1, 2, 3.
+__global__ void __launch_bounds__(128) k_scale_ab(G1XYZZ *g1, ProofConsts K, const Fr *r, const Fr *s, int with_consts) {
+    __shared__ uint4 sm_raw[3 * sizeof(G1XYZZ) / 16];
+    G1XYZZ *sm = reinterpret_cast<G1XYZZ *>(sm_raw);
+    const uint32_t role = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    G1XYZZ acc = G1XYZZ::inf();
+    if (lane == 0) {
+        G1XYZZ X = ld_vec(g1 + (role <= 1 ? 0 : 1));
+        if (with_consts) X.madd_cold(role <= 1 ? K.a0 : K.b0);
+        acc = glv_half(X, ld_vec(role <= 1 ? s : r), role & 1);
+        if (role) st_vec(sm + (role - 1), acc);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        acc.add_cold(ld_vec(sm));
+        acc.add_cold(ld_vec(sm + 1));
+        acc.add_cold(ld_vec(sm + 2));
+        st_vec(g1 + 1, acc);
+    }
+}
+
 // Latency form (small calls): g1[q * P + p] additionally holds q = 4: s*(alpha + a0) + sum (s z_i) a_i and
 // q = 5: r*(beta + b0) + sum (r z_i) b_i + 2 rs delta, so C is a sum of four MSM results and the tail of a proof is
 // three conversions to affine on three warps (no scalar multiplication).
+// (q0, q1) name the slots that hold the s*A and r*B1 shares: (4, 5) in the latency form; (1, -1) for one large proof,
+// where k_scale_ab has left s*A + r*B1 in slot 1.
 __global__ void __launch_bounds__(96) k_assemble_sums(const G1XYZZ *g1, const G2XYZZ *g2, ProofConsts K, uint32_t P,
-                                                      uint8_t *proofs) {
+                                                      uint8_t *proofs, int q0, int q1) {
     const uint32_t role = threadIdx.x >> 5, lane = threadIdx.x & 31, p = blockIdx.x * 32 + lane;
     if (p >= P) return;
     uint8_t *out = proofs + (size_t)p * 256;
     if (role == 0) {
-        G1XYZZ acc = ld_vec(g1 + 4 * (size_t)P + p);
-        acc.add_cold(ld_vec(g1 + 5 * (size_t)P + p));
+        G1XYZZ acc = ld_vec(g1 + (size_t)q0 * P + p);
+        if (q1 >= 0) acc.add_cold(ld_vec(g1 + (size_t)q1 * P + p));
         acc.add_cold(ld_vec(g1 + 2 * (size_t)P + p));
         acc.add_cold(ld_vec(g1 + 3 * (size_t)P + p));
         write_g1(out + 192, acc.to_affine());

@@ -8,8 +8,11 @@ queries (a, b1, l, h in G1; b2 in G2, ~2.8x per point) resident in HBM.  Per pro
      (1 up to 4 GPUs, 3 at 8: lzkp_pk_shard_info) also run the witness map THEMSELVES (7 tiled NTTs - not worth
      distributing below ~2^24) and share the H query between them, in exchange for smaller z-slices.  h is never
      sent between GPUs (round 1 broadcast 32 MiB of it from rank 0, which serialised every H slice behind rank 0);
-  3. ONE all_gather collects 784 B per rank: 768 B of XYZZ partial sums + the rank's status word;
-  4. rank 0 adds the partial sums, assembles and serializes the proof.
+  3. a rank that holds points of the A or B1 query multiplies ITS partial sums by s and r as soon as they exist
+     (k_scale_ab, beside its remaining MSMs): the two variable-base multiplications of the assembly (0.83 ms as a
+     serial chain on rank 0 in the first version) are gone from the tail;
+  4. ONE all_gather collects 784 B per rank: 768 B of XYZZ partial sums (A, s A + r B1, L, H, B2) + the status word;
+  5. rank 0 adds the partial sums, converts A, B, C to affine and serializes the proof.
 
 Two collectives per proof; everything between them is asynchronous on the caller's CUDA stream.
 """
