@@ -183,14 +183,15 @@ struct lzkp_pk {
     bool large = false;
     bool tiled_wm = false;     // witness map on the tiled multi-pass NTT (domain above 2^12)
     MsmBases *L_a = nullptr, *L_b1 = nullptr, *L_b2 = nullptr, *L_l = nullptr, *L_h = nullptr;
-    DBuf L_sa, L_sb, L_sl;
+    DBuf L_sa, L_sb, L_sl, L_sb1;
     // the five MSMs of one large proof run on side streams (each MsmBases has its own workspace), so the
     // latency-bound tail of one (bucket reduction, a few CTAs) runs under the accumulation of another
-    cudaStream_t L_st[3] = {nullptr, nullptr, nullptr};
-    cudaEvent_t L_ev_in = nullptr, L_ev_done[3] = {nullptr, nullptr, nullptr}, L_ev_a = nullptr;
+    cudaStream_t L_st[3] = {nullptr, nullptr, nullptr}, L_st_scale = nullptr;
+    cudaEvent_t L_ev_in = nullptr, L_ev_done[3] = {nullptr, nullptr, nullptr}, L_ev_a = nullptr, L_ev_scale = nullptr;
     // single-proof sharding across GPUs: this rank's point range [lo, lo + cnt) of each query,
     // in the order a, b1, l, h, b2 (extras +-delta included); unsharded = the full ranges
     uint32_t shard_index = 0, shard_count = 1, map_ranks = 1;
+    bool L_scaled = false;            // this proof's k_scale_a share is pending in res1[4]
     uint32_t L_lo[5] = {0, 0, 0, 0, 0}, L_cnt[5] = {0, 0, 0, 0, 0};
     cudaStream_t stream = nullptr, stream2 = nullptr;      // chunk i of a batch runs on streams[i & 1]
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
@@ -208,6 +209,8 @@ struct lzkp_pk {
         for (auto s_ : L_st) if (s_) cudaStreamDestroy(s_);
         if (L_ev_in) cudaEventDestroy(L_ev_in);
         if (L_ev_a) cudaEventDestroy(L_ev_a);
+        if (L_ev_scale) cudaEventDestroy(L_ev_scale);
+        if (L_st_scale) cudaStreamDestroy(L_st_scale);
         for (auto ev : L_ev_done) if (ev) cudaEventDestroy(ev);
         if (ev_fork) cudaEventDestroy(ev_fork);
         for (auto ev : ev_join) if (ev) cudaEventDestroy(ev);
@@ -403,9 +406,17 @@ static int pk_load_impl(const uint8_t *bytes, size_t len, int validate, const lz
             v.push_back(delta_g2);
             TRY(msm_bases_load(2, reinterpret_cast<const uint8_t *>(v.data() + pk->L_lo[4]), pk->L_cnt[4], wb, 1, validate, &pk->L_b2, 1));
         }
-        for (auto &s_ : pk->L_st) CUDA_TRY(cudaStreamCreateWithFlags(&s_, cudaStreamNonBlocking));
+        {   // the A-sum feeds the one serial chain left (k_scale_a, 0.8 ms): their stream goes first
+            int prio_lo = 0, prio_hi = 0;
+            CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+            const bool prio = !(getenv("LZKP_NO_STREAM_PRIORITY") && atoi(getenv("LZKP_NO_STREAM_PRIORITY")));
+            for (int i = 0; i < 3; i++)
+                CUDA_TRY(cudaStreamCreateWithPriority(&pk->L_st[i], cudaStreamNonBlocking, prio_lo));
+            CUDA_TRY(cudaStreamCreateWithPriority(&pk->L_st_scale, cudaStreamNonBlocking, prio ? prio_hi : prio_lo));
+        }
         CUDA_TRY(cudaEventCreateWithFlags(&pk->L_ev_in, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&pk->L_ev_a, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&pk->L_ev_scale, cudaEventDisableTiming));
         for (auto &ev : pk->L_ev_done) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         pk->c = wb ? wb : 16;
         pk->W = (255 + pk->c - 1) / pk->c;
@@ -694,7 +705,7 @@ static int ensure_workspace(lzkp_pk *pk, Workspace &ws, uint32_t P) {
     TRY(ws.h.ensure(P * n * 32));
     if (pk->tiled_wm) TRY(ws.tmp.ensure(3 * P * n * 32));
     if (pk->large) {
-        TRY(pk->L_sa.ensure(nv * 32)); TRY(pk->L_sb.ensure(nv * 32)); TRY(pk->L_sl.ensure(((size_t)pk->n_wit + 1) * 32));
+        TRY(pk->L_sa.ensure(nv * 32)); TRY(pk->L_sb.ensure(nv * 32)); TRY(pk->L_sb1.ensure(nv * 32)); TRY(pk->L_sl.ensure(((size_t)pk->n_wit + 1) * 32));
     } else {
         TRY(ws.dig.ensure((size_t)pk->n_dig_rows * pk->W * P * (pk->c > 16 ? 4 : 2)));
     }
@@ -784,18 +795,29 @@ static int run_prove(lzkp_pk *pk, Workspace &ws, uint32_t P, const Fr *d_r, cons
         // fork: the z-only MSMs (a, l | b1 | b2) on three side streams; this stream runs the witness map, then h
         CUDA_TRY(cudaEventRecord(pk->L_ev_in, st));
         for (auto s_ : pk->L_st) CUDA_TRY(cudaStreamWaitEvent(s_, pk->L_ev_in, 0));
+        CUDA_TRY(cudaStreamWaitEvent(pk->L_st_scale, pk->L_ev_in, 0));
+        // The A-sum feeds the one serial chain left: slot 4 <- s * A-sum (+ the constant terms on shard 0), k_scale_a.  Both
+        // run on the priority stream, so the chain (0.8 ms) ends under the other MSMs instead of after them.
+        TRY(msm_device_raw(pk->L_a, sa + (size_t)lo[0] * 32, cnt[0], res1 + 0, pk->L_st_scale));
+        pk->L_scaled = cnt[0] || pk->shard_index == 0;
+        if (pk->L_scaled) LAUNCH(k_scale_a, 1, 128, 0, pk->L_st_scale, res1, pk->consts, d_r, d_s, pk->shard_index == 0 ? 1 : 0);
+        CUDA_TRY(cudaEventRecord(pk->L_ev_scale, pk->L_st_scale));
         {
             Region reg(pk, LZKP_REGION_MSM_G1, pk->L_st[0]);
-            TRY(msm_device_raw(pk->L_a, sa + (size_t)lo[0] * 32, cnt[0], res1 + 0, pk->L_st[0]));
-            CUDA_TRY(cudaEventRecord(pk->L_ev_a, pk->L_st[0]));
             TRY(msm_device_raw(pk->L_l, sl + (size_t)lo[2] * 32, cnt[2], res1 + 2, pk->L_st[0]));
         }
-        TRY(msm_device_raw(pk->L_b1, sb + (size_t)lo[1] * 32, cnt[1], res1 + 1, pk->L_st[1]));
-        // slot 1 <- s * A-sum + r * B1-sum as soon as both exist, beside the remaining MSMs (k_scale_ab).  Shard 0 is the
-        // one whose sums carry the key's constant terms; a shard without points of either query has nothing to scale.
-        CUDA_TRY(cudaStreamWaitEvent(pk->L_st[1], pk->L_ev_a, 0));
-        if (cnt[0] || cnt[1] || pk->shard_index == 0)
-            LAUNCH(k_scale_ab, 1, 128, 0, pk->L_st[1], res1, pk->consts, d_r, d_s, pk->shard_index == 0 ? 1 : 0);
+        // B1 only enters the proof as r * B1: its MSM runs on r * z_i (the delta extra: r * s), so no scalar multiplication
+        // follows it; s * A-sum and the constant terms are scaled beside the remaining MSMs (k_scale_a).
+        if (cnt[1]) {
+            uint8_t *sb1 = pk->L_sb1.as<uint8_t>();
+            const uint32_t last = nv - 1, hi = lo[1] + cnt[1], zc = std::min(hi, last) - lo[1];
+            if (zc) LAUNCH(k_scalars_times, (zc + 127) / 128, 128, 0, pk->L_st[1], (const Fr *)(sb + (size_t)lo[1] * 32), d_r,
+                           (Fr *)(sb1 + (size_t)lo[1] * 32), zc);
+            if (hi > last) CUDA_TRY(cudaMemcpyAsync(sb1 + (size_t)last * 32, ws.rs.p, 32, dd, pk->L_st[1]));
+            TRY(msm_device_raw(pk->L_b1, sb1 + (size_t)lo[1] * 32, cnt[1], res1 + 1, pk->L_st[1]));
+        } else {
+            TRY(msm_device_raw(pk->L_b1, sb, 0, res1 + 1, pk->L_st[1]));
+        }
         {
             Region reg(pk, LZKP_REGION_MSM_G2, pk->L_st[2]);
             TRY(msm_device_raw(pk->L_b2, sb + (size_t)lo[4] * 32, cnt[4], ws.res2.p, pk->L_st[2]));
@@ -808,6 +830,8 @@ static int run_prove(lzkp_pk *pk, Workspace &ws, uint32_t P, const Fr *d_r, cons
             CUDA_TRY(cudaEventRecord(pk->L_ev_done[i], pk->L_st[i]));
             CUDA_TRY(cudaStreamWaitEvent(st, pk->L_ev_done[i], 0));
         }
+        CUDA_TRY(cudaStreamWaitEvent(st, pk->L_ev_scale, 0));
+        if (pk->L_scaled) LAUNCH(k_add_slot, 1, 1, 0, st, res1, 1, 4);
         if (!d_proofs) return LZKP_OK;           // partial sums only (sharded proving): the caller combines
         Region reg(pk, LZKP_REGION_ASSEMBLE, st);
         LAUNCH(k_assemble_sums, 1, 96, 0, st, res1, ws.res2.as<G2XYZZ>(), pk->consts, 1u, d_proofs, 1, -1);
@@ -1572,6 +1596,7 @@ int lzkp_prove_partial_device(lzkp_pk *pk, const void *d_z, const void *d_r, con
         // the side streams of the previous proof must have left the scalar vectors (their join events are recorded
         // in phase 2; waiting on a never-recorded event is a no-op)
         for (auto ev : pk->L_ev_done) CUDA_TRY(cudaStreamWaitEvent(st, ev, 0));
+        if (pk->L_ev_scale) CUDA_TRY(cudaStreamWaitEvent(st, pk->L_ev_scale, 0));
         CUDA_TRY(cudaMemsetAsync(d_status, 0, 4, st));
         CUDA_TRY(cudaMemcpyAsync(ws.z.p, d_z, (size_t)pk->n_vars * 32, cudaMemcpyDeviceToDevice, st));
     }

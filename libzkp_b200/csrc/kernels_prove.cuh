@@ -424,35 +424,49 @@ __global__ void __launch_bounds__(128) k_assemble(const G1XYZZ *g1, const G2XYZZ
     }
 }
 
-// One large proof (P = 1): slot 1 <- s * (slot 0 [+ a0]) + r * (slot 1 [+ b0]), the four GLV strands on four warps.  The
-// two variable-base multiplications of the assembly (0.83 ms as a serial chain) leave the proof's tail: they only need
-// the A and B1 sums, so they run on a side stream beside the L, H and B2 MSMs; a shard scales ITS partial sums before
-// the gather (with_consts: the shard that also carries alpha + a_0 and beta + b_0), and C = sum of slots 1, 2, 3.
-__global__ void __launch_bounds__(128) k_scale_ab(G1XYZZ *g1, ProofConsts K, const Fr *r, const Fr *s, int with_consts) {
+// One large proof (P = 1).  C = s*A + r*B1 + L + H needs neither B1 itself nor a variable-base multiplication after the
+// MSMs: the B1 MSM runs on the scalars r * z_i (k_scalars_times), so slot 1 IS r * (B1-sum), and
+//     slot 4 <- s * (slot 0 [+ alpha + a_0]) [+ r * (beta + b_0)]
+// runs here as soon as the A-sum exists, beside the remaining MSMs: the GLV strands of s * A on warps 0 and 1, those
+// of the constant term on warps 2 and 3 (with_consts: the shard whose sums carry the key's constant terms).  The
+// first version ran s*A + r*B1 after everything else: 0.83 ms of serial chain at the end of every proof.
+__global__ void __launch_bounds__(128) k_scale_a(G1XYZZ *g1, ProofConsts K, const Fr *r, const Fr *s, int with_consts) {
     __shared__ uint4 sm_raw[3 * sizeof(G1XYZZ) / 16];
     G1XYZZ *sm = reinterpret_cast<G1XYZZ *>(sm_raw);
     const uint32_t role = threadIdx.x >> 5, lane = threadIdx.x & 31;
     G1XYZZ acc = G1XYZZ::inf();
-    if (lane == 0) {
-        G1XYZZ X = ld_vec(g1 + (role <= 1 ? 0 : 1));
-        if (with_consts) X.madd_cold(role <= 1 ? K.a0 : K.b0);
+    if (lane == 0 && (role <= 1 || with_consts)) {
+        G1XYZZ X = role <= 1 ? ld_vec(g1) : G1XYZZ::from_affine(K.b0);
+        if (role <= 1 && with_consts) X.madd_cold(K.a0);
         acc = glv_half(X, ld_vec(role <= 1 ? s : r), role & 1);
-        if (role) st_vec(sm + (role - 1), acc);
     }
+    if (lane == 0 && role) st_vec(sm + (role - 1), acc);
     __syncthreads();
     if (threadIdx.x == 0) {
         acc.add_cold(ld_vec(sm));
         acc.add_cold(ld_vec(sm + 1));
         acc.add_cold(ld_vec(sm + 2));
-        st_vec(g1 + 1, acc);
+        st_vec(g1 + 4, acc);
     }
+}
+// out[i] = k * z[i] (canonical in and out)
+__global__ void k_scalars_times(const Fr *z, const Fr *k, Fr *out, uint32_t count) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    st_vec(out + i, (ld_vec(z + i) * ld_vec(k)) * Fr::r2());
+}
+// g1[dst] += g1[src] (one thread)
+__global__ void k_add_slot(G1XYZZ *g1, int dst, int src) {
+    G1XYZZ a = ld_vec(g1 + dst);
+    a.add_cold(ld_vec(g1 + src));
+    st_vec(g1 + dst, a);
 }
 
 // Latency form (small calls): g1[q * P + p] additionally holds q = 4: s*(alpha + a0) + sum (s z_i) a_i and
 // q = 5: r*(beta + b0) + sum (r z_i) b_i + 2 rs delta, so C is a sum of four MSM results and the tail of a proof is
 // three conversions to affine on three warps (no scalar multiplication).
 // (q0, q1) name the slots that hold the s*A and r*B1 shares: (4, 5) in the latency form; (1, -1) for one large proof,
-// where k_scale_ab has left s*A + r*B1 in slot 1.
+// where slot 1 holds r * B1 plus the share k_scale_a computed (s * A and the constant terms).
 __global__ void __launch_bounds__(96) k_assemble_sums(const G1XYZZ *g1, const G2XYZZ *g2, ProofConsts K, uint32_t P,
                                                       uint8_t *proofs, int q0, int q1) {
     const uint32_t role = threadIdx.x >> 5, lane = threadIdx.x & 31, p = blockIdx.x * 32 + lane;
