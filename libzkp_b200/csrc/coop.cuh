@@ -380,32 +380,40 @@ __device__ __noinline__ void line_chain(LineState *st, const G1Affine &P, const 
 // ---------------------------------------------------------------- the f chain of one Miller loop
 // SCALED: `lines` is the shared array a line_chain is filling (wait on *ready).  Otherwise `lines` are the PREPARED
 // (unscaled) coefficients of a fixed G2 point in global memory; lanes 18..20 of the preceding product scale the next
-// line by emb = {(yP, 0), (xP, 0), 1} into the double buffer ln[2][3].
+// line by emb = {(yP, 0), (xP, 0), 1}.  Either way the line l0 + l1 w + l2 v w is handed to the product as a dense
+// operand (l0, 0, 0, l1, l2, 0) in ln[2][6], whose other slots stay zero: ONE product body serves squarings and line
+// products - a second (sparse) instantiation doubles the instruction footprint of a loop that runs on a lone warp.
 template <bool SCALED>
 __device__ __noinline__ void miller_f(Fq2 *f, const Fq2 *lines, const int *ready, Fq2 *ln, const Fq2 *emb, Scratch *s) {
     const int lane = lane_id();
     f12_set_one(f);
     int c = 0, scaled = 0;
+    const int slot = lane % 3 == 0 ? 0 : 2 + lane % 3;          // coefficient index of line component lane % 3: 0, 3, 4
     auto step = [&](bool is_line) {
         const Fq2 *sa = nullptr, *sb = nullptr;
         Fq2 *so = nullptr;
         const Fq2 *b = f;
         if (SCALED) {
-            if (is_line) { flag_wait(ready, c + 1); b = lines + 3 * c; }
+            if (is_line) {
+                flag_wait(ready, c + 1);
+                if (lane < 3) stq(ln + slot, ldq(lines + 3 * c + lane));
+                __syncwarp();
+                b = ln;
+            }
         } else {
-            if (is_line) b = ln + 3 * (c & 1);
+            if (is_line) b = ln + 6 * (c & 1);
             const int target = is_line ? c + 1 : c;
             if (scaled == target && target < kLines) {
                 if (lane >= 18 && lane < 21) {
                     sa = lines + 3 * target + (lane - 18);
                     sb = emb + (lane - 18);
-                    so = ln + 3 * (target & 1) + (lane - 18);
+                    so = ln + 6 * (target & 1) + slot;
                 }
                 scaled++;
             }
         }
-        if (is_line) { f12_mul<true>(f, f, b, s, sa, sb, so); c++; }
-        else f12_mul<false>(f, f, f, s, sa, sb, so);
+        f12_mul<false>(f, f, b, s, sa, sb, so);
+        if (is_line) c++;
     };
 #pragma unroll 1
     for (int i = 63; i >= 0; i--) {

@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(64) k_vk_tables(const G1Affine *__restrict__ g
 }
 
 struct FChain {
-    Fq2 f[6], ln[6], emb[3];
+    Fq2 f[6], ln[12], emb[3];      // ln: two dense line operands, slots 1, 2, 5 stay zero
     coop::Scratch s;
 };
 struct CoopSmem {
@@ -393,6 +393,7 @@ constexpr uint32_t kCoopThreads = 192;   // six warps: roles 0-3 on the four SM 
 __device__ __forceinline__ void coop_prologue(CoopSmem &sm) {
     if (threadIdx.x == 0) { sm.ready = 0; sm.done[0] = sm.done[1] = sm.done[2] = 0; sm.sub_ok = 0; }
     if (threadIdx.x < 3) st_vec(&sm.fc[threadIdx.x].s.P[18], Fq2::zero());
+    if (threadIdx.x < 36) st_vec(&sm.fc[threadIdx.x / 12].ln[threadIdx.x % 12], Fq2::zero());
 }
 __device__ __forceinline__ void set_emb(FChain &c, const G1Affine &P) {
     if (coop::lane_id() == 0) {
@@ -436,7 +437,7 @@ __global__ void __launch_bounds__(kCoopThreads) k_verify_coop(const VkDev *__res
         if (!all_good) { if (lane == 0) ok[p] = 0; return; }
         FChain &c = sm.fc[0];
         if (skip_ab) coop::f12_set_one(c.f);
-        else coop::miller_f<true>(c.f, sm.lines, &sm.ready, nullptr, nullptr, &c.s);
+        else coop::miller_f<true>(c.f, sm.lines, &sm.ready, c.ln, nullptr, &c.s);
         coop::flag_wait(&sm.done[0], 1);
         coop::f12_mul<false>(c.f, c.f, sm.fc[1].f, &c.s);
         coop::flag_wait(&sm.done[1], 1);
@@ -491,18 +492,18 @@ __global__ void __launch_bounds__(kCoopThreads) k_coop_selftest(const VkDev *__r
         if (warp == 0) {
             if (solo == 2) coop::flag_wait(&sm.ready, coop::kLines);
             const long long t0 = clock64();
-            coop::miller_f<true>(sm.fc[0].f, sm.lines, &sm.ready, nullptr, nullptr, &sm.fc[0].s);
+            coop::miller_f<true>(sm.fc[0].f, sm.lines, &sm.ready, sm.fc[0].ln, nullptr, &sm.fc[0].s);
             if (lane == 0) { stamps[10] = clock64() - t_start; stamps[9] = clock64() - t0; }
         }
         return;
     }
     if (warp == 0) {
         FChain &c = sm.fc[0];
-        coop::miller_f<true>(c.f, sm.lines, &sm.ready, nullptr, nullptr, &c.s);
+        coop::miller_f<true>(c.f, sm.lines, &sm.ready, c.ln, nullptr, &c.s);
         stamp(0);
         {   // timing only: the same f chain again with every line already there, and 64 plain products
             const long long t0 = clock64();
-            coop::miller_f<true>(c.ln, sm.lines, &sm.ready, nullptr, nullptr, &c.s);
+            coop::miller_f<true>(c.ln, sm.lines, &sm.ready, c.ln + 6, nullptr, &c.s);
             if (lane == 0) stamps[5] = clock64() - t0;
             const long long t1 = clock64();
             for (int i = 0; i < 64; i++) coop::f12_mul<false>(c.ln, c.ln, c.f, &c.s);
