@@ -711,7 +711,16 @@ int verify_batch(VerifyingKeyDev *V, size_t n, const uint8_t *proofs, const uint
     // the combined check's tail (a whole pairing per group) would only add to it.
     const size_t rlc_min = getenv("LZKP_VERIFY_RLC_MIN") ? (size_t)atoll(getenv("LZKP_VERIFY_RLC_MIN")) : 16384;
     if (n < rlc_min || n > 0xFFFFFFFFull) {
+        static const bool timing = getenv("LZKP_VERIFY_TIMING") != nullptr;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, 0); }
         verify_range(0, n);
+        if (timing) {
+            cudaEventRecord(e1, 0); cudaEventSynchronize(e1);
+            float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+            fprintf(stderr, "lzkp verify_batch: %zu proofs, kernel %.3f ms (events)\n", n, ms);
+            cudaEventDestroy(e0); cudaEventDestroy(e1);
+        }
         CUDA_TRY(cudaMemcpy(ok_out, d_ok.p, n, cudaMemcpyDeviceToHost));
         CUDA_TRY(cudaGetLastError());
         return LZKP_OK;
