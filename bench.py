@@ -330,7 +330,8 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.empty_cache()
         dist.barrier()
         # a failure in an extra must not cost the headline line: it is recorded under its key instead
-        for key, fn in (("proof_2^20_sharded", bench_sharded_proof), ("mixed_batch_65536", bench_mixed_sharded)):
+        for key, fn in (("proof_2^20_sharded", bench_sharded_proof), ("mixed_batch_65536", bench_mixed_sharded),
+                        ("transform_replicas", bench_replicas)):
             try:
                 multi[key] = fn(torch, dist, dev, rank, world)
             except Exception as e:  # noqa: BLE001
@@ -491,6 +492,26 @@ def bench_sharded_proof(torch, dist, dev, rank, world, rounds=349524, iters=5):
         full.close()
     sp.close()
     return out
+
+
+def bench_replicas(torch, dist, dev, rank, world):
+    """The stand-alone transforms do not shard (replicas only): every rank runs its own 2^20 G1 MSM
+    and 2^22 NTT at the same time; the aggregate is the sum, the slowest rank is reported beside it."""
+    from libzkp_b200 import transforms
+    peak, _ = imad_peak()
+    dist.barrier()
+    m = transforms.bench_msm(torch, dev, peak, 20, 1)
+    dist.barrier()
+    t = transforms.bench_ntt(torch, dev, peak, measured_hbm(), 22)
+    v = torch.tensor([m["points_per_s"], t["elements_per_s"], -m["points_per_s"], -t["elements_per_s"]], device=dev, dtype=torch.float64)
+    tot = v.clone()
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    mx = v.clone()
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    return {"n_gpus": world, "msm_g1_2^20_points_per_s_total": float(tot[0]), "msm_g1_2^20_points_per_s_slowest_rank": float(-mx[2]),
+            "msm_g1_2^20_frac_of_imad_peak_rank0": m["imad_frac_of_measured_peak"], "msm_result_checked": m["result_equals_sum_k_s_times_G"],
+            "ntt_2^22_elements_per_s_total": float(tot[1]), "ntt_2^22_elements_per_s_slowest_rank": float(-mx[3]),
+            "what": "independent replicas, one per GPU, timed side by side (no collective: these transforms do not shard)"}
 
 
 def bench_mixed_sharded(torch, dist, dev, rank, world, total=65536, iters=3):

@@ -200,7 +200,9 @@ __device__ __forceinline__ void flag_publish(int *flag, int v) {     // whole wa
 }
 __device__ __forceinline__ void flag_wait(const int *flag, int at_least) {
     if (lane_id() == 0) {
-        while (*reinterpret_cast<const volatile int *>(flag) < at_least) {}
+        // back off between polls: a spinning lane takes issue slots from the warp that shares its SM partition
+        // (measured: a helper spinning beside the critical warp doubled that warp's time per product)
+        while (*reinterpret_cast<const volatile int *>(flag) < at_least) __nanosleep(40);
         __threadfence_block();
     }
     __syncwarp();
@@ -383,11 +385,22 @@ __device__ __noinline__ void line_chain(LineState *st, const G1Affine &P, const 
 // line by emb = {(yP, 0), (xP, 0), 1}.  Either way the line l0 + l1 w + l2 v w is handed to the product as a dense
 // operand (l0, 0, 0, l1, l2, 0) in ln[2][6], whose other slots stay zero: ONE product body serves squarings and line
 // products - a second (sparse) instantiation doubles the instruction footprint of a loop that runs on a lone warp.
+// The loop runs the iterations i_hi .. i_lo of the bits of 6x + 2 starting from f = 1, then `tail_sq` bare squarings,
+// then (final_lines) the two Frobenius lines.  The value of the whole loop factors as
+//     f = (loop over 63 .. m, then m squarings) * (loop over m-1 .. 0 and the final lines, started from 1),
+// so two warps can each run a share of the (A, B) loop (kMillerSplit): 102 + 104 products side by side instead of 166.
+constexpr int kMillerSplit = 40;
+LZ_HD constexpr int lines_before(int i_hi) {          // lines consumed by the iterations 63 .. i_hi + 1
+    int c = 0;
+    for (int i = 63; i > i_hi; i--) c += 1 + (int)((kAteLo >> i) & 1ull);
+    return c;
+}
 template <bool SCALED>
-__device__ __noinline__ void miller_f(Fq2 *f, const Fq2 *lines, const int *ready, Fq2 *ln, const Fq2 *emb, Scratch *s) {
+__device__ __noinline__ void miller_f(Fq2 *f, const Fq2 *lines, const int *ready, Fq2 *ln, const Fq2 *emb, Scratch *s,
+                                      int i_hi = 63, int i_lo = 0, int tail_sq = 0, bool final_lines = true) {
     const int lane = lane_id();
     f12_set_one(f);
-    int c = 0, scaled = 0;
+    int c = lines_before(i_hi), scaled = c;
     const int slot = lane % 3 == 0 ? 0 : 2 + lane % 3;          // coefficient index of line component lane % 3: 0, 3, 4
     auto step = [&](bool is_line) {
         const Fq2 *sa = nullptr, *sb = nullptr;
@@ -416,28 +429,58 @@ __device__ __noinline__ void miller_f(Fq2 *f, const Fq2 *lines, const int *ready
         if (is_line) c++;
     };
 #pragma unroll 1
-    for (int i = 63; i >= 0; i--) {
-        step(false);
+    for (int i = i_hi; i >= i_lo; i--) {
+        if (i != i_hi || !SCALED) step(false);      // f = 1 before the first iteration (prepared lines: the squaring of 1 carries the first scaling)
         step(true);
         if ((kAteLo >> i) & 1ull) step(true);
     }
-    step(true);
-    step(true);
+#pragma unroll 1
+    for (int i = 0; i < tail_sq; i++) step(false);
+    if (final_lines) {
+        step(true);
+        step(true);
+    }
 }
 
 // ---------------------------------------------------------------- final exponentiation (pairing.cuh's chain)
-// r = conj(a^x) for a in the cyclotomic subgroup; acc is a scratch value
-__device__ __noinline__ void f12_exp_neg_x(Fq2 *r, const Fq2 *a, Fq2 *acc, Scratch *s) {
-    f12_copy(acc, a);
+// r = conj(a^x) for a in the cyclotomic subgroup.  a^x = product of a^(2^t) over the set bits t of x: THIS warp only
+// squares (62 products) and hands every a^(2^t) with bit t set to a helper warp, which multiplies them up as they
+// appear (27 products, finished one product after the last squaring): 63 products of latency instead of 89.
+constexpr int kXBits = popcnt64(kBnX);               // 28
+struct ExpShare {
+    Fq2 *items;          // kXBits Fq12 values
+    Fq2 *prod;           // the helper's running product
+    int *count, *done;   // items published so far (all exponentiations of a proof), exponentiations finished
+};
+__device__ __noinline__ void f12_exp_neg_x(Fq2 *r, const Fq2 *a, Fq2 *q, Scratch *s, const ExpShare &sh, int gen) {
+    int j = 0;
 #pragma unroll 1
-    for (int i = 61; i >= 0; i--) {
-        f12_mul<false>(acc, acc, acc, s);
-        if ((kBnX >> i) & 1ull) f12_mul<false>(acc, acc, a, s);
+    for (int t = 0; t < 63; t++) {
+        if (t == 0) f12_copy(q, a);
+        else f12_mul<false>(q, q, q, s);
+        if ((kBnX >> t) & 1ull) {
+            f12_copy(sh.items + 6 * j, q);
+            j++;
+            flag_publish(sh.count, gen * kXBits + j);
+        }
     }
-    f12_conj(r, acc);
+    flag_wait(sh.done, gen + 1);
+    f12_conj(r, sh.prod);
 }
-// out = f^((p^12 - 1)/r * c) as final_exponentiation computes it; T: ten Fq12 slots of scratch (60 Fq2); out may be f
-__device__ __noinline__ void final_exp(Fq2 *out, const Fq2 *f, Fq2 *T, Scratch *s) {
+// the helper warp's side of exponentiation number `gen` of a proof
+__device__ __noinline__ void f12_exp_helper(Scratch *s, const ExpShare &sh, int gen) {
+    flag_wait(sh.count, gen * kXBits + 1);
+    f12_copy(sh.prod, sh.items);
+#pragma unroll 1
+    for (int j = 1; j < kXBits; j++) {
+        flag_wait(sh.count, gen * kXBits + j + 1);
+        f12_mul<false>(sh.prod, sh.prod, sh.items + 6 * j, s);
+    }
+    flag_publish(sh.done, gen + 1);
+}
+// out = f^((p^12 - 1)/r * c) as final_exponentiation computes it; T: ten Fq12 slots of scratch (60 Fq2); out may be f.
+// A helper warp must run f12_exp_helper(.., sh, 0 .. 2) beside it.
+__device__ __noinline__ void final_exp(Fq2 *out, const Fq2 *f, Fq2 *T, Scratch *s, const ExpShare &sh) {
     const int lane = lane_id();
     Fq2 *R = T + 6 * 8, *X = T + 6 * 9, *S0 = T, *S1 = T + 6, *S2 = T + 12, *S4 = T + 24, *S5 = T + 30, *S6 = T + 36, *S7 = T + 42;
     // easy part: r = conj(f) / f = conj(f)^2 / N with N = f conj(f) in Fq6
@@ -453,13 +496,13 @@ __device__ __noinline__ void final_exp(Fq2 *out, const Fq2 *f, Fq2 *T, Scratch *
     f12_frob<2>(S0, R);
     f12_mul<false>(R, S0, R, s);                        // ^(p^2 + 1)
     // hard part
-    f12_exp_neg_x(S0, R, S7, s);                        // y0
+    f12_exp_neg_x(S0, R, S7, s, sh, 0);                 // y0
     f12_mul<false>(S1, S0, S0, s);                      // y1 = y0^2
     f12_mul<false>(S2, S1, S1, s);                      // y2
     f12_mul<false>(S2, S2, S1, s);                      // y3
-    f12_exp_neg_x(S4, S2, S7, s);                       // y4
+    f12_exp_neg_x(S4, S2, S7, s, sh, 1);                // y4
     f12_mul<false>(S5, S4, S4, s);                      // y5
-    f12_exp_neg_x(S6, S5, S7, s);                       // y6
+    f12_exp_neg_x(S6, S5, S7, s, sh, 2);                // y6
     f12_conj(S2, S2);
     f12_conj(S6, S6);
     f12_mul<false>(S6, S6, S4, s);                      // y7

@@ -379,21 +379,24 @@ struct FChain {
 };
 struct CoopSmem {
     Fq2 lines[coop::kLines * 3];      // scaled lines of (A, B); afterwards the final exponentiation's ten Fq12 slots
-    FChain fc[3];
+    FChain fc[4];                     // (A, B) upper share / -gamma / -delta / (A, B) lower share, then the exponentiation helper
     coop::LineState ls;
     coop::LadderState lad;
     Fq2 ref[6];                       // self-test only
     G1Affine A, C;
     G2Affine B;
-    int ready, done[3], good[4], sub_ok;
+    int ready, done[4], good[4], sub_ok, xcount, xdone;
 };
-static_assert(coop::kLines * 3 >= 60, "final_exp slots");
-constexpr uint32_t kCoopThreads = 192;   // six warps: roles 0-3 on the four SM partitions, warp 4 idle, warp 5 beside warp 1
+static_assert(coop::kLines * 3 >= 60 + 6 * coop::kXBits, "final_exp slots and the exponentiation's shared powers");
+constexpr uint32_t kCoopThreads = 224;   // seven warps, one of them idle (CoopRole)
 
 __device__ __forceinline__ void coop_prologue(CoopSmem &sm) {
-    if (threadIdx.x == 0) { sm.ready = 0; sm.done[0] = sm.done[1] = sm.done[2] = 0; sm.sub_ok = 0; }
-    if (threadIdx.x < 3) st_vec(&sm.fc[threadIdx.x].s.P[18], Fq2::zero());
-    if (threadIdx.x < 36) st_vec(&sm.fc[threadIdx.x / 12].ln[threadIdx.x % 12], Fq2::zero());
+    if (threadIdx.x == 0) { sm.ready = 0; sm.done[0] = sm.done[1] = sm.done[2] = sm.done[3] = 0; sm.sub_ok = 0; sm.xcount = 0; sm.xdone = 0; }
+    if (threadIdx.x < 4) st_vec(&sm.fc[threadIdx.x].s.P[18], Fq2::zero());
+    if (threadIdx.x < 48) st_vec(&sm.fc[threadIdx.x / 12].ln[threadIdx.x % 12], Fq2::zero());
+}
+__device__ __forceinline__ coop::ExpShare exp_share(CoopSmem &sm) {
+    return coop::ExpShare{sm.lines + 60, sm.fc[3].f, &sm.xcount, &sm.xdone};
 }
 __device__ __forceinline__ void set_emb(FChain &c, const G1Affine &P) {
     if (coop::lane_id() == 0) {
@@ -404,10 +407,15 @@ __device__ __forceinline__ void set_emb(FChain &c, const G1Affine &P) {
     __syncwarp();
 }
 
-// ok[p] as k_verify4 decides it; one CTA per proof.
-//   warp 0: f chain of Miller(A, B), then the product of the three Miller values, final exponentiation, comparison
-//   warp 1: vk_x from the tables, Miller(vk_x, -gamma) on prepared lines      warp 2: Miller(C, -delta) likewise
-//   warp 3: twist-point chain of (A, B) -> scaled lines                       warp 5: B in the r-torsion subgroup?
+// ok[p] as k_verify4 decides it; one CTA per proof.  Roles by warp (warp w runs on SM partition w % 4; the two warps
+// that end the proof - role 0 and the exponentiation helper - have their partition to themselves by then):
+//   warp 0  AB_UPPER: upper share of the (A, B) f chain, product of the Miller values, final exponentiation (squaring side)
+//   warp 4  GAMMA:    vk_x from the tables, Miller(vk_x, -gamma) on prepared lines                   (beside warp 0)
+//   warp 1  LINES:    twist-point chain of (A, B) -> scaled lines in shared memory
+//   warp 2  AB_LOWER: lower share of the (A, B) f chain, then the multiplying side of the three exponentiations by x
+//   warp 6  DELTA:    Miller(C, -delta) on prepared lines                                            (beside warp 2)
+//   warp 3  LADDER:   B in the r-torsion subgroup?                                                    warp 5: idle
+enum CoopRole { kAbUpper = 0, kLines = 1, kAbLower = 2, kLadder = 3, kGamma = 4, kIdle = 5, kDelta = 6 };
 __global__ void __launch_bounds__(kCoopThreads) k_verify_coop(const VkDev *__restrict__ vk, const G1Affine *__restrict__ gamma_abc,
                                                               const G1Affine *__restrict__ tab, const Fq2 *__restrict__ lines_gamma,
                                                               const Fq2 *__restrict__ lines_delta, uint32_t n_pub,
@@ -419,10 +427,10 @@ __global__ void __launch_bounds__(kCoopThreads) k_verify_coop(const VkDev *__res
     const uint8_t *pb = proofs + (size_t)p * 256;
     const uint8_t *x = inputs + (size_t)p * n_pub * 32;
     coop_prologue(sm);
-    if (warp == 0 && lane == 0) { G1Affine A; sm.good[0] = read_g1_checked(pb, A) ? 1 : 0; st_vec(&sm.A, A); }
-    if (warp == 3 && lane == 0) { G2Affine B; sm.good[1] = read_g2_on_curve(pb + 64, B) ? 1 : 0; st_vec(&sm.B, B); }
-    if (warp == 2 && lane == 0) { G1Affine C; sm.good[2] = read_g1_checked(pb + 192, C) ? 1 : 0; st_vec(&sm.C, C); }
-    if (warp == 1) {
+    if (warp == kAbUpper && lane == 0) { G1Affine A; sm.good[0] = read_g1_checked(pb, A) ? 1 : 0; st_vec(&sm.A, A); }
+    if (warp == kLines && lane == 0) { G2Affine B; sm.good[1] = read_g2_on_curve(pb + 64, B) ? 1 : 0; st_vec(&sm.B, B); }
+    if (warp == kDelta && lane == 0) { G1Affine C; sm.good[2] = read_g1_checked(pb + 192, C) ? 1 : 0; st_vec(&sm.C, C); }
+    if (warp == kGamma) {
         bool g = true;
         for (uint32_t i = lane; i < n_pub; i += 32) g = fr_is_canonical(ld_vec(reinterpret_cast<const Fr *>(x) + i)) && g;
         g = __all_sync(0xffffffffu, g);
@@ -433,20 +441,22 @@ __global__ void __launch_bounds__(kCoopThreads) k_verify_coop(const VkDev *__res
     const G1Affine A = ld_vec(&sm.A);
     const G2Affine B = ld_vec(&sm.B);
     const bool skip_ab = !(sm.good[0] && sm.good[1]) || A.is_inf() || B.is_inf();
-    if (warp == 0) {
+    if (warp == kAbUpper) {
         if (!all_good) { if (lane == 0) ok[p] = 0; return; }
         FChain &c = sm.fc[0];
         if (skip_ab) coop::f12_set_one(c.f);
-        else coop::miller_f<true>(c.f, sm.lines, &sm.ready, c.ln, nullptr, &c.s);
+        else coop::miller_f<true>(c.f, sm.lines, &sm.ready, c.ln, nullptr, &c.s, 63, coop::kMillerSplit, coop::kMillerSplit, false);
         coop::flag_wait(&sm.done[0], 1);
         coop::f12_mul<false>(c.f, c.f, sm.fc[1].f, &c.s);
         coop::flag_wait(&sm.done[1], 1);
         coop::f12_mul<false>(c.f, c.f, sm.fc[2].f, &c.s);
-        coop::final_exp(c.f, c.f, sm.lines, &c.s);
+        coop::flag_wait(&sm.done[3], 1);                                  // the lower share of the (A, B) loop; its warp has left the lines
+        coop::f12_mul<false>(c.f, c.f, sm.fc[3].f, &c.s);
+        coop::final_exp(c.f, c.f, sm.lines, &c.s, exp_share(sm));
         const bool eq = coop::f12_equal(c.f, reinterpret_cast<const Fq2 *>(&vk->alpha_beta));
         coop::flag_wait(&sm.done[2], 1);
         if (lane == 0) ok[p] = (eq && sm.sub_ok) ? 1 : 0;
-    } else if (warp == 1) {
+    } else if (warp == kGamma) {
         FChain &c = sm.fc[1];
         bool skip = true;
         if (all_good) {
@@ -457,7 +467,7 @@ __global__ void __launch_bounds__(kCoopThreads) k_verify_coop(const VkDev *__res
         if (skip) coop::f12_set_one(c.f);
         else coop::miller_f<false>(c.f, lines_gamma, nullptr, c.ln, c.emb, &c.s);
         coop::flag_publish(&sm.done[0], 1);
-    } else if (warp == 2) {
+    } else if (warp == kDelta) {
         FChain &c = sm.fc[2];
         const G1Affine C = ld_vec(&sm.C);
         const bool skip = !all_good || C.is_inf() || vk->delta_neg.is_inf();
@@ -465,9 +475,17 @@ __global__ void __launch_bounds__(kCoopThreads) k_verify_coop(const VkDev *__res
         if (skip) coop::f12_set_one(c.f);
         else coop::miller_f<false>(c.f, lines_delta, nullptr, c.ln, c.emb, &c.s);
         coop::flag_publish(&sm.done[1], 1);
-    } else if (warp == 3) {
+    } else if (warp == kLines) {
         if (all_good && !skip_ab) coop::line_chain(&sm.ls, A, B, sm.lines, &sm.ready);
-    } else if (warp == 5) {
+    } else if (warp == kAbLower) {
+        if (!all_good) return;
+        FChain &c = sm.fc[3];
+        if (skip_ab) coop::f12_set_one(c.f);
+        else coop::miller_f<true>(c.f, sm.lines, &sm.ready, c.ln, nullptr, &c.s, coop::kMillerSplit - 1, 0, 0, true);
+        coop::flag_publish(&sm.done[3], 1);
+        const coop::ExpShare sh = exp_share(sm);
+        for (int g = 0; g < 3; g++) coop::f12_exp_helper(&c.s, sh, g);
+    } else if (warp == kLadder) {
         bool in = false;
         if (all_good) in = B.is_inf() ? true : coop::g2_in_subgroup(&sm.lad, B);
         if (lane == 0) sm.sub_ok = in ? 1 : 0;
@@ -488,8 +506,8 @@ __global__ void __launch_bounds__(kCoopThreads) k_coop_selftest(const VkDev *__r
     const long long t_start = clock64();
     auto stamp = [&](int k) { if (lane == 0) stamps[k] = clock64() - t_start; };
     if (solo) {              // timing only: the (A, B) Miller loop's two warps with nothing beside them (solo = 2: line chain alone first)
-        if (warp == 3) { coop::line_chain(&sm.ls, A, B, sm.lines, &sm.ready); stamp(11); }
-        if (warp == 0) {
+        if (warp == kLines) { coop::line_chain(&sm.ls, A, B, sm.lines, &sm.ready); stamp(11); }
+        if (warp == kAbUpper) {
             if (solo == 2) coop::flag_wait(&sm.ready, coop::kLines);
             const long long t0 = clock64();
             coop::miller_f<true>(sm.fc[0].f, sm.lines, &sm.ready, sm.fc[0].ln, nullptr, &sm.fc[0].s);
@@ -497,11 +515,13 @@ __global__ void __launch_bounds__(kCoopThreads) k_coop_selftest(const VkDev *__r
         }
         return;
     }
-    if (warp == 0) {
+    if (warp == kAbUpper) {
         FChain &c = sm.fc[0];
-        coop::miller_f<true>(c.f, sm.lines, &sm.ready, c.ln, nullptr, &c.s);
+        coop::miller_f<true>(c.f, sm.lines, &sm.ready, c.ln, nullptr, &c.s, 63, coop::kMillerSplit, coop::kMillerSplit, false);
+        coop::flag_wait(&sm.done[3], 1);
+        coop::f12_mul<false>(c.f, c.f, sm.fc[3].f, &c.s);
         stamp(0);
-        {   // timing only: the same f chain again with every line already there, and 64 plain products
+        {   // timing only: the whole f chain on one warp with every line already there, and 64 plain products
             const long long t0 = clock64();
             coop::miller_f<true>(c.ln, sm.lines, &sm.ready, c.ln + 6, nullptr, &c.s);
             if (lane == 0) stamps[5] = clock64() - t0;
@@ -523,11 +543,19 @@ __global__ void __launch_bounds__(kCoopThreads) k_coop_selftest(const VkDev *__r
         }
         coop::flag_wait(&sm.done[0], 1);
         if (!coop::f12_equal(c.f, sm.fc[1].f) && lane == 0) atomicOr(result, 1);
+        coop::flag_publish(&sm.done[2], 1);                              // the lines may now be overwritten: warp 4 turns helper
         const long long t2 = clock64();
-        coop::final_exp(c.f, c.f, sm.lines, &c.s);
+        coop::final_exp(c.f, c.f, sm.lines, &c.s, exp_share(sm));
         if (lane == 0) stamps[1] = clock64() - t2;
         if (!coop::f12_equal(c.f, reinterpret_cast<const Fq2 *>(&vk->alpha_beta)) && lane == 0) atomicOr(result, 2);
-    } else if (warp == 1) {
+    } else if (warp == kAbLower) {
+        FChain &c = sm.fc[3];
+        coop::miller_f<true>(c.f, sm.lines, &sm.ready, c.ln, nullptr, &c.s, coop::kMillerSplit - 1, 0, 0, true);
+        coop::flag_publish(&sm.done[3], 1);
+        coop::flag_wait(&sm.done[2], 1);
+        const coop::ExpShare sh = exp_share(sm);
+        for (int g = 0; g < 3; g++) coop::f12_exp_helper(&c.s, sh, g);
+    } else if (warp == kGamma) {
         if (lane == 0) {
             G1Affine P[1] = {A};
             G2Affine Q[1] = {B};
@@ -537,17 +565,17 @@ __global__ void __launch_bounds__(kCoopThreads) k_coop_selftest(const VkDev *__r
             *reinterpret_cast<Fq12 *>(sm.fc[1].f) = f;
         }
         coop::flag_publish(&sm.done[0], 1);
-    } else if (warp == 2) {
+    } else if (warp == kDelta) {
         FChain &c = sm.fc[2];
         set_emb(c, A);
         coop::miller_f<false>(c.f, lines_gamma, nullptr, c.ln, c.emb, &c.s);
         stamp(2);
         coop::flag_wait(&sm.done[1], 1);
         if (!coop::f12_equal(c.f, sm.ref) && lane == 0) atomicOr(result, 4);
-    } else if (warp == 3) {
+    } else if (warp == kLines) {
         coop::line_chain(&sm.ls, A, B, sm.lines, &sm.ready);
         stamp(3);
-    } else if (warp == 5) {
+    } else if (warp == kLadder) {
         if (lane == 0) {
             G1Affine P[1] = {A};
             G2Affine Q[1] = {vk->gamma_neg};
