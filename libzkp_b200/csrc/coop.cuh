@@ -29,8 +29,7 @@ LZ_HD constexpr int popcnt64(uint64_t v) {
     for (int i = 0; i < 64; i++) c += (int)((v >> i) & 1ull);
     return c;
 }
-constexpr uint64_t kAteLo = 0x9d797039be763ba8ull;            // bits 0..63 of 6x + 2 (bit 64 is the leading one)
-constexpr int kLines = 64 + popcnt64(kAteLo) + 2;             // doublings + additions + the two Frobenius additions
+constexpr int kLines = (kAteTop + 1) + popcnt64(kAteNafNz) + 2;   // doublings + additions (NAF digits of 6x + 2) + the two Frobenius additions
 constexpr uint32_t kTabDigits = 255, kTabWindows = 32;        // byte windows of a canonical 32-byte scalar
 
 __device__ __forceinline__ int lane_id() { return (int)(threadIdx.x & 31u); }
@@ -209,10 +208,10 @@ __device__ __forceinline__ void flag_wait(const int *flag, int at_least) {
 }
 
 // ---------------------------------------------------------------- the twist-point chain of one Miller loop
-// Walks R over the bits of 6x + 2 exactly as multi_miller_loop does and writes, per step, the line already scaled
+// Walks R over the NAF digits of 6x + 2 exactly as multi_miller_loop does and writes, per step, the line already scaled
 // by the G1 point: (c0 * yP, c1 * xP, c2).  One product per lane and round; `*ready` counts finished lines.
 struct LineState {
-    Fq2 Rx, Ry, Rz, Qx, Qy, Q1x, Q1y, Q2x, Q2y;
+    Fq2 Rx, Ry, Rz, Qx, Qy, Qny, Q1x, Q1y, Q2x, Q2y;      // Qny = -Qy (negative NAF digits add -Q)
     Fq2 ey, ex;                       // (yP, 0), (xP, 0)
     Fq2 t[11];
 };
@@ -343,7 +342,7 @@ __device__ __noinline__ void line_chain(LineState *st, const G1Affine &P, const 
     const int lane = lane_id();
     if (lane == 0) {
         stq(&st->Rx, Q.x); stq(&st->Ry, Q.y); stq(&st->Rz, Fq2::one());
-        stq(&st->Qx, Q.x); stq(&st->Qy, Q.y);
+        stq(&st->Qx, Q.x); stq(&st->Qy, Q.y); stq(&st->Qny, Q.y.neg());
         stq(&st->ey, fq2_embed(P.y)); stq(&st->ex, fq2_embed(P.x));
     }
     __syncwarp();
@@ -365,11 +364,12 @@ __device__ __noinline__ void line_chain(LineState *st, const G1Affine &P, const 
     });
     int n = 0;
 #pragma unroll 1
-    for (int i = 63; i >= 0; i--) {
+    for (int i = kAteTop; i >= 0; i--) {
         line_dbl(st, lines + 3 * n);
         flag_publish(ready, ++n);
-        if ((kAteLo >> i) & 1ull) {
-            line_add(st, &st->Qx, &st->Qy, lines + 3 * n);
+        const int d = ate_digit(i);
+        if (d) {
+            line_add(st, &st->Qx, d > 0 ? &st->Qy : &st->Qny, lines + 3 * n);
             flag_publish(ready, ++n);
         }
     }
@@ -387,17 +387,17 @@ __device__ __noinline__ void line_chain(LineState *st, const G1Affine &P, const 
 // products - a second (sparse) instantiation doubles the instruction footprint of a loop that runs on a lone warp.
 // The loop runs the iterations i_hi .. i_lo of the bits of 6x + 2 starting from f = 1, then `tail_sq` bare squarings,
 // then (final_lines) the two Frobenius lines.  The value of the whole loop factors as
-//     f = (loop over 63 .. m, then m squarings) * (loop over m-1 .. 0 and the final lines, started from 1),
-// so two warps can each run a share of the (A, B) loop (kMillerSplit): 102 + 104 products side by side instead of 166.
-constexpr int kMillerSplit = 40;
+//     f = (loop over 64 .. m, then m squarings) * (loop over m-1 .. 0 and the final lines, started from 1),
+// so two warps can each run a share of the (A, B) loop (kMillerSplit): 97 + 97 products side by side instead of 152.
+constexpr int kMillerSplit = 41;
 LZ_HD constexpr int lines_before(int i_hi) {          // lines consumed by the iterations 63 .. i_hi + 1
     int c = 0;
-    for (int i = 63; i > i_hi; i--) c += 1 + (int)((kAteLo >> i) & 1ull);
+    for (int i = kAteTop; i > i_hi; i--) c += 1 + (ate_digit(i) != 0 ? 1 : 0);
     return c;
 }
 template <bool SCALED>
 __device__ __noinline__ void miller_f(Fq2 *f, const Fq2 *lines, const int *ready, Fq2 *ln, const Fq2 *emb, Scratch *s,
-                                      int i_hi = 63, int i_lo = 0, int tail_sq = 0, bool final_lines = true) {
+                                      int i_hi = kAteTop, int i_lo = 0, int tail_sq = 0, bool final_lines = true) {
     const int lane = lane_id();
     f12_set_one(f);
     int c = lines_before(i_hi), scaled = c;
@@ -432,7 +432,7 @@ __device__ __noinline__ void miller_f(Fq2 *f, const Fq2 *lines, const int *ready
     for (int i = i_hi; i >= i_lo; i--) {
         if (i != i_hi || !SCALED) step(false);      // f = 1 before the first iteration (prepared lines: the squaring of 1 carries the first scaling)
         step(true);
-        if ((kAteLo >> i) & 1ull) step(true);
+        if (ate_digit(i)) step(true);
     }
 #pragma unroll 1
     for (int i = 0; i < tail_sq; i++) step(false);

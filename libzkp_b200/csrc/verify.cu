@@ -346,9 +346,10 @@ __global__ void k_prepare_lines(const VkDev *vk, Fq2 *lines_gamma, Fq2 *lines_de
     int n = 0;
     auto put = [&]() { out[3 * n] = L.c0; out[3 * n + 1] = L.c1; out[3 * n + 2] = L.c2; n++; };
 #pragma unroll 1
-    for (int i = 63; i >= 0; i--) {
+    for (int i = kAteTop; i >= 0; i--) {
         pairing_dbl_step(R, L); put();
-        if (ate_bit(i)) { pairing_add_step(R, Q, L); put(); }
+        const int d = ate_digit(i);
+        if (d) { pairing_add_step(R, d > 0 ? Q : Q.neg(), L); put(); }
     }
     Fq2 twx{PairingConsts::TW_X_C0(), PairingConsts::TW_X_C1()}, twy{PairingConsts::TW_Y_C0(), PairingConsts::TW_Y_C1()};
     G2Affine q1{fq2_conj(Q.x) * twx, fq2_conj(Q.y) * twy};
@@ -445,7 +446,7 @@ __global__ void __launch_bounds__(kCoopThreads) k_verify_coop(const VkDev *__res
         if (!all_good) { if (lane == 0) ok[p] = 0; return; }
         FChain &c = sm.fc[0];
         if (skip_ab) coop::f12_set_one(c.f);
-        else coop::miller_f<true>(c.f, sm.lines, &sm.ready, c.ln, nullptr, &c.s, 63, coop::kMillerSplit, coop::kMillerSplit, false);
+        else coop::miller_f<true>(c.f, sm.lines, &sm.ready, c.ln, nullptr, &c.s, kAteTop, coop::kMillerSplit, coop::kMillerSplit, false);
         coop::flag_wait(&sm.done[0], 1);
         coop::f12_mul<false>(c.f, c.f, sm.fc[1].f, &c.s);
         coop::flag_wait(&sm.done[1], 1);
@@ -517,7 +518,7 @@ __global__ void __launch_bounds__(kCoopThreads) k_coop_selftest(const VkDev *__r
     }
     if (warp == kAbUpper) {
         FChain &c = sm.fc[0];
-        coop::miller_f<true>(c.f, sm.lines, &sm.ready, c.ln, nullptr, &c.s, 63, coop::kMillerSplit, coop::kMillerSplit, false);
+        coop::miller_f<true>(c.f, sm.lines, &sm.ready, c.ln, nullptr, &c.s, kAteTop, coop::kMillerSplit, coop::kMillerSplit, false);
         coop::flag_wait(&sm.done[3], 1);
         coop::f12_mul<false>(c.f, c.f, sm.fc[3].f, &c.s);
         stamp(0);
