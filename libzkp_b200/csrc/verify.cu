@@ -335,11 +335,12 @@ __global__ void __launch_bounds__(128) k_rlc_tail(const VkDev *__restrict__ vk, 
 
 // ---------------------------------------------------------------- latency form: one proof per CTA (coop.cuh)
 // Line coefficients of the Miller loops against the key's fixed G2 points -gamma and -delta, in the order
-// multi_miller_loop consumes them (what ark-groth16's PreparedVerifyingKey stores).  Thread 0: gamma, thread 1: delta.
-__global__ void k_prepare_lines(const VkDev *vk, Fq2 *lines_gamma, Fq2 *lines_delta) {
-    if (threadIdx.x > 1) return;
-    const G2Affine Q = threadIdx.x == 0 ? vk->gamma_neg : vk->delta_neg;
-    Fq2 *out = threadIdx.x == 0 ? lines_gamma : lines_delta;
+// multi_miller_loop consumes them (what ark-groth16's PreparedVerifyingKey stores).  Thread 0: -gamma, thread 1: -delta,
+// thread 2: beta (the combined check of the random-linear-combination path pairs -(sum rho) alpha with it).
+__global__ void k_prepare_lines(const VkDev *vk, Fq2 *lines_gamma, Fq2 *lines_delta, Fq2 *lines_beta) {
+    if (threadIdx.x > 2) return;
+    const G2Affine Q = threadIdx.x == 0 ? vk->gamma_neg : threadIdx.x == 1 ? vk->delta_neg : vk->beta;
+    Fq2 *out = threadIdx.x == 0 ? lines_gamma : threadIdx.x == 1 ? lines_delta : lines_beta;
     if (Q.is_inf()) return;
     G2Proj R{Q.x, Q.y, Fq2::one()};
     LineCoeffs L;
@@ -494,6 +495,123 @@ __global__ void __launch_bounds__(kCoopThreads) k_verify_coop(const VkDev *__res
     }
 }
 
+// ---- the combined check of a GROUP, cooperative form (the lane-per-group k_rlc_reduce + k_rlc_tail put a whole pairing
+// and 63 Fq12 products on one thread: 14.7 of the 70 ms of kernel time at 65 536 proofs).  One CTA per group:
+//   warp 0: Miller(-(sum rho) alpha, beta) on prepared lines, product of everything, final exponentiation (squaring side)
+//   warp 1: sum_j X[g][j] (shuffle tree), Miller(., -gamma)      warp 2: sum_p rho_p C_p (shuffle tree), Miller(., -delta)
+//   warp 3: the product of the group's 64 Miller values f_p, then the multiplying side of the exponentiations by x
+// gX holds n_pub + 2 columns per group: the public-input shares and, last, (sum rho) alpha (k_rlc_inputs).
+struct TailSmem {
+    Fq2 slots[60 + 6 * coop::kXBits];
+    FChain fc[4];
+    int done[3], xcount, xdone;
+};
+__device__ __noinline__ G1Affine coop_sum_g1(const G1XYZZ *src, uint32_t count) {     // whole warp; result on every lane
+    const int lane = coop::lane_id();
+    G1XYZZ acc = G1XYZZ::inf();
+#pragma unroll 1
+    for (uint32_t i = lane; i < count; i += 32) acc.add_cold(ld_vec(src + i));
+#pragma unroll 1
+    for (int off = 16; off > 0; off >>= 1) {
+        G1XYZZ o;
+        uint32_t *ow = reinterpret_cast<uint32_t *>(&o);
+        const uint32_t *aw = reinterpret_cast<const uint32_t *>(&acc);
+#pragma unroll
+        for (int k = 0; k < (int)(sizeof(G1XYZZ) / 4); k++) ow[k] = __shfl_down_sync(0xffffffffu, aw[k], off);
+        acc.add_cold(o);
+    }
+    G1Affine r = G1Affine::inf();
+    if (lane == 0) r = acc.to_affine();
+    uint32_t *rw = reinterpret_cast<uint32_t *>(&r);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(G1Affine) / 4); k++) rw[k] = __shfl_sync(0xffffffffu, rw[k], 0);
+    return r;
+}
+__global__ void __launch_bounds__(128) k_rlc_tail_coop(const VkDev *__restrict__ vk, const Fq2 *__restrict__ lines_gamma,
+                                                       const Fq2 *__restrict__ lines_delta, const Fq2 *__restrict__ lines_beta,
+                                                       const Fq12 *__restrict__ f_in, const G1XYZZ *__restrict__ rc_in,
+                                                       const G1XYZZ *__restrict__ gX, uint32_t n, uint32_t n_pub,
+                                                       uint8_t *__restrict__ group_ok) {
+    extern __shared__ uint4 smem_raw[];
+    TailSmem &sm = *reinterpret_cast<TailSmem *>(smem_raw);
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = blockIdx.x;
+    const uint32_t lo = g * kRlcGroup, hi = min(n, lo + kRlcGroup), cols = n_pub + 2;
+    if (threadIdx.x == 0) { sm.done[0] = sm.done[1] = sm.done[2] = 0; sm.xcount = 0; sm.xdone = 0; }
+    if (threadIdx.x < 4) st_vec(&sm.fc[threadIdx.x].s.P[18], Fq2::zero());
+    if (threadIdx.x < 48) st_vec(&sm.fc[threadIdx.x / 12].ln[threadIdx.x % 12], Fq2::zero());
+    __syncthreads();
+    const coop::ExpShare sh{sm.slots + 60, sm.fc[3].f, &sm.xcount, &sm.xdone};
+    FChain &c = sm.fc[warp];
+    if (warp == 3) {
+        // the group's Miller values: f[0] * f[1] * ... (a malformed proof contributed 1)
+        for (uint32_t k = lane; k < 6; k += 32) st_vec(&c.f[k], ld_vec(reinterpret_cast<const Fq2 *>(f_in + lo) + k));
+        __syncwarp();
+#pragma unroll 1
+        for (uint32_t p = lo + 1; p < hi; p++) {
+            for (uint32_t k = lane; k < 6; k += 32) st_vec(&c.ln[k], ld_vec(reinterpret_cast<const Fq2 *>(f_in + p) + k));
+            __syncwarp();
+            coop::f12_mul<false>(c.f, c.f, c.ln, &c.s);
+        }
+        // hand the product to warp 0 in fc[3].ln (fc[3].f becomes the exponentiation helper's running product)
+        coop::f12_copy(c.ln + 6, c.f);
+        coop::flag_publish(&sm.done[2], 1);
+        for (int e = 0; e < 3; e++) coop::f12_exp_helper(&c.s, sh, e);
+        return;
+    }
+    G1Affine P;
+    const Fq2 *lines;
+    bool skip;
+    if (warp == 0) {
+        P = ld_vec(gX + (size_t)g * cols + n_pub + 1).to_affine().neg();
+        lines = lines_beta;
+        skip = P.is_inf() || vk->beta.is_inf();
+    } else if (warp == 1) {
+        P = coop_sum_g1(gX + (size_t)g * cols, n_pub + 1);
+        lines = lines_gamma;
+        skip = P.is_inf() || vk->gamma_neg.is_inf();
+    } else {
+        P = coop_sum_g1(rc_in + lo, hi - lo);
+        lines = lines_delta;
+        skip = P.is_inf() || vk->delta_neg.is_inf();
+    }
+    if (skip) coop::f12_set_one(c.f);
+    else { set_emb(c, P); coop::miller_f<false>(c.f, lines, nullptr, c.ln, c.emb, &c.s); }
+    if (warp) { coop::flag_publish(&sm.done[warp - 1], 1); return; }
+    coop::flag_wait(&sm.done[0], 1);
+    coop::f12_mul<false>(c.f, c.f, sm.fc[1].f, &c.s);
+    coop::flag_wait(&sm.done[1], 1);
+    coop::f12_mul<false>(c.f, c.f, sm.fc[2].f, &c.s);
+    coop::flag_wait(&sm.done[2], 1);
+    coop::f12_mul<false>(c.f, c.f, sm.fc[3].ln + 6, &c.s);
+    coop::final_exp(c.f, c.f, sm.slots, &c.s, sh);
+    coop::f12_set_one(c.ln);                    // c.ln is free again (the loop's dense line operand)
+    const bool eq = coop::f12_equal(c.f, c.ln);
+    if (lane == 0) group_ok[g] = eq ? 1 : 0;
+}
+// gS[g][j] = sum over the group's CTAs of the scalar sums of k_rlc_prepare (what k_rlc_reduce does beside its products)
+__global__ void __launch_bounds__(128) k_rlc_scalars(const Fr *__restrict__ sx_in, uint32_t n, uint32_t n_pub, uint32_t groups,
+                                                     Fr *__restrict__ gS) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= groups * (n_pub + 1)) return;
+    const uint32_t g = t / (n_pub + 1), j = t % (n_pub + 1);
+    const uint32_t lo = g * kRlcGroup, hi = min(n, lo + kRlcGroup), cta_lo = lo / 32, cta_hi = (hi + 31) / 32;
+    Fr sum = Fr::zero();
+    for (uint32_t b = cta_lo; b < cta_hi; b++) sum = sum + ld_vec(sx_in + (size_t)b * (n_pub + 1) + j);
+    st_vec(gS + t, sum);
+}
+// X[g][j] = S[g][j] * gamma_abc[j] for j <= n_pub, and the extra column X[g][n_pub + 1] = S[g][0] * alpha
+__global__ void __launch_bounds__(64) k_rlc_inputs2(const VkDev *__restrict__ vk, const Fr *__restrict__ gS, const G1Affine *__restrict__ gamma_abc,
+                                                    uint32_t n_pub, uint32_t groups, G1XYZZ *__restrict__ gX) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, cols = n_pub + 2;
+    if (t >= groups * cols) return;
+    const uint32_t g = t / cols, j = t % cols;
+    const Fr s = ld_vec(gS + (size_t)g * (n_pub + 1) + (j <= n_pub ? j : 0));
+    const G1Affine base = j <= n_pub ? ldg_vec(gamma_abc + j) : vk->alpha;
+    G1XYZZ r = G1XYZZ::inf();
+    if (!s.is_zero() && !base.is_inf()) r = scalar_mul(G1XYZZ::from_affine(base), s);
+    st_vec(gX + t, r);
+}
+
 // LZKP_COOP_SELFTEST=1 at key load: the cooperative Miller loop (both line sources), final exponentiation and subgroup
 // test against the serial code of pairing.cuh on the key's own points.  result: bit per failing stage.
 __global__ void __launch_bounds__(kCoopThreads) k_coop_selftest(const VkDev *__restrict__ vk, const Fq2 *__restrict__ lines_gamma, int *result, long long *stamps, int solo) {
@@ -606,7 +724,7 @@ struct VerifyingKeyDev {
     DBuf vk, gamma_abc;
     DBuf d_p, d_x, d_ok;          // grow-only staging of a batch (calls on one key serialize on mu)
     DBuf d_rho, d_f, d_rc, d_sx, d_gF, d_gC, d_gS, d_gX, d_gok;     // random-linear-combination path (large batches)
-    DBuf lines_gamma, lines_delta, tab;                             // latency form (coop.cuh): prepared lines, vk_x byte-window tables
+    DBuf lines_gamma, lines_delta, lines_beta, tab;                             // latency form (coop.cuh): prepared lines, vk_x byte-window tables
     bool coop_ok = false;
     uint32_t n_pub = 0;
     std::mutex mu;
@@ -618,9 +736,10 @@ constexpr uint32_t kCoopMaxInputs = 256;
 static int coop_prepare(VerifyingKeyDev *V) {
     if (V->n_pub > kCoopMaxInputs) return LZKP_OK;
     const size_t line_bytes = (size_t)coop::kLines * 3 * sizeof(Fq2);
-    TRY(V->lines_gamma.alloc(line_bytes)); TRY(V->lines_delta.alloc(line_bytes));
+    TRY(V->lines_gamma.alloc(line_bytes)); TRY(V->lines_delta.alloc(line_bytes)); TRY(V->lines_beta.alloc(line_bytes));
     CUDA_TRY(cudaMemset(V->lines_gamma.p, 0, line_bytes)); CUDA_TRY(cudaMemset(V->lines_delta.p, 0, line_bytes));
-    LAUNCH(k_prepare_lines, 1, 32, 0, 0, V->vk.as<VkDev>(), V->lines_gamma.as<Fq2>(), V->lines_delta.as<Fq2>());
+    CUDA_TRY(cudaMemset(V->lines_beta.p, 0, line_bytes));
+    LAUNCH(k_prepare_lines, 1, 32, 0, 0, V->vk.as<VkDev>(), V->lines_gamma.as<Fq2>(), V->lines_delta.as<Fq2>(), V->lines_beta.as<Fq2>());
     if (V->n_pub) {
         const uint32_t threads = V->n_pub * coop::kTabWindows;
         TRY(V->tab.alloc((size_t)threads * coop::kTabDigits * sizeof(G1Affine)));
@@ -770,7 +889,7 @@ int verify_batch(VerifyingKeyDev *V, size_t n, const uint8_t *proofs, const uint
     TRY(V->d_rho.ensure(n * 16)); TRY(V->d_f.ensure(n * sizeof(Fq12))); TRY(V->d_rc.ensure(n * sizeof(G1XYZZ)));
     TRY(V->d_sx.ensure((size_t)ctas * np1 * sizeof(Fr)));
     TRY(V->d_gF.ensure((size_t)groups * sizeof(Fq12))); TRY(V->d_gC.ensure((size_t)groups * sizeof(G1XYZZ)));
-    TRY(V->d_gS.ensure((size_t)groups * np1 * sizeof(Fr))); TRY(V->d_gX.ensure((size_t)groups * np1 * sizeof(G1XYZZ)));
+    TRY(V->d_gS.ensure((size_t)groups * np1 * sizeof(Fr))); TRY(V->d_gX.ensure((size_t)groups * (np1 + 1) * sizeof(G1XYZZ)));
     TRY(V->d_gok.ensure(groups));
     CUDA_TRY(cudaMemcpy(V->d_rho.p, rho.data(), n * 16, cudaMemcpyHostToDevice));
     // One launch per stage for the whole batch.  (Measured: cutting the batch into 16 384-proof chunks so that a chunk's
@@ -779,12 +898,22 @@ int verify_batch(VerifyingKeyDev *V, size_t n, const uint8_t *proofs, const uint
     // than one 2048-CTA launch.)
     LAUNCH(k_rlc_prepare, ctas, 128, 0, 0, V->vk.as<VkDev>(), (uint32_t)n_pub, d_p.as<uint8_t>(), d_x.as<Fr>(), V->d_rho.as<uint32_t>(),
            (uint32_t)n, V->d_f.as<Fq12>(), V->d_rc.as<G1XYZZ>(), V->d_sx.as<Fr>(), d_ok.as<uint8_t>());
+    static const bool tail_lanes = getenv("LZKP_RLC_TAIL_LANES") != nullptr;      // A/B switch: the lane-per-group tail
+    if (V->coop_ok && !tail_lanes) {
+        LAUNCH(k_rlc_scalars, (groups * np1 + 127) / 128, 128, 0, 0, V->d_sx.as<Fr>(), (uint32_t)n, (uint32_t)n_pub, groups, V->d_gS.as<Fr>());
+        LAUNCH(k_rlc_inputs2, (groups * (np1 + 1) + 63) / 64, 64, 0, 0, V->vk.as<VkDev>(), V->d_gS.as<Fr>(), V->gamma_abc.as<G1Affine>(),
+               (uint32_t)n_pub, groups, V->d_gX.as<G1XYZZ>());
+        LAUNCH(k_rlc_tail_coop, groups, 128, sizeof(TailSmem), 0, V->vk.as<VkDev>(), V->lines_gamma.as<Fq2>(), V->lines_delta.as<Fq2>(),
+               V->lines_beta.as<Fq2>(), V->d_f.as<Fq12>(), V->d_rc.as<G1XYZZ>(), V->d_gX.as<G1XYZZ>(), (uint32_t)n, (uint32_t)n_pub,
+               V->d_gok.as<uint8_t>());
+    } else {
     LAUNCH(k_rlc_reduce, (groups + 63) / 64, 64, 0, 0, V->d_f.as<Fq12>(), V->d_rc.as<G1XYZZ>(), V->d_sx.as<Fr>(), (uint32_t)n,
            (uint32_t)n_pub, groups, V->d_gF.as<Fq12>(), V->d_gC.as<G1XYZZ>(), V->d_gS.as<Fr>());
     LAUNCH(k_rlc_inputs, (groups * np1 + 63) / 64, 64, 0, 0, V->d_gS.as<Fr>(), V->gamma_abc.as<G1Affine>(), (uint32_t)n_pub, groups,
            V->d_gX.as<G1XYZZ>());
     LAUNCH(k_rlc_tail, (groups + 31) / 32, 128, 96 * sizeof(Fq12), 0, V->vk.as<VkDev>(), V->d_gF.as<Fq12>(), V->d_gC.as<G1XYZZ>(),
            V->d_gS.as<Fr>(), V->d_gX.as<G1XYZZ>(), (uint32_t)n_pub, groups, V->d_gok.as<uint8_t>());
+    }
     std::vector<uint8_t> gok(groups);
     CUDA_TRY(cudaMemcpy(gok.data(), V->d_gok.p, groups, cudaMemcpyDeviceToHost));
     // groups whose combined check failed hold at least one false proof: decide those proofs one by one
