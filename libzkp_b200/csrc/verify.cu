@@ -854,10 +854,12 @@ int verify_batch(VerifyingKeyDev *V, size_t n, const uint8_t *proofs, const uint
         LAUNCH(k_verify4, (unsigned)((cnt + 31) / 32), 128, 64 * sizeof(Fq12), 0, V->vk.as<VkDev>(), V->gamma_abc.as<G1Affine>(),
                (uint32_t)n_pub, d_p.as<uint8_t>() + off * 256, d_x.as<Fr>() + off * n_pub, (uint32_t)cnt, d_ok.as<uint8_t>() + off);
     };
-    // Large batches saturate the GPU (426 k verifies/s from ~16 k proofs on): there the work per proof decides, and the
-    // random-linear-combination form needs 2.4x less of it.  Below, a call is latency-bound by ONE proof's chain and
-    // the combined check's tail (a whole pairing per group) would only add to it.
-    const size_t rlc_min = getenv("LZKP_VERIFY_RLC_MIN") ? (size_t)atoll(getenv("LZKP_VERIFY_RLC_MIN")) : 16384;
+    // Above the latency form's range the random-linear-combination form takes over: 2.4x less work per proof (one Miller
+    // loop instead of three, one final exponentiation per 64 proofs) and, with the cooperative combined check, a short
+    // tail - 1024 / 4096 proofs in 9.5 / 9.7 ms against 13.4 / 14.0 ms for one proof per lane (k_verify4, which remains
+    // the path for keys without the latency form's tables, for re-verifying large failing ranges and when the OS has no
+    // entropy).
+    const size_t rlc_min = getenv("LZKP_VERIFY_RLC_MIN") ? (size_t)atoll(getenv("LZKP_VERIFY_RLC_MIN")) : (V->coop_ok ? 513 : 16384);
     if (n < rlc_min || n > 0xFFFFFFFFull) {
         static const bool timing = getenv("LZKP_VERIFY_TIMING") != nullptr;
         cudaEvent_t e0 = nullptr, e1 = nullptr;

@@ -239,6 +239,7 @@ def test_latency_form_equals_lane_per_proof_form(eq_keys, mb_keys, co, po, frs, 
     coop = vk.verify_batch(bad, x)
     one_by_one = np.array([vk.verify_batch(bad[k:k + 1], x[k:k + 1])[0] for k in range(n)])
     monkeypatch.setenv("LZKP_VERIFY_COOP_MAX", "0")
+    monkeypatch.setenv("LZKP_VERIFY_RLC_MIN", "1000000000")
     lanes = vk.verify_batch(bad, x)
     vk.close()
     assert np.array_equal(coop, want) and np.array_equal(lanes, want) and np.array_equal(one_by_one, want)
@@ -270,6 +271,7 @@ def test_latency_form_equals_lane_per_proof_form(eq_keys, mb_keys, co, po, frs, 
     monkeypatch.setenv("LZKP_VERIFY_COOP_MAX", "512")
     coop_m = vkm.verify_batch(mp, xs)
     monkeypatch.setenv("LZKP_VERIFY_COOP_MAX", "0")
+    monkeypatch.setenv("LZKP_VERIFY_RLC_MIN", "1000000000")
     lanes_m = vkm.verify_batch(mp, xs)
     vkm.close()
     assert np.array_equal(coop_m, wm) and np.array_equal(lanes_m, wm)
