@@ -254,6 +254,73 @@ __global__ void __launch_bounds__(128) k_rlc_prepare(const VkDev *__restrict__ v
     }
 }
 
+// The same per-proof work with ONE warp per 32 proofs running the four strands one after the other.  k_rlc_prepare's
+// four role warps finish at very different times (Miller loop ~2800 Fq2 products, subgroup ladder ~1500, rho * C ~500,
+// the input scan ~0) and at 255 registers only two such CTAs fit an SM: on average 3.4 of the 8 resident warps work.
+// Here every resident warp works all the time; CTAs of two warps = one group of 64 proofs.
+__global__ void __launch_bounds__(64) k_rlc_prepare_seq(const VkDev *__restrict__ vk, uint32_t n_pub, const uint8_t *__restrict__ proofs,
+                                                        const Fr *__restrict__ inputs, const uint32_t *__restrict__ rho, uint32_t n,
+                                                        Fq12 *__restrict__ f_out, G1XYZZ *__restrict__ rc_out, Fr *__restrict__ sx_out,
+                                                        uint8_t *__restrict__ ok) {
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, p = gw * 32 + lane;
+    if (gw * 32 >= n) return;
+    const bool live = p < n;
+    const uint8_t *pb = proofs + (size_t)p * 256;
+    uint32_t k[4] = {0, 0, 0, 0};
+    if (live) {
+        const uint4 r4 = reinterpret_cast<const uint4 *>(rho)[p];
+        k[0] = r4.x; k[1] = r4.y; k[2] = r4.z; k[3] = r4.w;
+    }
+    bool good = live;
+    G1Affine A = G1Affine::inf();
+    G2Affine B = G2Affine::inf();
+    if (live) {
+        good = read_g1_checked(pb, A);
+        good = read_g2_checked(pb + 64, B) && good;                       // curve and subgroup
+        const Fr *x = inputs + (size_t)p * n_pub;
+#pragma unroll 1
+        for (uint32_t i = 0; i < n_pub; i++) good = fr_is_canonical(ld_vec(x + i)) && good;
+    }
+    {   // rho * C
+        G1XYZZ rc = G1XYZZ::inf();
+        if (live) {
+            G1Affine C;
+            good = read_g1_checked(pb + 192, C) && good;
+            if (good && !C.is_inf()) rc = scalar_mul_u128(G1XYZZ::from_affine(C), k);
+            st_vec(rc_out + p, good ? rc : G1XYZZ::inf());
+        }
+    }
+    {   // sums over these 32 proofs of rho_p * x_pj, j = 0 .. n_pub (x_p0 = 1), as plain (canonical) residues mod r
+        Fr rho_c = Fr::zero(), rho_m = Fr::zero();
+        if (good) {
+            rho_c.l[0] = k[0]; rho_c.l[1] = k[1]; rho_c.l[2] = k[2]; rho_c.l[3] = k[3];
+            rho_m = Fr::from_canonical(rho_c);
+        }
+        Fr *dst = sx_out + (size_t)gw * (n_pub + 1);
+        const Fr s0 = warp_sum_fr(rho_c);
+        if (lane == 0) st_vec(dst, s0);
+        const Fr *x = inputs + (size_t)(live ? p : 0) * n_pub;
+#pragma unroll 1
+        for (uint32_t j = 0; j < n_pub; j++) {
+            Fr t = good ? rho_m * ld_vec(x + j) : Fr::zero();
+            t = warp_sum_fr(t);
+            if (lane == 0) st_vec(dst + 1 + j, t);
+        }
+    }
+    if (live) {
+        Fq12 f;
+        G1Affine P[1] = {A};
+        G2Affine Q[1] = {B};
+        bool skip[1];
+        if (good && !A.is_inf()) P[0] = scalar_mul_u128(G1XYZZ::from_affine(A), k).to_affine();
+        skip[0] = !good || P[0].is_inf() || Q[0].is_inf();
+        multi_miller_loop<1>(f, P, Q, skip);
+        if (!good) f12_one(f);
+        f_out[p] = f;
+        ok[p] = good ? 1 : 0;
+    }
+}
+
 __global__ void __launch_bounds__(64) k_rlc_reduce(const Fq12 *__restrict__ f_in, const G1XYZZ *__restrict__ rc_in,
                                                    const Fr *__restrict__ sx_in, uint32_t n, uint32_t n_pub, uint32_t groups,
                                                    Fq12 *__restrict__ gF, G1XYZZ *__restrict__ gC, Fr *__restrict__ gS) {
@@ -898,8 +965,19 @@ int verify_batch(VerifyingKeyDev *V, size_t n, const uint8_t *proofs, const uint
     // tail runs under the next chunk's k_rlc_prepare on a second stream is SLOWER - 98 to 108 ms against 81 ms at 65 536
     // proofs: the per-proof kernel is a latency-bound chain per CTA, and four 512-CTA launches fill whole waves worse
     // than one 2048-CTA launch.)
-    LAUNCH(k_rlc_prepare, ctas, 128, 0, 0, V->vk.as<VkDev>(), (uint32_t)n_pub, d_p.as<uint8_t>(), d_x.as<Fr>(), V->d_rho.as<uint32_t>(),
-           (uint32_t)n, V->d_f.as<Fq12>(), V->d_rc.as<G1XYZZ>(), V->d_sx.as<Fr>(), d_ok.as<uint8_t>());
+    // Up to one resident wave of the four-role kernel (2 CTAs of 32 proofs per SM at 255 registers: 9472 proofs on 148 SMs)
+    // a call is bound by ONE CTA's chain and the role warps shorten it (8192 proofs: 11.2 against 12.7 ms); beyond, work per
+    // resident warp decides (16 384: 18.7 against 13.6 ms, 65 536: 67.3 against 46.4 ms).  LZKP_RLC_PREPARE_ROLES=1/0 forces one.
+    int sm_count = 148;
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, current_device() < 0 ? 0 : current_device());
+    const char *force = getenv("LZKP_RLC_PREPARE_ROLES");
+    const bool prep_roles = force ? atoi(force) != 0 : n <= (size_t)sm_count * 2 * 32;
+    if (prep_roles)
+        LAUNCH(k_rlc_prepare, ctas, 128, 0, 0, V->vk.as<VkDev>(), (uint32_t)n_pub, d_p.as<uint8_t>(), d_x.as<Fr>(), V->d_rho.as<uint32_t>(),
+               (uint32_t)n, V->d_f.as<Fq12>(), V->d_rc.as<G1XYZZ>(), V->d_sx.as<Fr>(), d_ok.as<uint8_t>());
+    else
+        LAUNCH(k_rlc_prepare_seq, (ctas + 1) / 2, 64, 0, 0, V->vk.as<VkDev>(), (uint32_t)n_pub, d_p.as<uint8_t>(), d_x.as<Fr>(),
+               V->d_rho.as<uint32_t>(), (uint32_t)n, V->d_f.as<Fq12>(), V->d_rc.as<G1XYZZ>(), V->d_sx.as<Fr>(), d_ok.as<uint8_t>());
     static const bool tail_lanes = getenv("LZKP_RLC_TAIL_LANES") != nullptr;      // A/B switch: the lane-per-group tail
     if (V->coop_ok && !tail_lanes) {
         LAUNCH(k_rlc_scalars, (groups * np1 + 127) / 128, 128, 0, 0, V->d_sx.as<Fr>(), (uint32_t)n, (uint32_t)n_pub, groups, V->d_gS.as<Fr>());
