@@ -245,9 +245,9 @@ int lzkp_ntt_device(void *d_in, void *d_out, uint32_t log_n, int inverse, int co
  * of the key (curve and subgroup), as deserialize_uncompressed does, and prepares what ark-groth16 keeps in a
  * PreparedVerifyingKey (line coefficients of -gamma, -delta, beta) plus fixed-base tables for the public-input
  * combination (keys of up to 256 public inputs; 67 MB for membership's 129).
- * Calls of up to 512 proofs (LZKP_VERIFY_COOP_MAX) give every proof a CTA whose warps and lanes share the pairing's
- * arithmetic (one verification 1.85 ms).
- * Larger calls (LZKP_VERIFY_RLC_MIN, 513) check groups of 64 proofs with one random linear combination
+ * Calls of up to three proofs per SM (LZKP_VERIFY_COOP_MAX, 444 on a B200) give every proof a CTA whose warps and lanes
+ * share the pairing's arithmetic (one verification 1.8 ms).
+ * Larger calls (LZKP_VERIFY_RLC_MIN) check groups of 64 proofs with one random linear combination
  * each (128-bit coefficients from the OS CSPRNG: one Miller loop per proof, one final exponentiation per group);
  * malformed proofs are reported individually and a failing group is re-verified proof by proof, so the decisions are
  * those of independent verification up to a soundness error of 2^-128 per group. */

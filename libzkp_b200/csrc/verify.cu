@@ -186,11 +186,20 @@ __device__ __forceinline__ Fr warp_sum_fr(Fr v) {
     return v;
 }
 
+// Four role warps per 32 proofs, lane = proof, balanced so that the longest strand is ~2200 Fq2 products (a single warp
+// running rho * A and the whole Miller loop was ~3400):
+//   warp 0: A, rho * A -> shared; upper share of Miller(rho A, B), then its 41 squarings; at the end upper * lower
+//   warp 1: B on the twist; walks the twist point through the upper iterations, then the lower share of the loop
+//   warp 2: C, rho * C; the public-input scan and the scalar sums           warp 3: B in the r-torsion subgroup
+constexpr int kLaneSplit = 41;       // iterations kAteTop .. kLaneSplit on warp 0, kLaneSplit-1 .. 0 and the final lines on warp 1
 __global__ void __launch_bounds__(128) k_rlc_prepare(const VkDev *__restrict__ vk, uint32_t n_pub, const uint8_t *__restrict__ proofs,
                                                      const Fr *__restrict__ inputs, const uint32_t *__restrict__ rho, uint32_t n,
                                                      Fq12 *__restrict__ f_out, G1XYZZ *__restrict__ rc_out, Fr *__restrict__ sx_out,
                                                      uint8_t *__restrict__ ok) {
-    __shared__ uint8_t sgood[4][32];
+    extern __shared__ uint4 smem_raw[];
+    Fq12 *s_lower = reinterpret_cast<Fq12 *>(smem_raw);                          // [32] lower shares
+    G1Affine *s_P = reinterpret_cast<G1Affine *>(s_lower + 32);                  // [32] rho * A
+    __shared__ uint8_t sgood[4][32], s_goodA[32];
     const uint32_t role = threadIdx.x >> 5, lane = threadIdx.x & 31, p = blockIdx.x * 32 + lane;
     const bool live = p < n;
     const uint8_t *pb = proofs + (size_t)p * 256;
@@ -202,39 +211,64 @@ __global__ void __launch_bounds__(128) k_rlc_prepare(const VkDev *__restrict__ v
     bool good = true;
     Fq12 f;
     G1XYZZ rc = G1XYZZ::inf();
-    if (live) {
-        if (role == 0) {
-            G1Affine P[1];
-            G2Affine Q[1];
-            bool skip[1];
-            good = read_g1_checked(pb, P[0]);
-            good = read_g2_on_curve(pb + 64, Q[0]) && good;
-            if (good && !P[0].is_inf()) P[0] = scalar_mul_u128(G1XYZZ::from_affine(P[0]), k).to_affine();
-            skip[0] = !good || P[0].is_inf() || Q[0].is_inf();
-            multi_miller_loop<1>(f, P, Q, skip);
-        } else if (role == 1) {
-            const Fr *x = inputs + (size_t)p * n_pub;
-#pragma unroll 1
-            for (uint32_t i = 0; i < n_pub; i++) good = fr_is_canonical(ld_vec(x + i)) && good;
-        } else if (role == 2) {
+    if (role == 0) {
+        G1Affine P = G1Affine::inf();
+        G2Affine Q = G2Affine::inf();
+        if (live) {
+            good = read_g1_checked(pb, P);
+            if (good && !P.is_inf()) P = scalar_mul_u128(G1XYZZ::from_affine(P), k).to_affine();
+            st_vec(s_P + lane, P);
+            s_goodA[lane] = good ? 1 : 0;
+        }
+        asm volatile("bar.sync 1, 64;" ::: "memory");                           // rho * A is there (warps 0 and 1)
+        if (live) {
+            good = read_g2_on_curve(pb + 64, Q) && good;
+            if (!good || P.is_inf() || Q.is_inf()) f12_one(f);
+            else {
+                G2Proj R{Q.x, Q.y, Fq2::one()};
+                miller_share(f, P, Q, R, kAteTop, kLaneSplit, kLaneSplit, false);
+            }
+        }
+    } else if (role == 1) {
+        G2Affine Q = G2Affine::inf();
+        G2Proj R{Fq2::one(), Fq2::one(), Fq2::one()};
+        if (live) {
+            good = read_g2_on_curve(pb + 64, Q);
+            if (good && !Q.is_inf()) {
+                R = G2Proj{Q.x, Q.y, Fq2::one()};
+                miller_advance(R, Q, kAteTop, kLaneSplit);
+            }
+        }
+        asm volatile("bar.sync 1, 64;" ::: "memory");
+        if (live) {
+            const G1Affine P = ld_vec(s_P + lane);
+            if (!good || !s_goodA[lane] || P.is_inf() || Q.is_inf()) f12_one(f);
+            else miller_share(f, P, Q, R, kLaneSplit - 1, 0, 0, true);
+            s_lower[lane] = f;
+        }
+    } else if (role == 2) {
+        if (live) {
             G1Affine C;
             good = read_g1_checked(pb + 192, C);
             if (good && !C.is_inf()) rc = scalar_mul_u128(G1XYZZ::from_affine(C), k);
-        } else {
-            G2Affine B;
-            good = read_g2_checked(pb + 64, B);
+            const Fr *x = inputs + (size_t)p * n_pub;
+#pragma unroll 1
+            for (uint32_t i = 0; i < n_pub; i++) good = fr_is_canonical(ld_vec(x + i)) && good;
         }
+    } else if (live) {
+        G2Affine B;
+        good = read_g2_checked(pb + 64, B);
     }
     sgood[role][lane] = good ? 1 : 0;
     __syncthreads();
     good = live && sgood[0][lane] && sgood[1][lane] && sgood[2][lane] && sgood[3][lane];
     if (role == 0 && live) {
         if (!good) f12_one(f);
+        else { Fq12 t; f12_mul(t, f, s_lower[lane]); f = t; }
         f_out[p] = f;
         ok[p] = good ? 1 : 0;
-    } else if (role == 2 && live) {
-        st_vec(rc_out + p, good ? rc : G1XYZZ::inf());
-    } else if (role == 1) {
+    } else if (role == 2) {
+        if (live) st_vec(rc_out + p, good ? rc : G1XYZZ::inf());
         // sums over this CTA's 32 proofs of rho_p * x_pj, j = 0 .. n_pub (x_p0 = 1), as plain (canonical) residues mod r
         Fr rho_c = Fr::zero(), rho_m = Fr::zero();
         if (good) {
@@ -907,10 +941,13 @@ int verify_batch(VerifyingKeyDev *V, size_t n, const uint8_t *proofs, const uint
     TRY(d_p.ensure(n * 256)); TRY(d_x.ensure(n * std::max<size_t>(n_pub, 1) * 32)); TRY(d_ok.ensure(n));
     CUDA_TRY(cudaMemcpy(d_p.p, proofs, n * 256, cudaMemcpyHostToDevice));
     if (n_pub) CUDA_TRY(cudaMemcpy(d_x.p, inputs, n * n_pub * 32, cudaMemcpyHostToDevice));
-    // Calls of up to coop_max proofs are bound by ONE proof's dependent chain: there a proof gets a whole CTA whose
-    // lanes share every Fq12 product (coop.cuh); above, lane = proof (k_verify4) does less work per proof.  Measured:
-    // 1 / 64 / 256 / 512 proofs 2.5 / 2.9 / 6.5 / 12.5 ms this way against 13.7 - 14.3 ms for any count up to 4096 the other.
-    const size_t coop_max = getenv("LZKP_VERIFY_COOP_MAX") ? (size_t)atoll(getenv("LZKP_VERIFY_COOP_MAX")) : 512;
+    // Calls of up to coop_max proofs are bound by ONE proof's dependent chain: there a proof gets a whole CTA whose warps
+    // and lanes share the pairing's arithmetic (coop.cuh): 1 / 64 / 128 / 256 proofs in 1.85 / 1.9 / 2.2 / 4.3 ms, i.e. ~2.1 ms
+    // per wave of one CTA per SM, against 7.5 ms for the random-linear-combination form at any count up to ~8000 and
+    // 13.4 ms for one proof per lane: three waves (444 proofs on 148 SMs) is where the combined form takes over.
+    int sm_count = 148;
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, current_device() < 0 ? 0 : current_device());
+    const size_t coop_max = getenv("LZKP_VERIFY_COOP_MAX") ? (size_t)atoll(getenv("LZKP_VERIFY_COOP_MAX")) : (size_t)3 * sm_count;
     auto verify_range = [&](size_t off, size_t cnt) {             // independent verification of proofs [off, off + cnt)
         if (V->coop_ok && cnt <= coop_max) {
             LAUNCH(k_verify_coop, (unsigned)cnt, kCoopThreads, sizeof(CoopSmem), 0, V->vk.as<VkDev>(), V->gamma_abc.as<G1Affine>(),
@@ -923,10 +960,10 @@ int verify_batch(VerifyingKeyDev *V, size_t n, const uint8_t *proofs, const uint
     };
     // Above the latency form's range the random-linear-combination form takes over: 2.4x less work per proof (one Miller
     // loop instead of three, one final exponentiation per 64 proofs) and, with the cooperative combined check, a short
-    // tail - 1024 / 4096 proofs in 9.5 / 9.7 ms against 13.4 / 14.0 ms for one proof per lane (k_verify4, which remains
+    // tail - 1024 / 4096 proofs in 7.5 / 7.9 ms against 13.4 / 14.0 ms for one proof per lane (k_verify4, which remains
     // the path for keys without the latency form's tables, for re-verifying large failing ranges and when the OS has no
     // entropy).
-    const size_t rlc_min = getenv("LZKP_VERIFY_RLC_MIN") ? (size_t)atoll(getenv("LZKP_VERIFY_RLC_MIN")) : (V->coop_ok ? 513 : 16384);
+    const size_t rlc_min = getenv("LZKP_VERIFY_RLC_MIN") ? (size_t)atoll(getenv("LZKP_VERIFY_RLC_MIN")) : (V->coop_ok ? (size_t)3 * sm_count + 1 : 16384);
     if (n < rlc_min || n > 0xFFFFFFFFull) {
         static const bool timing = getenv("LZKP_VERIFY_TIMING") != nullptr;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -968,12 +1005,10 @@ int verify_batch(VerifyingKeyDev *V, size_t n, const uint8_t *proofs, const uint
     // Up to one resident wave of the four-role kernel (2 CTAs of 32 proofs per SM at 255 registers: 9472 proofs on 148 SMs)
     // a call is bound by ONE CTA's chain and the role warps shorten it (8192 proofs: 11.2 against 12.7 ms); beyond, work per
     // resident warp decides (16 384: 18.7 against 13.6 ms, 65 536: 67.3 against 46.4 ms).  LZKP_RLC_PREPARE_ROLES=1/0 forces one.
-    int sm_count = 148;
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, current_device() < 0 ? 0 : current_device());
     const char *force = getenv("LZKP_RLC_PREPARE_ROLES");
     const bool prep_roles = force ? atoi(force) != 0 : n <= (size_t)sm_count * 2 * 32;
     if (prep_roles)
-        LAUNCH(k_rlc_prepare, ctas, 128, 0, 0, V->vk.as<VkDev>(), (uint32_t)n_pub, d_p.as<uint8_t>(), d_x.as<Fr>(), V->d_rho.as<uint32_t>(),
+        LAUNCH(k_rlc_prepare, ctas, 128, 32 * (sizeof(Fq12) + sizeof(G1Affine)), 0, V->vk.as<VkDev>(), (uint32_t)n_pub, d_p.as<uint8_t>(), d_x.as<Fr>(), V->d_rho.as<uint32_t>(),
                (uint32_t)n, V->d_f.as<Fq12>(), V->d_rc.as<G1XYZZ>(), V->d_sx.as<Fr>(), d_ok.as<uint8_t>());
     else
         LAUNCH(k_rlc_prepare_seq, (ctas + 1) / 2, 64, 0, 0, V->vk.as<VkDev>(), (uint32_t)n_pub, d_p.as<uint8_t>(), d_x.as<Fr>(),

@@ -193,7 +193,7 @@ def test_rlc_batched_verification_equals_independent_verification(eq_keys, mb_ke
 
 
 def test_latency_form_equals_lane_per_proof_form(eq_keys, mb_keys, co, po, frs, monkeypatch):
-    # Calls of up to 512 proofs give every proof a CTA whose lanes share each Fq12 product (coop.cuh: prepared lines for
+    # Calls of up to three waves of one CTA per SM (444 proofs on a B200) give every proof a CTA whose lanes share each Fq12 product (coop.cuh: prepared lines for
     # -gamma / -delta, byte-window tables for vk_x, lane-parallel subgroup ladder); larger calls run one proof per lane
     # (k_verify4).  Both must decide what the oracle's pairing verifier decides (snark.rs:377-401), case by case.
     pk = engine.ProvingKey(eq_keys.pk_bytes, window_bits=WINDOW_BITS)
