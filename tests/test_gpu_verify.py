@@ -275,3 +275,36 @@ def test_latency_form_equals_lane_per_proof_form(eq_keys, mb_keys, co, po, frs, 
     lanes_m = vkm.verify_batch(mp, xs)
     vkm.close()
     assert np.array_equal(coop_m, wm) and np.array_equal(lanes_m, wm)
+
+
+def test_verifier_forms_at_scale(eq_keys, po, frs):
+    # Size-independent property at the sizes where the engine changes form (default thresholds): every valid proof is
+    # accepted and exactly the corrupted ones are rejected - latency form (300), combined form with role warps (3000: the
+    # Miller loop split over two warps, cooperative combined check, proof-by-proof fallback of failing groups) and combined
+    # form with one warp per 32 proofs (10 240, beyond one resident wave).
+    pk = engine.ProvingKey(eq_keys.pk_bytes, window_bits=WINDOW_BITS)
+    pk.circuit_builtin(engine.EQUALITY, 110)
+    n = 10240
+    rng = po.SplitMix64(1234)
+    a = np.array([rng.next_u64() for _ in range(n)], np.uint64)
+    proofs, cms, st = pk.prove_equality_batch(a, a, frs(5, n), frs(6, n))
+    pk.close()
+    assert not st.any()
+    vk = engine.VerifyingKey(eq_keys.vk_bytes)
+    for m in (300, 3000, n):
+        bad, x = proofs[:m].copy(), cms[:m].copy()
+        want = np.ones(m, bool)
+        spots = [0, 1, 63, 64, m // 3, m // 2, m - 65, m - 1]
+        for t, i in enumerate(spots):
+            want[i] = False
+            if t % 4 == 0:
+                bad[i, 7] ^= 1                                           # A off the curve
+            elif t % 4 == 1:
+                bad[i, 192:256] = proofs[(i + 5) % m, 192:256]           # valid point, wrong C
+            elif t % 4 == 2:
+                x[i] = cms[(i + 9) % m]                                  # wrong public input
+            else:
+                bad[i, 64:192] = proofs[(i + 3) % m, 64:192]             # valid G2 point, wrong B
+        assert np.array_equal(vk.verify_batch(bad, x), want), m
+        assert vk.verify_batch(proofs[:m], cms[:m]).all(), m
+    vk.close()
