@@ -519,7 +519,10 @@ __device__ __forceinline__ void set_emb(FChain &c, const G1Affine &P) {
 //   warp 6  DELTA:    Miller(C, -delta) on prepared lines                                            (beside warp 2)
 //   warp 3  LADDER:   B in the r-torsion subgroup?                                                    warp 5: idle
 enum CoopRole { kAbUpper = 0, kLines = 1, kAbLower = 2, kLadder = 3, kGamma = 4, kIdle = 5, kDelta = 6 };
-__global__ void __launch_bounds__(kCoopThreads) k_verify_coop(const VkDev *__restrict__ vk, const G1Affine *__restrict__ gamma_abc,
+// MIN_CTAS = 1: all the registers the code wants (250; one CTA per SM) for calls of at most one proof per SM; MIN_CTAS = 2: 128
+// registers, two proofs per SM side by side - 10 % slower each (1.99 against 1.80 ms), 1.5x the throughput from 149 proofs on.
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(kCoopThreads, MIN_CTAS) k_verify_coop(const VkDev *__restrict__ vk, const G1Affine *__restrict__ gamma_abc,
                                                               const G1Affine *__restrict__ tab, const Fq2 *__restrict__ lines_gamma,
                                                               const Fq2 *__restrict__ lines_delta, uint32_t n_pub,
                                                               const uint8_t *__restrict__ proofs, const uint8_t *__restrict__ inputs,
@@ -942,17 +945,22 @@ int verify_batch(VerifyingKeyDev *V, size_t n, const uint8_t *proofs, const uint
     CUDA_TRY(cudaMemcpy(d_p.p, proofs, n * 256, cudaMemcpyHostToDevice));
     if (n_pub) CUDA_TRY(cudaMemcpy(d_x.p, inputs, n * n_pub * 32, cudaMemcpyHostToDevice));
     // Calls of up to coop_max proofs are bound by ONE proof's dependent chain: there a proof gets a whole CTA whose warps
-    // and lanes share the pairing's arithmetic (coop.cuh): 1 / 64 / 128 / 256 proofs in 1.85 / 1.9 / 2.2 / 4.3 ms, i.e. ~2.1 ms
-    // per wave of one CTA per SM, against 7.5 ms for the random-linear-combination form at any count up to ~8000 and
-    // 13.4 ms for one proof per lane: three waves (444 proofs on 148 SMs) is where the combined form takes over.
+    // and lanes share the pairing's arithmetic (coop.cuh): 1 / 64 / 148 proofs in 1.8 / 1.9 / 2.2 ms with one CTA per SM,
+    // 296 / 444 proofs in 3.1 / 5.7 ms with two per SM, against 7.5 ms for the random-linear-combination form at any
+    // count up to ~8000 and 13.4 ms for one proof per lane: three proofs per SM is where the combined form takes over.
     int sm_count = 148;
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, current_device() < 0 ? 0 : current_device());
     const size_t coop_max = getenv("LZKP_VERIFY_COOP_MAX") ? (size_t)atoll(getenv("LZKP_VERIFY_COOP_MAX")) : (size_t)3 * sm_count;
     auto verify_range = [&](size_t off, size_t cnt) {             // independent verification of proofs [off, off + cnt)
         if (V->coop_ok && cnt <= coop_max) {
-            LAUNCH(k_verify_coop, (unsigned)cnt, kCoopThreads, sizeof(CoopSmem), 0, V->vk.as<VkDev>(), V->gamma_abc.as<G1Affine>(),
-                   V->tab.as<G1Affine>(), V->lines_gamma.as<Fq2>(), V->lines_delta.as<Fq2>(), (uint32_t)n_pub,
-                   d_p.as<uint8_t>() + off * 256, d_x.as<uint8_t>() + off * n_pub * 32, d_ok.as<uint8_t>() + off);
+            if (cnt <= (size_t)sm_count)
+                LAUNCH(k_verify_coop<1>, (unsigned)cnt, kCoopThreads, sizeof(CoopSmem), 0, V->vk.as<VkDev>(), V->gamma_abc.as<G1Affine>(),
+                       V->tab.as<G1Affine>(), V->lines_gamma.as<Fq2>(), V->lines_delta.as<Fq2>(), (uint32_t)n_pub,
+                       d_p.as<uint8_t>() + off * 256, d_x.as<uint8_t>() + off * n_pub * 32, d_ok.as<uint8_t>() + off);
+            else
+                LAUNCH(k_verify_coop<2>, (unsigned)cnt, kCoopThreads, sizeof(CoopSmem), 0, V->vk.as<VkDev>(), V->gamma_abc.as<G1Affine>(),
+                       V->tab.as<G1Affine>(), V->lines_gamma.as<Fq2>(), V->lines_delta.as<Fq2>(), (uint32_t)n_pub,
+                       d_p.as<uint8_t>() + off * 256, d_x.as<uint8_t>() + off * n_pub * 32, d_ok.as<uint8_t>() + off);
             return;
         }
         LAUNCH(k_verify4, (unsigned)((cnt + 31) / 32), 128, 64 * sizeof(Fq12), 0, V->vk.as<VkDev>(), V->gamma_abc.as<G1Affine>(),
