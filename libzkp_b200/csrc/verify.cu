@@ -631,7 +631,8 @@ __device__ __noinline__ G1Affine coop_sum_g1(const G1XYZZ *src, uint32_t count) 
     for (int k = 0; k < (int)(sizeof(G1Affine) / 4); k++) rw[k] = __shfl_sync(0xffffffffu, rw[k], 0);
     return r;
 }
-__global__ void __launch_bounds__(128) k_rlc_tail_coop(const VkDev *__restrict__ vk, const Fq2 *__restrict__ lines_gamma,
+template <int MIN_CTAS>       // 2: the registers the code wants; 4: capped at 128 for twice the resident groups (large batches)
+__global__ void __launch_bounds__(128, MIN_CTAS) k_rlc_tail_coop(const VkDev *__restrict__ vk, const Fq2 *__restrict__ lines_gamma,
                                                        const Fq2 *__restrict__ lines_delta, const Fq2 *__restrict__ lines_beta,
                                                        const Fq12 *__restrict__ f_in, const G1XYZZ *__restrict__ rc_in,
                                                        const G1XYZZ *__restrict__ gX, uint32_t n, uint32_t n_pub,
@@ -1026,9 +1027,14 @@ int verify_batch(VerifyingKeyDev *V, size_t n, const uint8_t *proofs, const uint
         LAUNCH(k_rlc_scalars, (groups * np1 + 127) / 128, 128, 0, 0, V->d_sx.as<Fr>(), (uint32_t)n, (uint32_t)n_pub, groups, V->d_gS.as<Fr>());
         LAUNCH(k_rlc_inputs2, (groups * (np1 + 1) + 63) / 64, 64, 0, 0, V->vk.as<VkDev>(), V->d_gS.as<Fr>(), V->gamma_abc.as<G1Affine>(),
                (uint32_t)n_pub, groups, V->d_gX.as<G1XYZZ>());
-        LAUNCH(k_rlc_tail_coop, groups, 128, sizeof(TailSmem), 0, V->vk.as<VkDev>(), V->lines_gamma.as<Fq2>(), V->lines_delta.as<Fq2>(),
-               V->lines_beta.as<Fq2>(), V->d_f.as<Fq12>(), V->d_rc.as<G1XYZZ>(), V->d_gX.as<G1XYZZ>(), (uint32_t)n, (uint32_t)n_pub,
-               V->d_gok.as<uint8_t>());
+        if (groups <= 2u * (uint32_t)sm_count)
+            LAUNCH(k_rlc_tail_coop<2>, groups, 128, sizeof(TailSmem), 0, V->vk.as<VkDev>(), V->lines_gamma.as<Fq2>(), V->lines_delta.as<Fq2>(),
+                   V->lines_beta.as<Fq2>(), V->d_f.as<Fq12>(), V->d_rc.as<G1XYZZ>(), V->d_gX.as<G1XYZZ>(), (uint32_t)n, (uint32_t)n_pub,
+                   V->d_gok.as<uint8_t>());
+        else
+            LAUNCH(k_rlc_tail_coop<4>, groups, 128, sizeof(TailSmem), 0, V->vk.as<VkDev>(), V->lines_gamma.as<Fq2>(), V->lines_delta.as<Fq2>(),
+                   V->lines_beta.as<Fq2>(), V->d_f.as<Fq12>(), V->d_rc.as<G1XYZZ>(), V->d_gX.as<G1XYZZ>(), (uint32_t)n, (uint32_t)n_pub,
+                   V->d_gok.as<uint8_t>());
     } else {
     LAUNCH(k_rlc_reduce, (groups + 63) / 64, 64, 0, 0, V->d_f.as<Fq12>(), V->d_rc.as<G1XYZZ>(), V->d_sx.as<Fr>(), (uint32_t)n,
            (uint32_t)n_pub, groups, V->d_gF.as<Fq12>(), V->d_gC.as<G1XYZZ>(), V->d_gS.as<Fr>());
