@@ -81,26 +81,40 @@ __device__ __forceinline__ Fq2 operand(const Fq2 *b, int X, int i) {      // coe
 
 // r = a * b.  Every lane of the warp calls; r may alias a or b.  Lanes 18.. may carry one extra Fq2 product each
 // (*so = *sa * *sb, so == nullptr: none) that rides in the same instruction stream.
+#ifdef LZKP_COOP_PROF          // per-phase cycle counters of f12_mul (variant build only; warp 0 of CTA 0)
+__device__ long long g_coop_prof[8];
+#define LZ_PROF_T(k) const long long prof_t##k = clock64()
+#define LZ_PROF_ADD(i, k0, k1) if (threadIdx.x == 0 && blockIdx.x == 0) g_coop_prof[i] += prof_t##k1 - prof_t##k0
+#else
+#define LZ_PROF_T(k)
+#define LZ_PROF_ADD(i, k0, k1)
+#endif
 template <bool SPARSE>
 __device__ __noinline__ void f12_mul(Fq2 *r, const Fq2 *a, const Fq2 *b, Scratch *s, const Fq2 *sa = nullptr,
                                      const Fq2 *sb = nullptr, Fq2 *so = nullptr) {
     const int lane = lane_id();
+    LZ_PROF_T(0);
     Fq2 x = Fq2::zero(), y = Fq2::zero();
+    const bool same = !SPARSE && a == b;             // a squaring (warp-uniform): the operand sums are computed once
     if (lane < 18) {
         const int X = lane / 6, j = lane - 6 * X;
         const int i1 = j < 3 ? j : (j == 3 ? 1 : 0), i2 = j < 3 ? -1 : (j == 4 ? 1 : 2);
         x = operand<false>(a, X, i1);
-        y = operand<SPARSE>(b, X, i1);
+        if (!same) y = operand<SPARSE>(b, X, i1);
         if (i2 >= 0) {
             x = qadd(x, operand<false>(a, X, i2));
-            y = qadd(y, operand<SPARSE>(b, X, i2));
+            if (!same) y = qadd(y, operand<SPARSE>(b, X, i2));
         }
+        if (same) y = x;
     } else if (so) {
         x = ldq(sa);
         y = ldq(sb);
     }
+    __syncwarp();
+    LZ_PROF_T(1);
     const Fq2 p = x * y;
     __syncwarp();
+    LZ_PROF_T(2);
     if (lane < 18) stq(&s->P[lane], p);
     else if (so) stq(so, p);
     __syncwarp();
@@ -128,6 +142,7 @@ __device__ __noinline__ void f12_mul(Fq2 *r, const Fq2 *a, const Fq2 *b, Scratch
         stq(&s->T[lane], qadd(base, qxi(e)));      // k = 2: e = 0
     }
     __syncwarp();
+    LZ_PROF_T(3);
     // Fq12 level:  c0 = T0 + v T1 = (T0[0] + xi T1[2], T0[1] + T1[0], T0[2] + T1[1]),  c1 = T2 - T0 - T1
     if (lane < 6) {
         Fq2 t;
@@ -136,6 +151,11 @@ __device__ __noinline__ void f12_mul(Fq2 *r, const Fq2 *a, const Fq2 *b, Scratch
         stq(r + lane, t);
     }
     __syncwarp();
+    LZ_PROF_T(4);
+    LZ_PROF_ADD(0, 0, 1); LZ_PROF_ADD(1, 1, 2); LZ_PROF_ADD(2, 2, 3); LZ_PROF_ADD(3, 3, 4);
+#ifdef LZKP_COOP_PROF
+    if (threadIdx.x == 0 && blockIdx.x == 0) g_coop_prof[4] += 1;
+#endif
 }
 
 __device__ __forceinline__ void f12_set_one(Fq2 *f) {

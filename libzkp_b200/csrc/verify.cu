@@ -871,6 +871,14 @@ static int coop_prepare(VerifyingKeyDev *V) {
             fprintf(stderr, "lzkp coop selftest cycles, two warps only (%s): line chain done %lld, f chain done %lld (its own span %lld)\n",
                     solo == 1 ? "side by side" : "line chain first", s2[11], s2[10], s2[9]);
         }
+#ifdef LZKP_COOP_PROF
+        {
+            long long pr[8];
+            CUDA_TRY(cudaMemcpyFromSymbol(pr, coop::g_coop_prof, sizeof(pr)));
+            fprintf(stderr, "lzkp coop f12_mul phases over %lld products of warp 0 (cycles each): operands %lld, Fq2 product %lld, Fq6 level %lld, Fq12 level %lld\n",
+                    pr[4], pr[0] / pr[4], pr[1] / pr[4], pr[2] / pr[4], pr[3] / pr[4]);
+        }
+#endif
         fprintf(stderr, "lzkp coop selftest: %s (mask %d: 1 Miller(A,B), 2 final exponentiation, 4 Miller on prepared lines, 8 subgroup)\n",
                 res == 0 ? "ok" : "MISMATCH", res);
         if (res != 0) return fail(LZKP_E_CUDA, "cooperative verifier self-test failed");
