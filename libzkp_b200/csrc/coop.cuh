@@ -14,8 +14,8 @@
 //     product.
 //   * vk_x = gamma_abc_0 + sum x_i gamma_abc_i comes from fixed-base byte-window tables built at lzkp_vk_load
 //     (lane = (input, byte) pair, then a shuffle tree).
-//   * the r-torsion test of B ([6x^2] B == psi(B)) runs its G2 ladder with the independent products of every
-//     doubling / addition on different lanes, beside the Miller loops and the final exponentiation.
+//   * the r-torsion test of B (one 63-bit ladder, pairing.cuh g2_subgroup_from_xp) runs with the independent products of
+//     every doubling / addition on different lanes, beside the Miller loops and the final exponentiation.
 // Same formulas as pairing.cuh (the serial code is the checker: LZKP_COOP_SELFTEST=1 compares both at key load).
 #pragma once
 #include "dev_util.cuh"
@@ -647,10 +647,10 @@ __device__ __noinline__ bool ladder_madd(LadderState *st) {
     __syncwarp();
     return true;
 }
-// B (on the twist, not infinity) in the r-torsion subgroup?  [6 x^2] B == psi(B), as read_g2_checked tests it.
+// B (on the twist, not infinity) in the r-torsion subgroup?  The ladder computes [x] B (62 doublings, 27 additions with
+// their independent products on different lanes); lane 0 then finishes the test of pairing.cuh g2_subgroup_from_xp.
 __device__ __noinline__ bool g2_in_subgroup(LadderState *st, const G2Affine &B) {
     const int lane = lane_id();
-    const uint32_t k[4] = {0xe87cfd46u, 0xf83e9682u, 0xeeb859fbu, 0x6f4d8248u};       // 6 x^2, 127 bits
     if (lane == 0) {
         stq(&st->X, B.x); stq(&st->Y, B.y); stq(&st->ZZ, Fq2::one()); stq(&st->ZZZ, Fq2::one());
         stq(&st->bx, B.x); stq(&st->by, B.y);
@@ -671,22 +671,15 @@ __device__ __noinline__ bool g2_in_subgroup(LadderState *st, const G2Affine &B) 
         return __shfl_sync(0xffffffffu, (int)sp, 0) != 0;
     };
 #pragma unroll 1
-    for (int i = 125; i >= 0; i--) {       // bit 126 is the leading one
+    for (int i = 61; i >= 0; i--) {        // bit 62 is the leading one of x
         if (is_special()) serial(false);
         else ladder_dbl(st);
-        if ((k[i >> 5] >> (i & 31)) & 1u) {
+        if ((kBnX >> i) & 1ull) {
             if (is_special() || !ladder_madd(st)) serial(true);
         }
     }
     bool ok = false;
-    if (lane == 0) {
-        const Fq2 zz = ldq(&st->ZZ);
-        if (!zz.is_zero()) {
-            const Fq2 twx{PairingConsts::TW_X_C0(), PairingConsts::TW_X_C1()}, twy{PairingConsts::TW_Y_C0(), PairingConsts::TW_Y_C1()};
-            const Fq2 px = fq2_conj(B.x) * twx, py = fq2_conj(B.y) * twy;
-            ok = ldq(&st->X) == px * zz && ldq(&st->Y) == py * ldq(&st->ZZZ);
-        }
-    }
+    if (lane == 0) ok = g2_subgroup_from_xp(B, G2XYZZ{ldq(&st->X), ldq(&st->Y), ldq(&st->ZZ), ldq(&st->ZZZ)});
     return __shfl_sync(0xffffffffu, (int)ok, 0) != 0;
 }
 

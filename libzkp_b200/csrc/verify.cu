@@ -58,15 +58,9 @@ __device__ __noinline__ bool read_g2_on_curve(const uint8_t *b, G2Affine &p) {
 __device__ __noinline__ bool read_g2_checked(const uint8_t *b, G2Affine &p) {
     if (!read_g2_on_curve(b, p)) return false;
     if (p.is_inf()) return true;
-    // subgroup check (deserialize_uncompressed validates it).  On BN curves the untwist-Frobenius-twist map psi
-    // acts on G2 as multiplication by p = t - 1 = 6 x^2 (mod r), and psi(P) == [6 x^2] P characterises G2 among the
-    // points of the twist (the test gnark-crypto uses for bn254): a 127-bit ladder instead of a 254-bit one.
-    const uint32_t six_x2[4] = {0xe87cfd46u, 0xf83e9682u, 0xeeb859fbu, 0x6f4d8248u};
-    G2XYZZ t = scalar_mul_u128(G2XYZZ::from_affine(p), six_x2);
-    if (t.is_inf()) return false;
-    Fq2 twx{PairingConsts::TW_X_C0(), PairingConsts::TW_X_C1()}, twy{PairingConsts::TW_Y_C0(), PairingConsts::TW_Y_C1()};
-    Fq2 px = fq2_conj(p.x) * twx, py = fq2_conj(p.y) * twy;
-    return t.x == px * t.zz && t.y == py * t.zzz;
+    // subgroup check (deserialize_uncompressed validates it): pairing.cuh g2_subgroup_from_xp, one 63-bit ladder
+    const uint32_t x[2] = {kBnXLimbs[0], kBnXLimbs[1]};
+    return g2_subgroup_from_xp(p, scalar_mul_window<Fq2, 2>(G2XYZZ::from_affine(p), x));
 }
 
 // e(alpha, beta) once per key (what process_vk precomputes)
