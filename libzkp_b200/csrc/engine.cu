@@ -358,7 +358,7 @@ static int pk_load_impl(const uint8_t *bytes, size_t len, int validate, const lz
         // (every MSM call also carries ~0.55 ms (G1) / ~1 ms (G2) that does not scale with its range, so the best
         // weights drift with the shard count: fitted at 2, 4 and 8 shards)
         const uint32_t G_ = pk->shard_count;
-        const uint64_t w_g2 = getenv("LZKP_SHARD_G2_WEIGHT") ? (uint64_t)atoi(getenv("LZKP_SHARD_G2_WEIGHT")) : (G_ > 4 ? 32 : 28);
+        const uint64_t w_g2 = getenv("LZKP_SHARD_G2_WEIGHT") ? (uint64_t)atoi(getenv("LZKP_SHARD_G2_WEIGHT")) : (G_ > 2 ? 32 : 28);
         const uint64_t sizes[5] = {nv, nv, (uint64_t)pk->n_wit + 1, (uint64_t)n - 1, nv}, wts[5] = {10, 10, 10, 10, w_g2};
         const double Wh = (double)sizes[3] * wts[3];
         double Wz = 0;
@@ -368,9 +368,38 @@ static int pk_load_impl(const uint8_t *bytes, size_t len, int validate, const lz
         uint32_t k = 1;
         while (k < G_ && k * ((Wz + Wh + k * M) / G_ - M) < Wh) k++;
         const double T = (Wz + Wh + k * M) / G_;
-        std::vector<double> cutz(G_ + 1, 0.0);
-        for (uint32_t i = 0; i < G_; i++) cutz[i + 1] = cutz[i] + (i < k ? std::max(0.0, T - M - Wh / k) : T);
-        for (uint32_t i = 0; i <= G_; i++) cutz[i] *= Wz / cutz[G_];                 // (clamping may leave a remainder)
+        std::vector<double> cutz(G_ + 1, 0.0), share(G_, 0.0);
+        for (uint32_t i = 0; i < G_; i++) share[i] = i < k ? std::max(0.0, T - M - Wh / k) : T;
+        // A rank whose share straddles a query boundary runs one MSM call more than its neighbours, and a call carries
+        // ~0.25 ms that does not depend on its range (sort floor, segment and bucket reductions; tools/shard_balance.py:
+        // the rank holding the end of l and the start of b2 was the slowest of 8 at every weight).  Shares of such ranks
+        // shrink by that much per extra piece, the others absorb it; three rounds settle the cuts.  Slowest shard 4.64 -> 4.42 ms
+        // at 8 shards, 7.37 -> 7.14 ms at 4 (with the G2 weight of 8 shards); two shards keep the plain split (the adjustment
+        // only moved a sliver across and made it worse).
+        const double piece_cost = G_ > 2 ? (getenv("LZKP_SHARD_PIECE_COST") ? atof(getenv("LZKP_SHARD_PIECE_COST")) : (G_ > 4 ? 0.25 : 0.45)) * 2.76e6 : 0.0;
+        std::vector<double> adj(share);
+        for (int round = 0; round < 4; round++) {
+            double tot = 0;
+            for (uint32_t i = 0; i < G_; i++) tot += adj[i];
+            for (uint32_t i = 0; i < G_; i++) cutz[i + 1] = cutz[i] + adj[i] * Wz / tot;   // (clamping may leave a remainder)
+            double bounds[5] = {0, 0, 0, 0, 0};                                             // weighted ends of a | b1 | l | b2
+            { int j = 0; for (int q : {0, 1, 2, 4}) { bounds[j + 1] = bounds[j] + (double)sizes[q] * wts[q]; j++; } }
+            if (piece_cost != 0.0)                      // a sliver of a query next to a boundary is not worth an MSM call: snap
+                for (uint32_t i = 1; i < G_; i++)
+                    for (int j = 1; j < 4; j++)
+                        if (std::fabs(cutz[i] - bounds[j]) < 1.0e5) cutz[i] = bounds[j];        // < 10 k G1 points
+            if (round == 3 || piece_cost == 0.0) break;
+            double extra_total = 0;
+            std::vector<double> extra(G_, 0.0);
+            for (uint32_t i = 0; i < G_; i++) {
+                int pieces = 0;
+                for (int j = 0; j < 4; j++)
+                    if (std::min(cutz[i + 1], bounds[j + 1]) - std::max(cutz[i], bounds[j]) > 1e-6 * Wz) pieces++;
+                extra[i] = piece_cost * std::max(0, pieces - 1);
+                extra_total += extra[i];
+            }
+            for (uint32_t i = 0; i < G_; i++) adj[i] = std::max(0.0, share[i] - extra[i] + extra_total / G_);
+        }
         pk->map_ranks = k;
         const uint32_t me = pk->shard_index;
         if (me < k) {
