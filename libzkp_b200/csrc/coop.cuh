@@ -3,19 +3,23 @@
 // k_verify4 (verify.cu) runs one proof per LANE: right for throughput, but a single verification is then one
 // thread's dependent chain of ~20 000 field products (13.7 ms, against ~3 ms for arkworks on a CPU, which is what the
 // reference pays per call at src/backend/snark.rs:377-401).  A warp instruction costs the same whether 1 or 32 lanes
-// are active, so here ONE proof owns a CTA and the lanes of a warp share every Fq12 product:
+// are active, so here ONE proof owns a CTA and both the lanes of a warp and the warps share the work:
 //   * f12_mul: the 18 Fq2 products of a Karatsuba Fq12 product (3 Fq6 products of 6) run on 18 lanes at once; the
-//     recombination runs on 10 and then 6 lanes.  Squarings, cyclotomic squarings and sparse line products all use
-//     this one primitive - in the latency regime a cheaper formula on fewer lanes buys nothing.
-//   * the Miller loop of (A, B) is split over two warps: one walks the twist point (the dependent chain of G2
-//     doublings / additions, 3-4 product rounds each) and publishes scaled line coefficients in shared memory, the
-//     other folds them into f as they appear.  The loops against -gamma and -delta read line coefficients PREPARED
-//     at lzkp_vk_load (what ark-groth16's PreparedVerifyingKey holds) and scale them on idle lanes of the previous
-//     product.
+//     recombination runs on 10 and then 6 lanes.  Squarings, cyclotomic squarings and line products all use this one
+//     body (lines as dense operands with zero slots) - in the latency regime a cheaper formula on fewer lanes buys
+//     nothing, and a second body only widens the instruction footprint of a loop a lone warp runs.
+//   * the Miller loop of (A, B) runs on three warps: line_chain walks the twist point (the dependent chain of G2
+//     doublings / additions, 3-4 product rounds each) and publishes scaled line coefficients in shared memory; two
+//     warps fold them into f, each running a share of the loop (miller_f, kMillerSplit).  The loops against -gamma,
+//     -delta (and beta, for the combined check of verify.cu) read line coefficients PREPARED at lzkp_vk_load (what
+//     ark-groth16's PreparedVerifyingKey holds) and scale them on idle lanes of the previous product.
 //   * vk_x = gamma_abc_0 + sum x_i gamma_abc_i comes from fixed-base byte-window tables built at lzkp_vk_load
 //     (lane = (input, byte) pair, then a shuffle tree).
 //   * the r-torsion test of B (one 63-bit ladder, pairing.cuh g2_subgroup_from_xp) runs with the independent products of
 //     every doubling / addition on different lanes, beside the Miller loops and the final exponentiation.
+//   * the final exponentiation's three powers by x are split into a squaring warp and a multiplying warp
+//     (f12_exp_neg_x / f12_exp_helper).
+// Warps talk through counters in shared memory polled with __nanosleep back-off (flag_publish / flag_wait).
 // Same formulas as pairing.cuh (the serial code is the checker: LZKP_COOP_SELFTEST=1 compares both at key load).
 #pragma once
 #include "dev_util.cuh"
