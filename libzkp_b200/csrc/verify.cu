@@ -185,7 +185,7 @@ __device__ __forceinline__ Fr warp_sum_fr(Fr v) {
 //   warp 0: A, rho * A -> shared; upper share of Miller(rho A, B), then its 41 squarings; at the end upper * lower
 //   warp 1: B on the twist; walks the twist point through the upper iterations, then the lower share of the loop
 //   warp 2: C, rho * C; the public-input scan and the scalar sums           warp 3: B in the r-torsion subgroup
-constexpr int kLaneSplit = 41;       // iterations kAteTop .. kLaneSplit on warp 0, kLaneSplit-1 .. 0 and the final lines on warp 1
+constexpr int kLaneSplit = 38;       // iterations kAteTop .. kLaneSplit on warp 0, kLaneSplit-1 .. 0 and the final lines on warp 1
 __global__ void __launch_bounds__(128) k_rlc_prepare(const VkDev *__restrict__ vk, uint32_t n_pub, const uint8_t *__restrict__ proofs,
                                                      const Fr *__restrict__ inputs, const uint32_t *__restrict__ rho, uint32_t n,
                                                      Fq12 *__restrict__ f_out, G1XYZZ *__restrict__ rc_out, Fr *__restrict__ sx_out,
