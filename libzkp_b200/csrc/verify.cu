@@ -453,12 +453,14 @@ __global__ void k_prepare_lines(const VkDev *vk, Fq2 *lines_gamma, Fq2 *lines_de
     pairing_add_step(R, q1, L); put();
     pairing_add_step(R, q2, L); put();
 }
-// tab[((i * 32 + w) * 255 + d - 1)] = d * 256^w * gamma_abc[i + 1]: fixed-base byte windows for vk_x.  Thread = (i, w).
-__global__ void __launch_bounds__(64) k_vk_tables(const G1Affine *__restrict__ gamma_abc, uint32_t n_pub, G1Affine *__restrict__ tab) {
+// tab[((i * 32 + w) * 255 + d - 1)] = d * 256^w * base_i: fixed-base byte windows.  Rows i < n_pub: gamma_abc[i + 1] (vk_x of
+// the latency form); row n_pub: gamma_abc[0], row n_pub + 1: alpha (the combined check's public-input shares).  Thread = (i, w).
+__global__ void __launch_bounds__(64) k_vk_tables(const VkDev *__restrict__ vk, const G1Affine *__restrict__ gamma_abc, uint32_t n_pub,
+                                                  G1Affine *__restrict__ tab) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_pub * coop::kTabWindows) return;
+    if (t >= (n_pub + 2) * coop::kTabWindows) return;
     const uint32_t i = t / coop::kTabWindows, w = t % coop::kTabWindows;
-    G1XYZZ b = G1XYZZ::from_affine(ldg_vec(gamma_abc + 1 + i));
+    G1XYZZ b = G1XYZZ::from_affine(i < n_pub ? ldg_vec(gamma_abc + 1 + i) : i == n_pub ? ldg_vec(gamma_abc) : vk->alpha);
 #pragma unroll 1
     for (uint32_t k = 0; k < 8 * w; k++) b.dbl_cold();
     G1XYZZ acc = G1XYZZ::inf();
@@ -698,17 +700,28 @@ __global__ void __launch_bounds__(128) k_rlc_scalars(const Fr *__restrict__ sx_i
     for (uint32_t b = cta_lo; b < cta_hi; b++) sum = sum + ld_vec(sx_in + (size_t)b * (n_pub + 1) + j);
     st_vec(gS + t, sum);
 }
-// X[g][j] = S[g][j] * gamma_abc[j] for j <= n_pub, and the extra column X[g][n_pub + 1] = S[g][0] * alpha
-__global__ void __launch_bounds__(64) k_rlc_inputs2(const VkDev *__restrict__ vk, const Fr *__restrict__ gS, const G1Affine *__restrict__ gamma_abc,
-                                                    uint32_t n_pub, uint32_t groups, G1XYZZ *__restrict__ gX) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, cols = n_pub + 2;
+// X[g][j] = S[g][j] * gamma_abc[j] for j <= n_pub, and the extra column X[g][n_pub + 1] = S[g][0] * alpha, from the byte-window
+// tables: one warp per (g, j), lane = byte of the scalar, then a shuffle tree.  (As a 254-bit scalar multiplication on one
+// thread per (g, j) this stage was a 1.4 ms chain in EVERY combined-form call, whatever its size.)
+__global__ void __launch_bounds__(128) k_rlc_inputs2(const Fr *__restrict__ gS, const G1Affine *__restrict__ tab, uint32_t n_pub,
+                                                     uint32_t groups, G1XYZZ *__restrict__ gX) {
+    const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, cols = n_pub + 2;
     if (t >= groups * cols) return;
     const uint32_t g = t / cols, j = t % cols;
-    const Fr s = ld_vec(gS + (size_t)g * (n_pub + 1) + (j <= n_pub ? j : 0));
-    const G1Affine base = j <= n_pub ? ldg_vec(gamma_abc + j) : vk->alpha;
-    G1XYZZ r = G1XYZZ::inf();
-    if (!s.is_zero() && !base.is_inf()) r = scalar_mul(G1XYZZ::from_affine(base), s);
-    st_vec(gX + t, r);
+    const uint8_t *sbytes = reinterpret_cast<const uint8_t *>(gS + (size_t)g * (n_pub + 1) + (j <= n_pub ? j : 0));
+    const uint32_t row = j == 0 ? n_pub : j <= n_pub ? j - 1 : n_pub + 1, d = sbytes[lane];
+    G1XYZZ acc = G1XYZZ::inf();
+    if (d) acc = G1XYZZ::from_affine(ldg_vec(tab + ((size_t)row * coop::kTabWindows + lane) * coop::kTabDigits + (d - 1)));
+#pragma unroll 1
+    for (int off = 16; off > 0; off >>= 1) {
+        G1XYZZ o;
+        uint32_t *ow = reinterpret_cast<uint32_t *>(&o);
+        const uint32_t *aw = reinterpret_cast<const uint32_t *>(&acc);
+#pragma unroll
+        for (int k = 0; k < (int)(sizeof(G1XYZZ) / 4); k++) ow[k] = __shfl_down_sync(0xffffffffu, aw[k], off);
+        acc.add_cold(o);
+    }
+    if (lane == 0) st_vec(gX + t, acc);
 }
 
 // LZKP_COOP_SELFTEST=1 at key load: the cooperative Miller loop (both line sources), final exponentiation and subgroup
@@ -839,10 +852,10 @@ static int coop_prepare(VerifyingKeyDev *V) {
     CUDA_TRY(cudaMemset(V->lines_gamma.p, 0, line_bytes)); CUDA_TRY(cudaMemset(V->lines_delta.p, 0, line_bytes));
     CUDA_TRY(cudaMemset(V->lines_beta.p, 0, line_bytes));
     LAUNCH(k_prepare_lines, 1, 32, 0, 0, V->vk.as<VkDev>(), V->lines_gamma.as<Fq2>(), V->lines_delta.as<Fq2>(), V->lines_beta.as<Fq2>());
-    if (V->n_pub) {
-        const uint32_t threads = V->n_pub * coop::kTabWindows;
+    {
+        const uint32_t threads = (V->n_pub + 2) * coop::kTabWindows;
         TRY(V->tab.alloc((size_t)threads * coop::kTabDigits * sizeof(G1Affine)));
-        LAUNCH(k_vk_tables, (threads + 63) / 64, 64, 0, 0, V->gamma_abc.as<G1Affine>(), V->n_pub, V->tab.as<G1Affine>());
+        LAUNCH(k_vk_tables, (threads + 63) / 64, 64, 0, 0, V->vk.as<VkDev>(), V->gamma_abc.as<G1Affine>(), V->n_pub, V->tab.as<G1Affine>());
     }
     CUDA_TRY(cudaDeviceSynchronize());
     if (getenv("LZKP_COOP_SELFTEST")) {
@@ -1029,8 +1042,8 @@ int verify_batch(VerifyingKeyDev *V, size_t n, const uint8_t *proofs, const uint
     static const bool tail_lanes = getenv("LZKP_RLC_TAIL_LANES") != nullptr;      // A/B switch: the lane-per-group tail
     if (V->coop_ok && !tail_lanes) {
         LAUNCH(k_rlc_scalars, (groups * np1 + 127) / 128, 128, 0, 0, V->d_sx.as<Fr>(), (uint32_t)n, (uint32_t)n_pub, groups, V->d_gS.as<Fr>());
-        LAUNCH(k_rlc_inputs2, (groups * (np1 + 1) + 63) / 64, 64, 0, 0, V->vk.as<VkDev>(), V->d_gS.as<Fr>(), V->gamma_abc.as<G1Affine>(),
-               (uint32_t)n_pub, groups, V->d_gX.as<G1XYZZ>());
+        LAUNCH(k_rlc_inputs2, (groups * (np1 + 1) + 3) / 4, 128, 0, 0, V->d_gS.as<Fr>(), V->tab.as<G1Affine>(), (uint32_t)n_pub, groups,
+               V->d_gX.as<G1XYZZ>());
         if (groups <= 2u * (uint32_t)sm_count)
             LAUNCH(k_rlc_tail_coop<2>, groups, 128, sizeof(TailSmem), 0, V->vk.as<VkDev>(), V->lines_gamma.as<Fq2>(), V->lines_delta.as<Fq2>(),
                    V->lines_beta.as<Fq2>(), V->d_f.as<Fq12>(), V->d_rc.as<G1XYZZ>(), V->d_gX.as<G1XYZZ>(), (uint32_t)n, (uint32_t)n_pub,
