@@ -4,7 +4,13 @@
 // :455-495): Proof::deserialize_uncompressed (validating), Groth16::process_vk — recomputed there on EVERY call,
 // here once per key at lzkp_vk_load —, the public-input accumulation and verify_with_processed_vk:
 //     e(A, B) * e(vk_x, -gamma) * e(C, -delta) == e(alpha, beta),   vk_x = gamma_abc[0] + sum_i x_i gamma_abc[i+1].
-// One proof per thread: three Miller loops sharing their squarings, one final exponentiation.
+// Three forms, chosen by the size of the call, with the same decisions (tests/test_gpu_verify.py):
+//   * up to three proofs per SM: one proof per CTA, warps and lanes share the pairing's arithmetic (k_verify_coop, coop.cuh);
+//   * larger calls: random-linear-combination form - per proof ONE Miller loop e(rho A, B), the format / curve / subgroup
+//     checks and rho C (k_rlc_prepare: four role warps per 32 proofs; k_rlc_prepare_seq beyond one resident wave), per group
+//     of 64 one cooperative combined check (k_rlc_scalars, k_rlc_inputs2, k_rlc_tail_coop); a failing group is re-verified
+//     proof by proof;
+//   * one proof per lane (k_verify4): keys without the latency form's tables, no OS entropy, large failing ranges.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
