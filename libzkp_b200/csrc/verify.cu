@@ -968,8 +968,8 @@ int verify_batch(VerifyingKeyDev *V, size_t n, const uint8_t *proofs, const uint
     if (n_pub) CUDA_TRY(cudaMemcpy(d_x.p, inputs, n * n_pub * 32, cudaMemcpyHostToDevice));
     // Calls of up to coop_max proofs are bound by ONE proof's dependent chain: there a proof gets a whole CTA whose warps
     // and lanes share the pairing's arithmetic (coop.cuh): 1 / 64 / 148 proofs in 1.8 / 1.9 / 2.2 ms with one CTA per SM,
-    // 296 / 444 proofs in 3.1 / 5.7 ms with two per SM, against 7.5 ms for the random-linear-combination form at any
-    // count up to ~8000 and 13.4 ms for one proof per lane: three proofs per SM is where the combined form takes over.
+    // 296 / 444 proofs in 2.7 / 5.2 ms with two per SM, against 5.9 ms for the random-linear-combination form at any
+    // count up to ~4000 and 13.4 ms for one proof per lane: three proofs per SM is where the combined form takes over.
     int sm_count = 148;
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, current_device() < 0 ? 0 : current_device());
     const size_t coop_max = getenv("LZKP_VERIFY_COOP_MAX") ? (size_t)atoll(getenv("LZKP_VERIFY_COOP_MAX")) : (size_t)3 * sm_count;
@@ -990,7 +990,7 @@ int verify_batch(VerifyingKeyDev *V, size_t n, const uint8_t *proofs, const uint
     };
     // Above the latency form's range the random-linear-combination form takes over: 2.4x less work per proof (one Miller
     // loop instead of three, one final exponentiation per 64 proofs) and, with the cooperative combined check, a short
-    // tail - 1024 / 4096 proofs in 7.5 / 7.9 ms against 13.4 / 14.0 ms for one proof per lane (k_verify4, which remains
+    // tail - 1024 / 4096 proofs in 5.9 / 6.3 ms against 13.4 / 14.0 ms for one proof per lane (k_verify4, which remains
     // the path for keys without the latency form's tables, for re-verifying large failing ranges and when the OS has no
     // entropy).
     const size_t rlc_min = getenv("LZKP_VERIFY_RLC_MIN") ? (size_t)atoll(getenv("LZKP_VERIFY_RLC_MIN")) : (V->coop_ok ? (size_t)3 * sm_count + 1 : 16384);
