@@ -226,6 +226,75 @@ LZ_COLD XYZZ<F> scalar_mul_u128(const XYZZ<F> &p, const uint32_t (&k)[4]) {
     return scalar_mul_window<F, 4>(p, k);
 }
 
+// k1 * p + k2 * phi(p) for 64-bit k1 = (k[0], k[1]) and k2 = (k[2], k[3]), phi(x, y) = (beta x, y) = [lambda] (x, y):
+// the two signed 4-bit window ladders share their doublings (17 windows: 68 doublings and at most 34 additions, where a
+// 128-bit scalar needs 132 and 33).  Used with RANDOM (k1, k2): the coefficient is k1 + lambda k2 mod r, and
+// (k1, k2) -> k1 + lambda k2 is injective on [0, 2^64)^2 (the GLV lattice of lambda has no non-zero point in that box:
+// its reduced basis, glv_split's A1 / A2 / B2, has entries of 127 bits), so the coefficient still takes 2^128 values.
+static LZ_COLD XYZZ<Fq> scalar_mul_glv64(const XYZZ<Fq> &p, const uint32_t (&k)[4]) {
+    XYZZ<Fq> T[8];
+    T[0] = p;
+    T[1] = p;
+    T[1].dbl_cold();
+#pragma unroll 1
+    for (int i = 2; i < 8; i++) {
+        T[i] = T[i - 1];
+        T[i].add_cold(p);
+    }
+    Fq beta;
+#pragma unroll
+    for (int i = 0; i < 8; i++) beta.l[i] = FqParams::BETA(i);
+    uint32_t carries[2] = {0, 0}, top[2] = {0, 0};
+#pragma unroll 1
+    for (int h = 0; h < 2; h++) {
+        uint32_t c = 0;
+#pragma unroll 1
+        for (int i = 0; i < 16; i++) {
+            const uint32_t v = ((k[2 * h + (i >> 3)] >> ((i & 7) * 4)) & 15u) + c;
+            c = v >= 8u ? 1u : 0u;
+            carries[h] |= c << i;
+        }
+        top[h] = c;
+    }
+    XYZZ<Fq> acc = XYZZ<Fq>::inf();
+#pragma unroll 1
+    for (int i = 16; i >= 0; i--) {
+        acc.dbl_cold(); acc.dbl_cold(); acc.dbl_cold(); acc.dbl_cold();
+#pragma unroll 1
+        for (int h = 0; h < 2; h++) {
+            int d;
+            if (i == 16) d = (int)top[h];
+            else {
+                const uint32_t cin = i ? (carries[h] >> (i - 1)) & 1u : 0u, cout = (carries[h] >> i) & 1u;
+                d = (int)(((k[2 * h + (i >> 3)] >> ((i & 7) * 4)) & 15u) + cin) - (int)(16u * cout);
+            }
+            if (d != 0) {
+                XYZZ<Fq> q = T[(d < 0 ? -d : d) - 1];
+                if (h) q.x = q.x * beta;
+                if (d < 0) q.y = q.y.neg();
+                acc.add_cold(q);
+            }
+        }
+    }
+    return acc;
+}
+// lambda (the eigenvalue of phi on G1: phi(P) = [lambda] P for FqParams::BETA), Montgomery form mod r
+// lambda = 0x30644e72e131a029048b6e193fd84104cc37a73fec2bc5e9b8ca0b2d36636f23 (checked with the big-integer oracle)
+LZ_HD Fr glv_lambda_mont() {
+    const uint32_t v[8] = {0x55fcd653u, 0x0363f299u, 0x5fc1e200u, 0x73e7950bu, 0x576d9d24u, 0xc5fce83eu, 0xa1c3a4d4u, 0x059c805du};
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = v[i];
+    return r;
+}
+// k1 + lambda k2 mod r as a canonical residue
+LZ_HD Fr glv64_coefficient(const uint32_t (&k)[4]) {
+    Fr k1 = Fr::zero(), k2 = Fr::zero();
+    k1.l[0] = k[0]; k1.l[1] = k[1];
+    k2.l[0] = k[2]; k2.l[1] = k[3];
+    return k1 + k2 * glv_lambda_mont();          // (k2)(lambda R) R^-1 = k2 lambda, canonical
+}
+
 using G1Affine = Affine<Fq>;
 using G2Affine = Affine<Fq2>;
 using G1XYZZ = XYZZ<Fq>;

@@ -162,7 +162,8 @@ __global__ void __launch_bounds__(128) k_verify4(const VkDev *__restrict__ vk, c
 }
 
 // ---------------------------------------------------------------- random-linear-combination batching (large batches)
-// With independent random 128-bit rho_p, all proofs of a GROUP of kRlcGroup hold iff (up to 2^-128)
+// With independent random rho_p (128 random bits each, used as rho = k1 + lambda k2 with 64-bit halves: ec.cuh
+// scalar_mul_glv64 / glv64_coefficient - still 2^128 distinct values), all proofs of a GROUP of kRlcGroup hold iff (up to 2^-128)
 //     prod_p e(rho_p A_p, B_p) * e(sum_p rho_p vk_x_p, -gamma) * e(sum_p rho_p C_p, -delta) * e(-(sum_p rho_p) alpha, beta) == 1:
 // one Miller loop per proof instead of three and ONE final exponentiation per group instead of per proof.  Four kernels:
 //   k_rlc_prepare  lane = proof: format / curve / subgroup checks (exactly k_verify4's), f_p = Miller(rho_p A_p, B_p),
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__(128) k_rlc_prepare(const VkDev *__restrict__ v
         G2Affine Q = G2Affine::inf();
         if (live) {
             good = read_g1_checked(pb, P);
-            if (good && !P.is_inf()) P = scalar_mul_u128(G1XYZZ::from_affine(P), k).to_affine();
+            if (good && !P.is_inf()) P = scalar_mul_glv64(G1XYZZ::from_affine(P), k).to_affine();
             st_vec(s_P + lane, P);
             s_goodA[lane] = good ? 1 : 0;
         }
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(128) k_rlc_prepare(const VkDev *__restrict__ v
         if (live) {
             G1Affine C;
             good = read_g1_checked(pb + 192, C);
-            if (good && !C.is_inf()) rc = scalar_mul_u128(G1XYZZ::from_affine(C), k);
+            if (good && !C.is_inf()) rc = scalar_mul_glv64(G1XYZZ::from_affine(C), k);
             const Fr *x = inputs + (size_t)p * n_pub;
 #pragma unroll 1
             for (uint32_t i = 0; i < n_pub; i++) good = fr_is_canonical(ld_vec(x + i)) && good;
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(128) k_rlc_prepare(const VkDev *__restrict__ v
         // sums over this CTA's 32 proofs of rho_p * x_pj, j = 0 .. n_pub (x_p0 = 1), as plain (canonical) residues mod r
         Fr rho_c = Fr::zero(), rho_m = Fr::zero();
         if (good) {
-            rho_c.l[0] = k[0]; rho_c.l[1] = k[1]; rho_c.l[2] = k[2]; rho_c.l[3] = k[3];
+            rho_c = glv64_coefficient(k);
             rho_m = Fr::from_canonical(rho_c);
         }
         Fr *dst = sx_out + (size_t)blockIdx.x * (n_pub + 1);
@@ -320,14 +321,14 @@ __global__ void __launch_bounds__(64) k_rlc_prepare_seq(const VkDev *__restrict_
         if (live) {
             G1Affine C;
             good = read_g1_checked(pb + 192, C) && good;
-            if (good && !C.is_inf()) rc = scalar_mul_u128(G1XYZZ::from_affine(C), k);
+            if (good && !C.is_inf()) rc = scalar_mul_glv64(G1XYZZ::from_affine(C), k);
             st_vec(rc_out + p, good ? rc : G1XYZZ::inf());
         }
     }
     {   // sums over these 32 proofs of rho_p * x_pj, j = 0 .. n_pub (x_p0 = 1), as plain (canonical) residues mod r
         Fr rho_c = Fr::zero(), rho_m = Fr::zero();
         if (good) {
-            rho_c.l[0] = k[0]; rho_c.l[1] = k[1]; rho_c.l[2] = k[2]; rho_c.l[3] = k[3];
+            rho_c = glv64_coefficient(k);
             rho_m = Fr::from_canonical(rho_c);
         }
         Fr *dst = sx_out + (size_t)gw * (n_pub + 1);
@@ -346,7 +347,7 @@ __global__ void __launch_bounds__(64) k_rlc_prepare_seq(const VkDev *__restrict_
         G1Affine P[1] = {A};
         G2Affine Q[1] = {B};
         bool skip[1];
-        if (good && !A.is_inf()) P[0] = scalar_mul_u128(G1XYZZ::from_affine(A), k).to_affine();
+        if (good && !A.is_inf()) P[0] = scalar_mul_glv64(G1XYZZ::from_affine(A), k).to_affine();
         skip[0] = !good || P[0].is_inf() || Q[0].is_inf();
         multi_miller_loop<1>(f, P, Q, skip);
         if (!good) f12_one(f);

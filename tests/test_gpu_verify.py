@@ -156,7 +156,9 @@ def test_rlc_batched_verification_equals_independent_verification(eq_keys, mb_ke
     assert np.array_equal(independent, want)
     monkeypatch.setenv("LZKP_VERIFY_RLC_MIN", "64")
     assert np.array_equal(vk.verify_batch(bad, x), want)                 # groups 0, 1, 3, 4 re-verified; group 2 by the combined check
-    assert vk.verify_batch(proofs, cms).all()                            # all valid: no fallback at all
+    before = engine.kernel_launches()
+    assert vk.verify_batch(proofs, cms).all()                            # all valid: no fallback at all -
+    assert engine.kernel_launches() - before == 4                        # per-proof kernel, scalar sums, input shares, combined check
     assert not vk.verify_batch(proofs, np.roll(cms, 1, axis=0)).any()    # all false
     bad2 = proofs.copy()
     bad2[130:140, 0] ^= 1                                                # only malformed proofs in group 2: excluded, the rest of the group still passes combined
